@@ -1,0 +1,309 @@
+#!/usr/bin/env python
+"""bench.py -- APGD adversarial-training throughput on B200 (BASELINE.json metric / configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+           --master-port P bench.py --gpus N --steps K --warmup W
+
+A "step" is one adversarial training step of ConvNeXt-T-CvSt on one synthetic batch of 128 images per
+GPU (3x224x224, l-inf 4/255, APGD n_iter=2, bf16 autocast): 4 forwards + 2 input-grad backwards inside
+`apgd_train`, one full backward with DDP's NCCL all-reduce, fused AdamW.  Rank 0 prints ONE JSON line.
+
+  value     images/s over all ranks, inputs resident in HBM, K steps between CUDA events, max over ranks
+  e2e       same, but every step starts from pinned HOST buffers (H2D inside the timed region) and ends
+            with a D2H read of the loss
+  roofline  the fused l-inf APGD update kernel (b200at_linf_step): 20 B/element x B x n_fts per launch
+             / mean launch duration, measured live with CUDA events on the launching
+            stream over the timed region; peak = MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline  oracle port of the same step (oracle/train_step_oracle.py), fp32, on this box's host
+            cores, bounded sample, rank 0 at N=1 only
+  --impl reference   times that CPU implementation instead (rank 0 only)
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+METRIC = 'apgd_adv_train_images_per_sec'
+UNIT = 'images/s'
+BATCH_PER_GPU = 128
+RES = 224
+EPS = 4. / 255.
+N_ITER = 2
+ARCH = 'convnext_tiny'
+N_FTS = 3 * RES * RES
+FALLBACK_HBM_GBS = 6650.0   # B200_PROFILING.md fallback, used only if MEASURED_PEAKS.json is absent
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=8)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--batch', type=int, default=BATCH_PER_GPU)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--cpu-seconds', type=float, default=20.0, help='budget of the cpu_baseline sample')
+    return ap.parse_args()
+
+
+def workload_config(n_gpus, batch):
+    return {'workload': f'ConvNeXt-T-CvSt APGD l-inf 4/255 n_iter={N_ITER} adversarial train step, bf16 autocast, '
+                        f'batch {batch}/GPU, 3x{RES}x{RES} (BASELINE.json configs[1])',
+            'arch': ARCH, 'batch_per_gpu': batch, 'global_batch': batch * n_gpus, 'resolution': RES,
+            'norm': 'Linf', 'eps': '4/255', 'n_iter': N_ITER, 'parallelism': f'dp{n_gpus}',
+            'l2_policy': 'inputs_exceed_l2 (per-step working set >> 126 MB; image-sized passes stream 385 MB)'}
+
+
+def synth_batch(batch, seed):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.rand(batch, 3, RES, RES, generator=g)
+    y = torch.randint(0, 1000, (batch,), generator=g)
+    return x, y
+
+
+# ---------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+         'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--id={self.index}', f'--query-gpu={self.Q}',
+                                          '--format=csv,noheader,nounits', '-lms', '200'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except ValueError:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[5:9]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------- CPU arm
+def cpu_step_factory():
+    from oracle import convnext_oracle
+    from oracle.train_step_oracle import OracleTrainStep
+    torch.set_num_threads(os.cpu_count())
+    model = convnext_oracle.build(ARCH, normalize=True, seed=0)
+    return OracleTrainStep(model, 'Linf', EPS, N_ITER)
+
+
+def cpu_baseline(seconds):
+    """Oracle port of the step on the host cores, bounded sample: one warm-up step at batch 4, then as many
+    images as fit in ~`seconds` (batch 8..32), timed with the wall clock."""
+    step = cpu_step_factory()
+    x, y = synth_batch(4, 7)
+    t0 = time.time(); step(x, y); t_warm = time.time() - t0
+    ips_guess = 4 / max(t_warm, 1e-3)
+    batch = int(min(32, max(8, ips_guess * seconds / 2)))
+    x, y = synth_batch(batch, 8)
+    n, t0 = 0, time.time()
+    while True:
+        step(x, y); n += batch
+        if time.time() - t0 > seconds / 2 or n >= 64:
+            break
+    dt = time.time() - t0
+    return {'value': n / dt, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
+            'sample': f'{n} images in steps of {batch} (fp32, oracle/train_step_oracle.py, same model/attack config), '
+                      f'{dt:.1f} s wall after one warm-up step'}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (oracle port; the reference is pure
+    Python and /root/reference does not travel to the GPU box), all host threads, rank 0 only."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    step = cpu_step_factory()
+    total = args.steps + args.warmup
+    x, y = synth_batch(2, 7)
+    t0 = time.time(); step(x, y); t2 = time.time() - t0
+    budget = 150.0                                          # whole run ends within a few minutes
+    batch = int(min(32, max(2, (budget / max(total, 1)) * (2 / max(t2, 1e-3)) * 0.6)))
+    x, y = synth_batch(batch, 8)
+    for _ in range(args.warmup):
+        step(x, y)
+    t0 = time.time()
+    for _ in range(args.steps):
+        step(x, y)
+    dt = time.time() - t0
+    v = batch * args.steps / dt
+    cores = torch.get_num_threads()
+    sample = f'{args.steps} steps of {batch} images (bounded sample of the {BATCH_PER_GPU}/GPU step), fp32, {cores} threads'
+    line = {'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(args.gpus, args.batch),
+            'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
+            'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------- GPU arm
+def run_b200(args):
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device (the product path has no CPU fallback; use --impl reference)')
+    dev = torch.device('cuda', local)
+    torch.cuda.set_device(dev)
+    distributed = world > 1
+    if distributed:
+        dist.init_process_group('nccl', device_id=dev)
+    import revisiting_at_b200  # noqa: F401
+    from revisiting_at_b200 import _abi, convnext
+    from revisiting_at_b200.train_step import AdvTrainStep
+    _abi.lib()                                              # fail loudly if the CUDA library is missing
+    torch.backends.cudnn.benchmark = True                   # main.py:25
+
+    batch = args.batch
+    model = convnext.build(ARCH, normalize=True, seed=0)
+    step = AdvTrainStep(model, 'apgd', 'Linf', EPS, N_ITER, distributed=distributed, device=dev)
+
+    pool = 2
+    host = [synth_batch(batch, 1234 + 17 * rank + i) for i in range(pool)]
+    host = [(x.pin_memory(), y.pin_memory()) for x, y in host]
+    resident = [(x.to(dev), y.to(dev)) for x, y in host]
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if distributed:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    def timed(fn, steps):
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        sync_all()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if distributed:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    def resident_step(i):
+        x, y = resident[i % pool]
+        step(x, y)
+
+    sink = torch.zeros(1, pin_memory=True)
+
+    def e2e_step(i):
+        hx, hy = host[i % pool]
+        x = hx.to(dev, non_blocking=True)
+        y = hy.to(dev, non_blocking=True)
+        loss = step(x, y)
+        sink.copy_(loss.reshape(1), non_blocking=False)     # D2H read of the step's result
+
+    for i in range(max(args.warmup, 3)):
+        resident_step(i)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = _abi.LAUNCHES['count']
+    _abi.TIMING['enabled'] = True
+    _abi.TIMING['events'].clear()
+    ms = timed(resident_step, args.steps)
+    _abi.TIMING['enabled'] = False
+    launches = _abi.LAUNCHES['count'] - launches0
+    k1 = [a.elapsed_time(b) for name, a, b in _abi.TIMING['events'] if name == 'linf_step']
+    _abi.TIMING['events'].clear()
+    for i in range(2):
+        e2e_step(i)
+    ms_e2e = timed(e2e_step, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank != 0:
+        if distributed:
+            dist.destroy_process_group()
+        return
+    imgs = batch * world * args.steps
+    peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(peaks_path):
+        peak, peak_src = json.load(open(peaks_path))['hbm_gbs'], 'MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)'
+    else:
+        peak, peak_src = FALLBACK_HBM_GBS, 'fallback (B200_PROFILING.md)'
+    k1_ms = sum(k1) / len(k1) if k1 else float('nan')
+    # the first move of each call has x_old == x_adv (one stream fewer) but seeds x_best/grad_best/x_best_adv;
+    # all launches are credited with the same 20 B/element figure
+    alg_bytes = 20.0 * batch * N_FTS
+    achieved = alg_bytes / (k1_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, 'profiles', 'k1_linf_step_traffic.json')
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get('dram_bytes_per_launch')
+    line = {
+        'metric': METRIC, 'value': imgs / (ms * 1e-3), 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+        'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic', 'config': workload_config(world, batch),
+        'e2e': {'value': imgs / (ms_e2e * 1e-3), 'unit': UNIT,
+                'h2d_bytes_per_step': batch * N_FTS * 4 + batch * 8, 'd2h_bytes_per_step': 4,
+                'ms_per_step': ms_e2e / args.steps},
+        'gpu_launches': launches,
+        'roofline': {'kernel': 'b200at_linf_step (fused l-inf APGD update)', 'bound': 'hbm', 'achieved': achieved,
+                     'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic,
+                     'algorithmic_bytes_per_launch': alg_bytes, 'launch_ms_mean': k1_ms, 'launches_timed': len(k1),
+                     'peak_source': peak_src, 'frac_of_nominal_8TBps': achieved / 8000.0},
+        'clocks': clocks,
+        'model_engine': 'torch library kernels (cuDNN/cuBLAS) for the network in round 1; attack kernels hand-written',
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        torch.cuda.empty_cache()
+        line['cpu_baseline'] = cpu_baseline(args.cpu_seconds)
+    print(json.dumps(line), flush=True)
+    if distributed:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == '__main__':
+    main()

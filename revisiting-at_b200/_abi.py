@@ -1,0 +1,190 @@
+"""ctypes binding of libb200at.so (C ABI: include/b200at.h).
+
+Passes raw device pointers, sizes and the caller's current CUDA stream; every wrapper checks
+device / dtype / density so that a wrong buffer fails here and not inside a kernel.  The library
+is the product: if it is missing this module raises -- there is no fallback of any kind.
+"""
+import ctypes
+import os
+from ctypes import c_float, c_int, c_int64, c_void_p
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'csrc', 'libb200at.so')
+ABI_VERSION = 1
+
+# state rows (csrc/b200at_math.cuh)
+ST_STEP, ST_LOSS_BEST, ST_LOSS_BEST_LAST, ST_REDUCED_LAST, ST_ACC, ST_FLAGS, ST_LOSS_CUR = range(7)
+ST_TOPK, ST_SP_OLD, ST_SP_BEST, ST_SP_ADV, ST_PRED = 7, 8, 9, 10, 11
+ST_ROWS = 16
+F_IMPROVED, F_WRITE_ADV, F_RESTORE = 1, 2, 4
+NORMS = {'Linf': 0, 'L2': 1, 'L1': 2}
+LOSSES = {'ce': 0, 'dlr': 1}
+_DT = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
+
+_lib = None
+LAUNCHES = {'count': 0}   # kernels launched through this ABI (bench.py reports it as gpu_launches)
+
+
+# optional per-launch device timing (bench.py): CUDA events recorded on the launching stream around
+# each kernel; nothing is synchronised here, the reader calls elapsed_time after its own sync
+TIMING = {'enabled': False, 'events': []}
+
+
+class B200atError(RuntimeError):
+    pass
+
+
+class _Timed:
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if TIMING['enabled']:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.b = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+        return self
+
+    def __exit__(self, *exc):
+        if TIMING['enabled']:
+            self.b.record()
+            TIMING['events'].append((self.name, self.a, self.b))
+        LAUNCHES['count'] += 1
+        return False
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise B200atError(
+                f'{LIB_PATH} is not built; run `python -c "import __graft_entry__ as g; g.build()"` '
+                '(nvcc, sm_100a).  There is no CPU fallback for the attack kernels.')
+        L = ctypes.CDLL(LIB_PATH)
+        L.b200at_abi_version.restype = c_int
+        if L.b200at_abi_version() != ABI_VERSION:
+            raise B200atError(f'ABI mismatch: library {L.b200at_abi_version()} != binding {ABI_VERSION}')
+        _declare(L)
+        _lib = L
+    return _lib
+
+
+def _declare(L):
+    P, F, I, I64 = c_void_p, c_float, c_int, c_int64
+    sig = {
+        'b200at_apgd_init': [P, P, P, I64, I64, F, F, P],
+        'b200at_linf_step': [P, P, P, P, P, P, P, P, P, I64, I64, F, F, P],
+        'b200at_flush_best': [P, P, P, P, I64, I64, P],
+        'b200at_loss_bookkeep': [P, I, P, P, P, P, P, P, I64, I64, I, I, I, I, I, F, F, I64, P],
+        'b200at_fgsm_start': [P, P, P, I64, F, F, I, P],
+        'b200at_fgsm_step': [P, P, P, P, I64, F, F, I, P],
+    }
+    for name, args in sig.items():
+        fn = getattr(L, name)
+        fn.argtypes = args
+        fn.restype = c_int
+    for name in OPTIONAL:
+        if hasattr(L, name):
+            fn = getattr(L, name)
+            fn.argtypes = OPTIONAL[name]
+            fn.restype = c_int
+
+
+OPTIONAL = {}
+
+
+def exported_symbols():
+    """Names include/b200at.h declares; tests check each one resolves in the .so."""
+    import re
+    hdr = os.path.join(os.path.dirname(_HERE), 'include', 'b200at.h')
+    with open(hdr) as f:
+        return sorted(set(re.findall(r'^\s*int\s+(b200at_\w+)\s*\(', f.read(), flags=re.M)))
+
+
+def _check(err, what):
+    if err != 0:
+        raise B200atError(f'{what}: CUDA error {err}')
+
+
+def _stream():
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _dense(t):
+    return t.is_contiguous() or (t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last))
+
+
+def _img(t, like=None, name='tensor'):
+    if not t.is_cuda:
+        raise B200atError(f'{name} must be a CUDA tensor (no CPU path)')
+    if t.dtype != torch.float32 or not _dense(t):
+        raise B200atError(f'{name} must be dense fp32, got {t.dtype} strides {t.stride()}')
+    if like is not None and (t.shape != like.shape or t.stride() != like.stride()):
+        raise B200atError(f'{name}: layout differs from x ({t.shape}/{t.stride()} vs {like.shape}/{like.stride()})')
+    return c_void_p(t.data_ptr())
+
+
+def _p(t):
+    return c_void_p(t.data_ptr()) if t is not None else c_void_p(0)
+
+
+def apgd_init(x, x_adv, state, step0, topk0):
+    B, n = x.shape[0], x[0].numel() if x.shape[0] else 0
+    with _Timed('apgd_init'):
+        _check(lib().b200at_apgd_init(_img(x, name='x'), _img(x_adv, x, 'x_adv'), _p(state), B, n, step0, topk0,
+                                      _stream()), 'apgd_init')
+
+
+def linf_step(x, x_adv, x_old, x_new, grad, x_best, grad_best, x_best_adv, state, eps, a):
+    B, n = x.shape[0], x[0].numel() if x.shape[0] else 0
+    args = (_img(x, name='x'), _img(x_adv, x, 'x_adv'), _img(x_old, x, 'x_old'), _img(x_new, x, 'x_new'),
+            _img(grad, x, 'grad'), _img(x_best, x, 'x_best'), _img(grad_best, x, 'grad_best'),
+            _img(x_best_adv, x, 'x_best_adv'), _p(state), B, n, eps, a, _stream())
+    with _Timed('linf_step'):
+        _check(lib().b200at_linf_step(*args), 'linf_step')
+
+
+def flush_best(x_adv, x_best, x_best_adv, state):
+    B, n = x_adv.shape[0], x_adv[0].numel() if x_adv.shape[0] else 0
+    with _Timed('flush_best'):
+        _check(lib().b200at_flush_best(_img(x_adv, name='x_adv'), _img(x_best, x_adv, 'x_best'),
+                                       _img(x_best_adv, x_adv, 'x_best_adv'), _p(state), B, n, _stream()),
+               'flush_best')
+
+
+def loss_bookkeep(logits, y, dlogits, loss_out, state, loss_steps, it, n_iter, ckpt_k, norm, loss, step_full,
+                  step_min, n_fts):
+    if not logits.is_cuda or logits.dim() != 2 or not logits.is_contiguous() or logits.dtype not in _DT:
+        raise B200atError(f'logits must be a contiguous CUDA [B,C] fp32/bf16/fp16 tensor, got '
+                          f'{tuple(logits.shape)} {logits.dtype}')
+    B, C = logits.shape
+    if y.dtype == torch.int64 and y.dim() == 1:
+        yh, ys = _p(y.contiguous()), c_void_p(0)
+    elif y.dim() == 2 and y.shape == logits.shape:
+        y = y.to(torch.float32).contiguous()
+        yh, ys = c_void_p(0), _p(y)
+    else:
+        raise B200atError(f'target must be int64 [B] or soft [B,C], got {tuple(y.shape)} {y.dtype}')
+    if dlogits is not None and (dlogits.dtype != logits.dtype or dlogits.shape != logits.shape
+                                or not dlogits.is_contiguous()):
+        raise B200atError('dlogits must match logits')
+    with _Timed('loss_bookkeep'):
+        _check(lib().b200at_loss_bookkeep(_p(logits), _DT[logits.dtype], yh, ys, _p(dlogits), _p(loss_out),
+                                          _p(state), _p(loss_steps), B, C, it, n_iter, ckpt_k, NORMS[norm],
+                                          LOSSES[loss], step_full, step_min, n_fts, _stream()), 'loss_bookkeep')
+
+
+def fgsm_start(x, noise, x_adv, eps, noise_level, skip_projection):
+    with _Timed('fgsm_start'):
+        _check(lib().b200at_fgsm_start(_img(x, name='x'), _img(noise, x, 'noise'), _img(x_adv, x, 'x_adv'),
+                                       x.numel(), eps, noise_level, int(bool(skip_projection)), _stream()),
+               'fgsm_start')
+
+
+def fgsm_step(x, x_adv, grad, out, eps, step, skip_projection):
+    with _Timed('fgsm_step'):
+        _check(lib().b200at_fgsm_step(_img(x, name='x'), _img(x_adv, x, 'x_adv'), _img(grad, x, 'grad'),
+                                      _img(out, x, 'out'), x.numel(), eps, step, int(bool(skip_projection)),
+                                      _stream()), 'fgsm_step')

@@ -1,0 +1,191 @@
+"""Device-resident APGD state machine behind the reference's `apgd_train` signature.
+
+Reference: /root/reference/autopgd_train_clean.py:123-371.  Same positional/keyword arguments, same
+return tuple `(x_best, acc, loss_best, x_best_adv)`, same preconditions and error behaviour.
+
+What is different is everything underneath (SURVEY.md §3.2 -> DESIGN.md):
+  * no host synchronisation inside the loop: the three data-dependent host branches of the
+    reference (`nonzero` at :304/:321, `if fl.sum() > 0` at :340) are per-sample flags in a
+    device-resident state block, produced by one loss+bookkeeping kernel per forward and consumed
+    by the next image pass;
+  * one HBM pass per iteration over the image-sized tensors (the ~36 eager launches of
+    :213-226,:304,:321-324,:345-346 collapse into `b200at_linf_step`);
+  * the checkpoint schedule (:153-158,:327-349) is data independent and precomputed on the host.
+
+`run_apgd` is written against a small backend object so the CPU test-suite can drive the same
+host logic through the host-compiled kernel bodies (tests/hostcheck); the product entry point
+`apgd_train` always binds the CUDA library and refuses non-CUDA inputs.
+"""
+from __future__ import annotations
+
+import math
+import time
+
+import torch
+
+from . import _abi
+
+_SUPPORTED_LOSS = ('ce', 'dlr')
+
+
+def checkpoint_schedule(norm: str, n_iter: int):
+    """k at iteration i if i is a checkpoint else 0 (autopgd_train_clean.py:153-161,327-349,364)."""
+    out = [0] * n_iter
+    if norm in ('Linf', 'L2'):
+        k = max(int(0.22 * n_iter), 1)
+        k_min = max(int(0.06 * n_iter), 1)
+        dec = max(int(0.03 * n_iter), 1)
+    else:
+        k = max(int(.04 * n_iter), 1)
+        k_min, dec = k, 0
+    since = 0
+    for i in range(n_iter):
+        since += 1
+        if since == k:
+            out[i], since = k, 0
+            k = max(k - dec, k_min)
+    return out
+
+
+class CudaBackend:
+    """Product backend: hand-written sm_100a kernels through the C ABI."""
+    name = 'cuda'
+
+    def check_input(self, x):
+        if not x.is_cuda:
+            raise _abi.B200atError('apgd_train: x must live on a CUDA device; this build has no CPU path')
+        _abi.lib()
+
+    init = staticmethod(_abi.apgd_init)
+    linf_step = staticmethod(_abi.linf_step)
+    flush_best = staticmethod(_abi.flush_best)
+    loss_bookkeep = staticmethod(_abi.loss_bookkeep)
+
+    def l2_step(self, *a, **k):
+        return _abi.l2_step(*a, **k)
+
+    def l1_step(self, *a, **k):
+        return _abi.l1_step(*a, **k)
+
+
+_CUDA = CudaBackend()
+
+
+def _dense_like_input(x):
+    """One dense layout per call (SURVEY.md §7 'tensor layouts'): keep NCHW-contiguous or
+    channels_last inputs as they are, densify anything else."""
+    if x.is_contiguous() or (x.dim() == 4 and x.is_contiguous(memory_format=torch.channels_last)):
+        return x
+    return x.contiguous()
+
+
+def run_apgd(be, model, x, y, norm, eps, n_iter=10, use_rs=False, loss='ce', verbose=False, mixup=None,
+             is_train=True):
+    assert not model.training                                     # autopgd_train_clean.py:125
+    if use_rs:
+        raise TypeError('exceptions must derive from BaseException')   # `raise NotImplemented` (:137)
+    if loss not in _SUPPORTED_LOSS:
+        if loss in ('softloss', 'dlr-targeted'):
+            # in the reference's table (:113-114) but not drivable through apgd_train's call sites
+            raise TypeError(f'loss {loss!r} cannot be driven through apgd_train')
+        raise KeyError(loss)                                      # criterion_dict[loss] (:149)
+    if norm not in ('Linf', 'L2', 'L1'):
+        raise UnboundLocalError(f"norm {norm!r}: the reference defines no step rule (:153-169)")
+    be.check_input(x)
+    t_total = time.time()
+
+    x = _dense_like_input(x.detach())
+    if x.dtype != torch.float32:
+        raise _abi.B200atError(f'apgd_train: x must be fp32 (got {x.dtype})')
+    B = x.shape[0]
+    n_fts = math.prod(x.shape[1:])
+    dev = x.device
+    alpha = 2. if norm in ('Linf', 'L2') else 1.
+    step_full = alpha * eps                                       # double product, rounded once (:169)
+    step_min = alpha * eps / 10.                                  # l1 adasp_minstep (:166,358)
+    topk0 = (.05 if is_train else .2) if norm == 'L1' else 0.
+    sched = checkpoint_schedule(norm, n_iter)
+    soft = mixup is not None
+    if loss == 'dlr' and (soft or y.dim() != 1):
+        raise _abi.B200atError("loss 'dlr' needs hard labels")
+
+    buf_a, buf_b = torch.empty_like(x), torch.empty_like(x)
+    x_best, x_best_adv, grad_best = torch.empty_like(x), torch.empty_like(x), torch.empty_like(x)
+    grad_buf = None
+    state = torch.empty(_abi.ST_ROWS, B, device=dev, dtype=torch.float32)
+    loss_steps = torch.zeros(max(n_iter, 1), B, device=dev, dtype=torch.float32)
+    scratch = None
+    be.init(x, buf_a, state, step_full, topk0)
+
+    times = {'fp': 0., 'bp': 0.}
+
+    def evaluate(x_cur, it, need_grad):
+        nonlocal grad_buf
+        xin = x_cur.detach()
+        if need_grad:
+            xin.requires_grad_()
+        t0 = time.time()
+        with torch.enable_grad():
+            logits = model(xin)
+        times['fp'] += time.time() - t0
+        lg = logits.detach()
+        if not lg.is_contiguous():
+            lg = lg.contiguous()
+        dl = torch.empty_like(lg) if need_grad else None
+        be.loss_bookkeep(lg, y, dl, None, state, loss_steps, it, n_iter, sched[it] if it >= 0 else 0, norm, loss,
+                         step_full, step_min, n_fts)
+        if not need_grad:
+            return None
+        t0 = time.time()
+        (g,) = torch.autograd.grad(logits, [xin], grad_outputs=dl.view_as(logits))   # input-grad only (:185,:283)
+        times['bp'] += time.time() - t0
+        if g.dtype != torch.float32 or g.shape != x.shape or g.stride() != x.stride():
+            # backward handed back another layout (e.g. channels_last from a cuDNN dgrad): one dense copy
+            if grad_buf is None:
+                grad_buf = torch.empty_like(x)
+            grad_buf.copy_(g)
+            g = grad_buf
+        return g
+
+    grad = evaluate(buf_a, -1, True)
+    cur, old, first = buf_a, buf_a, True
+    for i in range(n_iter):
+        a = 0.75 if i > 0 else 1.0
+        new = buf_b if first else old                             # in place over the previous iterate
+        if norm == 'Linf':
+            be.linf_step(x, cur, old, new, grad, x_best, grad_best, x_best_adv, state, eps, a)
+        elif norm == 'L2':
+            scratch = be.l2_step(x, cur, old, new, grad, x_best, grad_best, x_best_adv, state, eps, a, scratch)
+        else:
+            scratch = be.l1_step(x, cur, new, grad, x_best, grad_best, x_best_adv, state, eps, scratch)
+        old, cur, first = cur, new, False
+        g = evaluate(cur, i, i < n_iter - 1)                      # last backward skipped (:281-283)
+        if g is not None:
+            grad = g
+        if verbose:
+            _report(state, i, norm, n_fts)
+    be.flush_best(cur, x_best, x_best_adv, state)
+
+    acc = state[_abi.ST_ACC].view(torch.int32) != 0
+    loss_best = state[_abi.ST_LOSS_BEST].clone()
+    if verbose:
+        times['total'] = time.time() - t_total
+        print(' '.join(f'{k}={v:.5f} s' for k, v in times.items()))
+    return x_best, acc, loss_best, x_best_adv
+
+
+def _report(state, i, norm, n_fts):
+    """verbose line of autopgd_train_clean.py:306-311 (reads device state => synchronises)."""
+    s = state.cpu()
+    acc = (s[_abi.ST_ACC].view(torch.int32) != 0).float().mean().item()
+    extra = ' - topk: {:.2f}'.format(s[_abi.ST_TOPK].mean().item() * n_fts) if norm == 'L1' else ''
+    print('iteration: {} - best loss: {:.6f} curr loss {:.6f} - robust accuracy: {:.2%} - step size: {:.5f}{}'.format(
+        i, s[_abi.ST_LOSS_BEST].sum().item(), s[_abi.ST_LOSS_CUR].sum().item(), acc,
+        s[_abi.ST_STEP].mean().item(), extra))
+
+
+def apgd_train(model, x, y, norm, eps, n_iter=10, use_rs=False, loss='ce',
+               verbose=False, mixup=None, is_train=True):
+    """Drop-in for the reference `apgd_train` (autopgd_train_clean.py:123-124)."""
+    return run_apgd(_CUDA, model, x, y, norm, eps, n_iter=n_iter, use_rs=use_rs, loss=loss, verbose=verbose,
+                    mixup=mixup, is_train=is_train)

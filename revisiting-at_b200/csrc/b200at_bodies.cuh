@@ -1,0 +1,173 @@
+// Kernel bodies of the image-sized APGD passes, one call per VEC consecutive elements.
+// The sm_100a kernels (b200at_attack.cu) call these from their grid loops; tests/hostcheck
+// compiles the same bodies for the host to check indexing / flag handling against the oracle.
+#pragma once
+#include "b200at_math.cuh"
+
+template <int VEC>
+struct B200atVec {
+  float v[VEC];
+};
+
+#if defined(__CUDA_ARCH__)
+// streaming (evict-first) 16-byte accesses for data that is touched once per pass
+template <int VEC>
+__device__ __forceinline__ B200atVec<VEC> b200at_ld_stream(const float* p) {
+  B200atVec<VEC> r;
+  if constexpr (VEC == 4) {
+    const float4 t = __ldcs(reinterpret_cast<const float4*>(p));
+    r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
+  } else {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) r.v[i] = __ldcs(p + i);
+  }
+  return r;
+}
+template <int VEC>
+__device__ __forceinline__ void b200at_st_stream(float* p, const B200atVec<VEC>& r) {
+  if constexpr (VEC == 4) {
+    __stcs(reinterpret_cast<float4*>(p), make_float4(r.v[0], r.v[1], r.v[2], r.v[3]));
+  } else {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) __stcs(p + i, r.v[i]);
+  }
+}
+// default-policy store: the new iterate is read next by the model's first layer, keep it in L2
+template <int VEC>
+__device__ __forceinline__ void b200at_st_keep(float* p, const B200atVec<VEC>& r) {
+  if constexpr (VEC == 4) {
+    *reinterpret_cast<float4*>(p) = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) p[i] = r.v[i];
+  }
+}
+#else
+template <int VEC>
+B200AT_HD B200atVec<VEC> b200at_ld_stream(const float* p) {
+  B200atVec<VEC> r;
+  for (int i = 0; i < VEC; ++i) r.v[i] = p[i];
+  return r;
+}
+template <int VEC>
+B200AT_HD void b200at_st_stream(float* p, const B200atVec<VEC>& r) {
+  for (int i = 0; i < VEC; ++i) p[i] = r.v[i];
+}
+template <int VEC>
+B200AT_HD void b200at_st_keep(float* p, const B200atVec<VEC>& r) {
+  for (int i = 0; i < VEC; ++i) p[i] = r.v[i];
+}
+#endif
+
+// Image buffers of one attack call, all [B][n] fp32 in the same dense layout.
+struct B200atImages {
+  const float* x;      // clean input (never written)
+  float* x_adv;        // current iterate (rewritten only where a restore is pending)
+  const float* x_old;  // previous iterate   (may alias x_adv on the first move, or x_new)
+  float* x_new;        // next iterate       (may alias x_old: each element is read before it is written)
+  const float* grad;   // dL/dx at x_adv
+  float* x_best;
+  float* grad_best;
+  float* x_best_adv;
+  const float* st;     // per-sample state rows (b200at_math.cuh)
+  int64_t B, n;
+};
+
+// ---- K1: fused l-inf update + pending best/adv/restore image ops (autopgd_train_clean.py:213-226,
+// :304, :321-324, :345-346).  Algorithmic traffic 20 B/element (+4 per pending predicated write).
+template <int VEC>
+B200AT_HD void b200at_linf_body(const B200atImages& p, int64_t vi, float eps, float a, float one_minus_a) {
+  const int64_t e = vi * VEC;
+  const int b = (int)(e / p.n);
+  const int32_t fl = b200at_f2i(p.st[(int64_t)B200AT_ST_FLAGS * p.B + b]);
+  const float step = p.st[(int64_t)B200AT_ST_STEP * p.B + b];
+  const bool improved = fl & B200AT_F_IMPROVED;
+  const bool write_adv = fl & B200AT_F_WRITE_ADV;
+  const bool restore = (fl & B200AT_F_RESTORE) && !improved;  // improved => x_best == x_adv already
+
+  const B200atVec<VEC> x = b200at_ld_stream<VEC>(p.x + e);
+  const B200atVec<VEC> xo = b200at_ld_stream<VEC>(p.x_old + e);
+  B200atVec<VEC> xc, g;
+  if (!restore) {
+    xc = b200at_ld_stream<VEC>(p.x_adv + e);
+    g = b200at_ld_stream<VEC>(p.grad + e);
+    if (write_adv) b200at_st_stream<VEC>(p.x_best_adv + e, xc);
+    if (improved) {
+      b200at_st_stream<VEC>(p.x_best + e, xc);
+      b200at_st_stream<VEC>(p.grad_best + e, g);
+    }
+  } else {
+    if (write_adv) b200at_st_stream<VEC>(p.x_best_adv + e, b200at_ld_stream<VEC>(p.x_adv + e));
+    xc = b200at_ld_stream<VEC>(p.x_best + e);
+    g = b200at_ld_stream<VEC>(p.grad_best + e);
+    b200at_st_stream<VEC>(p.x_adv + e, xc);  // becomes x_old of the next move
+  }
+  B200atVec<VEC> o;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) o.v[i] = b200at_linf_elem(x.v[i], xc.v[i], xo.v[i], g.v[i], step, eps, a, one_minus_a);
+  b200at_st_keep<VEC>(p.x_new + e, o);
+}
+
+// ---- final pass: apply the pending x_best / x_best_adv writes after the last forward ----
+template <int VEC>
+B200AT_HD void b200at_flush_body(const B200atImages& p, int64_t vi) {
+  const int64_t e = vi * VEC;
+  const int b = (int)(e / p.n);
+  const int32_t fl = b200at_f2i(p.st[(int64_t)B200AT_ST_FLAGS * p.B + b]);
+  if (!(fl & (B200AT_F_IMPROVED | B200AT_F_WRITE_ADV))) return;
+  const B200atVec<VEC> xc = b200at_ld_stream<VEC>(p.x_adv + e);
+  if (fl & B200AT_F_WRITE_ADV) b200at_st_stream<VEC>(p.x_best_adv + e, xc);
+  if (fl & B200AT_F_IMPROVED) b200at_st_stream<VEC>(p.x_best + e, xc);
+}
+
+// ---- entry pass: x_adv = clamp(x, 0, 1) (:141); returns nnz(x_adv - x) of this vector (l1 state) ----
+template <int VEC>
+B200AT_HD int b200at_init_body(const float* x, float* x_adv, int64_t vi) {
+  const int64_t e = vi * VEC;
+  const B200atVec<VEC> xi = b200at_ld_stream<VEC>(x + e);
+  B200atVec<VEC> o;
+  int nnz = 0;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    o.v[i] = b200at_clamp01(xi.v[i]);
+    nnz += (B200AT_SUB(o.v[i], xi.v[i]) != 0.0f);
+  }
+  b200at_st_keep<VEC>(x_adv + e, o);
+  return nnz;
+}
+
+// ---- FGSM random start (fgsm_train.py:79-83): x_adv = x + (2t-1)*eps*noise_level [, clamp to [0,1]] ----
+template <int VEC>
+B200AT_HD void b200at_fgsm_start_body(const float* x, const float* noise, float* x_adv, int64_t vi, float eps,
+                                      float noise_level, int skip_projection) {
+  const int64_t e = vi * VEC;
+  const B200atVec<VEC> xi = b200at_ld_stream<VEC>(x + e), t = b200at_ld_stream<VEC>(noise + e);
+  B200atVec<VEC> o;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    const float r = B200AT_MUL(B200AT_MUL(B200AT_SUB(B200AT_MUL(2.0f, t.v[i]), 1.0f), eps), noise_level);
+    const float v = B200AT_ADD(xi.v[i], r);
+    o.v[i] = skip_projection ? v : b200at_clamp01(v);
+  }
+  b200at_st_keep<VEC>(x_adv + e, o);
+}
+
+// ---- FGSM step (fgsm_train.py:93-96): x_adv + alpha*eps*sign(grad), then eps-box around x and [0,1] ----
+template <int VEC>
+B200AT_HD void b200at_fgsm_step_body(const float* x, const float* x_adv, const float* grad, float* out, int64_t vi,
+                                     float eps, float step, int skip_projection) {
+  const int64_t e = vi * VEC;
+  const B200atVec<VEC> xi = b200at_ld_stream<VEC>(x + e), xa = b200at_ld_stream<VEC>(x_adv + e),
+                       g = b200at_ld_stream<VEC>(grad + e);
+  B200atVec<VEC> o;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    float v = B200AT_ADD(xa.v[i], B200AT_MUL(step, b200at_sign(g.v[i])));
+    if (!skip_projection) {
+      const float d = b200at_min(b200at_max(B200AT_SUB(v, xi.v[i]), -eps), eps);
+      v = b200at_clamp01(B200AT_ADD(xi.v[i], d));
+    }
+    o.v[i] = v;
+  }
+  b200at_st_keep<VEC>(out + e, o);
+}

@@ -1,0 +1,147 @@
+// Per-element / per-sample arithmetic of the APGD attack step, shared by the sm_100a kernels
+// (b200at_attack.cu) and by the host-compiled checker in tests/hostcheck/ (test infrastructure:
+// it lets the CPU test-suite run these exact bodies against the oracle without a GPU).
+//
+// Contract (reference autopgd_train_clean.py:213-226): every operation is rounded
+// to fp32 on its own -- no FMA contraction.  Device code uses the __f*_rn intrinsics (never
+// contracted) and the TU is additionally built with -fmad=false; host code is built with
+// -ffp-contract=off.
+#pragma once
+#include <stdint.h>
+#include <math.h>
+#include <string.h>
+
+#if defined(__CUDA_ARCH__)
+#define B200AT_HD __host__ __device__ __forceinline__
+#define B200AT_ADD(a, b) __fadd_rn((a), (b))
+#define B200AT_SUB(a, b) __fsub_rn((a), (b))
+#define B200AT_MUL(a, b) __fmul_rn((a), (b))
+#define B200AT_DIV(a, b) __fdiv_rn((a), (b))
+#elif defined(__CUDACC__)
+#define B200AT_HD __host__ __device__ __forceinline__
+#define B200AT_ADD(a, b) ((a) + (b))
+#define B200AT_SUB(a, b) ((a) - (b))
+#define B200AT_MUL(a, b) ((a) * (b))
+#define B200AT_DIV(a, b) ((a) / (b))
+#else
+#define B200AT_HD static inline
+#define B200AT_ADD(a, b) ((a) + (b))
+#define B200AT_SUB(a, b) ((a) - (b))
+#define B200AT_MUL(a, b) ((a) * (b))
+#define B200AT_DIV(a, b) ((a) / (b))
+#endif
+
+// ---- per-sample state block: float rows [B200AT_ST_ROWS][B]; integer rows are bit-cast int32 ----
+enum {
+  B200AT_ST_STEP = 0,            // step size (autopgd_train_clean.py:169)
+  B200AT_ST_LOSS_BEST = 1,       // :199
+  B200AT_ST_LOSS_BEST_LAST = 2,  // loss_best_last_check :200
+  B200AT_ST_REDUCED_LAST = 3,    // reduced_last_check :201
+  B200AT_ST_ACC = 4,             // int32 0/1, robust-so-far mask :197,296
+  B200AT_ST_FLAGS = 5,           // int32 pending image ops for the next pass (B200AT_F_*)
+  B200AT_ST_LOSS_CUR = 6,        // loss at the current iterate
+  B200AT_ST_TOPK = 7,            // l1: fraction of coordinates moved :163,355
+  B200AT_ST_SP_OLD = 8,          // l1: sparsity at the previous checkpoint :164,359
+  B200AT_ST_SP_BEST = 9,         // int32 l1: nnz(x_best - x)
+  B200AT_ST_SP_ADV = 10,         // int32 l1: nnz(x_adv - x), written by the step kernel
+  B200AT_ST_PRED = 11,           // int32 0/1 prediction correct at the current iterate
+  B200AT_ST_ROWS = 16
+};
+enum {
+  B200AT_F_IMPROVED = 1,   // x_best <- x_adv, grad_best <- grad   (:321-324)
+  B200AT_F_WRITE_ADV = 2,  // x_best_adv <- x_adv                  (:304)
+  B200AT_F_RESTORE = 4     // x_adv <- x_best, grad <- grad_best   (:345-346, :361-362)
+};
+enum { B200AT_NORM_LINF = 0, B200AT_NORM_L2 = 1, B200AT_NORM_L1 = 2 };
+
+B200AT_HD int32_t b200at_f2i(float f) { int32_t i; memcpy(&i, &f, 4); return i; }
+B200AT_HD float b200at_i2f(int32_t i) { float f; memcpy(&f, &i, 4); return f; }
+
+// torch.max / torch.min / clamp semantics: NaN propagates
+B200AT_HD float b200at_max(float a, float b) { return (a != a || b != b) ? (a + b) : (a < b ? b : a); }
+B200AT_HD float b200at_min(float a, float b) { return (a != a || b != b) ? (a + b) : (b < a ? b : a); }
+B200AT_HD float b200at_clamp01(float v) { return b200at_min(b200at_max(v, 0.0f), 1.0f); }
+// torch.sign: 0 for +-0 and NaN
+B200AT_HD float b200at_sign(float g) { return (float)((g > 0.0f) - (g < 0.0f)); }
+
+// l-inf move with momentum (:214-226).  xc = current iterate, xo = previous iterate.
+B200AT_HD float b200at_linf_elem(float x, float xc, float xo, float g, float step, float eps, float a,
+                                 float one_minus_a) {
+  const float lo = B200AT_SUB(x, eps), hi = B200AT_ADD(x, eps);
+  const float g2 = B200AT_SUB(xc, xo);
+  float z = B200AT_ADD(xc, B200AT_MUL(step, b200at_sign(g)));
+  z = b200at_clamp01(b200at_min(b200at_max(z, lo), hi));
+  float w = B200AT_ADD(xc, B200AT_MUL(B200AT_SUB(z, xc), a));
+  w = B200AT_ADD(w, B200AT_MUL(g2, one_minus_a));
+  return b200at_clamp01(b200at_min(b200at_max(w, lo), hi));
+}
+
+// Per-sample bookkeeping after a forward pass (:194-205 for iter < 0, :291-364 otherwise).
+// `loss_steps` is [n_iter][B].  ckpt_k > 0 marks a checkpoint iteration with window k.
+// step_full = float32(alpha*eps), step_min = float32(alpha*eps/10) (l1 only).
+B200AT_HD void b200at_bookkeep_sample(float* st, float* loss_steps, int B, int b, float loss, int pred,
+                                      int iter, int n_iter, int ckpt_k, int norm_kind, float step_full,
+                                      float step_min, float n_fts) {
+  float* step = st + (int64_t)B200AT_ST_STEP * B + b;
+  float* loss_best = st + (int64_t)B200AT_ST_LOSS_BEST * B + b;
+  float* loss_best_last = st + (int64_t)B200AT_ST_LOSS_BEST_LAST * B + b;
+  float* reduced_last = st + (int64_t)B200AT_ST_REDUCED_LAST * B + b;
+  float* acc = st + (int64_t)B200AT_ST_ACC * B + b;
+  float* flags = st + (int64_t)B200AT_ST_FLAGS * B + b;
+  float* sp_best = st + (int64_t)B200AT_ST_SP_BEST * B + b;
+  const float* sp_adv = st + (int64_t)B200AT_ST_SP_ADV * B + b;
+  st[(int64_t)B200AT_ST_LOSS_CUR * B + b] = loss;
+  st[(int64_t)B200AT_ST_PRED * B + b] = b200at_i2f(pred);
+
+  if (iter < 0) {  // first evaluation: everything "improves" so the next pass seeds x_best/grad_best/x_best_adv
+    *acc = b200at_i2f(pred);
+    *loss_best = loss;
+    *loss_best_last = loss;
+    *reduced_last = 1.0f;
+    *sp_best = *sp_adv;
+    *flags = b200at_i2f(B200AT_F_IMPROVED | B200AT_F_WRITE_ADV);
+    return;
+  }
+  int32_t fl = 0;
+  *acc = b200at_i2f(b200at_f2i(*acc) & pred);
+  if (!pred) fl |= B200AT_F_WRITE_ADV;
+  loss_steps[(int64_t)iter * B + b] = loss;
+  if (loss > *loss_best) {  // strict; false for NaN
+    fl |= B200AT_F_IMPROVED;
+    *loss_best = loss;
+    *sp_best = *sp_adv;
+  }
+  if (ckpt_k > 0) {
+    if (norm_kind != B200AT_NORM_L1) {
+      float ups = 0.0f;
+      for (int c = 0; c < ckpt_k; ++c) {  // Python-style negative row wrap (:119)
+        int r1 = (iter - c) % n_iter, r0 = (iter - c - 1) % n_iter;
+        if (r1 < 0) r1 += n_iter;
+        if (r0 < 0) r0 += n_iter;
+        ups += (loss_steps[(int64_t)r1 * B + b] > loss_steps[(int64_t)r0 * B + b]) ? 1.0f : 0.0f;
+      }
+      const float thr = (float)((double)ckpt_k * 0.75);
+      const float osc = (ups <= thr) ? 1.0f : 0.0f;
+      const float stalled = B200AT_MUL(B200AT_SUB(1.0f, *reduced_last), (*loss_best_last >= *loss_best) ? 1.0f : 0.0f);
+      const float f = b200at_max(osc, stalled);
+      *reduced_last = f;
+      *loss_best_last = *loss_best;
+      if (f > 0.0f) {
+        *step = B200AT_DIV(*step, 2.0f);
+        fl |= B200AT_F_RESTORE;
+      }
+    } else {  // l1 sparsity adaptation (:351-364)
+      float* topk = st + (int64_t)B200AT_ST_TOPK * B + b;
+      float* sp_old = st + (int64_t)B200AT_ST_SP_OLD * B + b;
+      const float sp = (float)b200at_f2i(*sp_best);
+      const int red = B200AT_DIV(sp, *sp_old) < 0.95f;
+      *topk = B200AT_DIV(B200AT_DIV(sp, n_fts), 1.5f);
+      float s = red ? step_full : B200AT_DIV(*step, 1.5f);
+      s = b200at_min(b200at_max(s, step_min), step_full);
+      *step = s;
+      *sp_old = sp;
+      if (red) fl |= B200AT_F_RESTORE;
+    }
+  }
+  *flags = b200at_i2f(fl);
+}

@@ -1,0 +1,130 @@
+"""Adversarial train step: the caller side of the attack.
+
+`WrappedModel` mirrors /root/reference/main.py:260-301 (attack inside the forward of the wrapped
+module: eval -> perturb -> train -> forward on element [0] of the attack's return).  `AdvTrainStep`
+restates the body of `ImageNetTrainer.train_loop` (main.py:961-997): autocast forward (incl. attack),
+loss, backward with DDP's bucketed NCCL gradient all-reduce, AdamW step, optional EMA.  Differences
+from the reference, all deliberate: bf16 autocast without GradScaler instead of
+fp16 + GradScaler; EMA kept on the device (the reference's `ModelEmaV2(device='cpu')` forces a
+full-parameter D2H copy every step).
+"""
+from __future__ import annotations
+
+import time
+from functools import partial
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .attack import apgd_train
+from .fgsm import fgsm_train
+
+
+class WrappedModel(nn.Module):
+    """include the generation of the adversarial perturbation in the forward pass (main.py:260-301)."""
+
+    def __init__(self, base_model, perturb, verbose=False):
+        super().__init__()
+        self.base_model = base_model
+        self.perturb = perturb
+        self.perturb_input = False
+        self.verbose = verbose
+
+    def forward(self, x, y=None):
+        if self.perturb_input:
+            assert y is not None
+            self.base_model.eval()                         # attack runs in eval mode (main.py:279)
+            if self.verbose:
+                print('perturb input')
+                t0 = time.time()
+            z = self.perturb(self.base_model, x, y)
+            if self.verbose:
+                print(f'inference time={time.time() - t0:.5f}')
+            self.base_model.train()
+            if isinstance(z, (tuple, list)):
+                z = z[0]                                   # x_best, not x_best_adv
+            return self.base_model(z)
+        if self.verbose:
+            print('clean inference')
+        return self.base_model(x)
+
+    def set_perturb(self, mode):
+        self.perturb_input = mode
+
+
+def make_attack(attack='apgd', norm='Linf', eps=4. / 255., n_iter=2, verbose=False, mixup_fn=None, alpha=1.25,
+                noise_level=1., skip_projection=0):
+    """The wiring of main.py:831-842 (`adv.*` config keys -> functools.partial)."""
+    if attack == 'apgd':
+        return partial(apgd_train, norm=norm, eps=eps, n_iter=n_iter, verbose=verbose, mixup=mixup_fn)
+    if attack == 'fgsm':
+        return partial(fgsm_train, eps=eps, use_rs=True, alpha=alpha, noise_level=noise_level,
+                       skip_projection=skip_projection == 1)
+    if attack == 'none':
+        return None
+    raise ValueError(attack)
+
+
+class DeviceEma:
+    """EMA of the parameters kept on the device: one fused multi-tensor lerp per step
+    (replaces timm ModelEmaV2(decay=0.9999, device='cpu'), main.py:882-887,996-997)."""
+
+    def __init__(self, model, decay=0.9999):
+        self.decay = decay
+        self.params = [p for p in model.parameters()]
+        self.shadow = [p.detach().clone() for p in self.params]
+
+    @torch.no_grad()
+    def update(self):
+        torch._foreach_lerp_(self.shadow, [p.detach() for p in self.params], 1. - self.decay)
+
+
+class AdvTrainStep:
+    """One adversarial training step on one rank (main.py:961-997)."""
+
+    def __init__(self, base_model, attack='apgd', norm='Linf', eps=4. / 255., n_iter=2, lr=1e-3, weight_decay=0.05,
+                 label_smoothing=0., ema=False, distributed=False, device=None, autocast_dtype=torch.bfloat16,
+                 channels_last=True, mixup_fn=None):
+        self.device = device
+        perturb = make_attack(attack, norm, eps, n_iter, mixup_fn=mixup_fn)
+        if channels_last:
+            base_model = base_model.to(memory_format=torch.channels_last)      # misc.use_channel_last (main.py:815-817)
+        model = WrappedModel(base_model, perturb) if perturb is not None else base_model
+        model = model.to(device)
+        self.raw = model
+        self.ema = DeviceEma(model) if ema else None                           # created before the DDP wrap (main.py:884)
+        if distributed:
+            model = nn.parallel.DistributedDataParallel(model, device_ids=[device.index])   # main.py:890
+        self.model = model
+        self.perturb = perturb is not None
+        decay, no_decay = [], []
+        for n, p in self.raw.named_parameters():                               # main.py:395-459 param groups
+            (no_decay if p.ndim <= 1 else decay).append(p)
+        self.optimizer = torch.optim.AdamW(
+            [{'params': decay, 'weight_decay': weight_decay}, {'params': no_decay, 'weight_decay': 0.}],
+            lr=lr, betas=(0.9, 0.95), fused=True if (device is not None and device.type == 'cuda') else False)
+        self.label_smoothing = label_smoothing
+        self.mixup_fn = mixup_fn
+        self.autocast_dtype = autocast_dtype
+
+    def loss(self, output, target):
+        if target.dim() == 2:                                                   # timm SoftTargetCrossEntropy (main.py:461-466)
+            return torch.sum(-target * F.log_softmax(output.float(), dim=-1), dim=-1).mean()
+        return F.cross_entropy(output.float(), target, label_smoothing=self.label_smoothing)
+
+    def __call__(self, images, target):
+        self.model.train()
+        if self.perturb:
+            self.raw.set_perturb(True)
+        if self.mixup_fn is not None:
+            images, target = self.mixup_fn(images, target)
+        self.optimizer.zero_grad(set_to_none=True)
+        with torch.autocast(device_type=images.device.type, dtype=self.autocast_dtype):
+            output = self.model(images, target) if self.perturb else self.model(images)
+            loss = self.loss(output, target)
+        loss.backward()                                                         # DDP all-reduce overlaps here
+        self.optimizer.step()
+        if self.ema is not None:
+            self.ema.update()
+        return loss.detach()

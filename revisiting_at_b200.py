@@ -1,0 +1,15 @@
+"""Import alias: the package directory is `revisiting-at_b200/` (not a Python identifier).
+
+`import revisiting_at_b200` loads that directory as this module's package, so
+`from revisiting_at_b200 import attack` works from the repo root.
+"""
+import importlib.util
+import os
+import sys
+
+_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'revisiting-at_b200')
+_spec = importlib.util.spec_from_file_location(
+    __name__, os.path.join(_dir, '__init__.py'), submodule_search_locations=[_dir])
+_mod = importlib.util.module_from_spec(_spec)
+sys.modules[__name__] = _mod
+_spec.loader.exec_module(_mod)

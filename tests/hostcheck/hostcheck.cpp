@@ -1,0 +1,62 @@
+// TEST INFRASTRUCTURE ONLY: host build of the kernel bodies in revisiting-at_b200/csrc/b200at_bodies.cuh
+// so the CPU test-suite can check indexing, flag protocol and arithmetic against the oracle without a
+// GPU.  The product never loads this library (see revisiting-at_b200/_abi.py: CUDA library or error).
+// Build: g++ -O2 -ffp-contract=off -shared -fPIC (tests/hostcheck/build.py)
+#include "../../revisiting-at_b200/csrc/b200at_bodies.cuh"
+
+template <int VEC>
+static void linf_all(const B200atImages& p, float eps, float a, float oma) {
+  const int64_t nvec = p.B * p.n / VEC;
+  for (int64_t v = 0; v < nvec; ++v) b200at_linf_body<VEC>(p, v, eps, a, oma);
+}
+
+extern "C" {
+
+void hc_init(const float* x, float* x_adv, float* st, int64_t B, int64_t n, float step0, float topk0, int vec) {
+  for (int64_t i = 0; i < (int64_t)B200AT_ST_ROWS * B; ++i) st[i] = 0.f;
+  for (int64_t b = 0; b < B; ++b) {
+    int nnz = 0;
+    if (vec == 4) for (int64_t v = 0; v < n / 4; ++v) nnz += b200at_init_body<4>(x, x_adv, b * (n / 4) + v);
+    else for (int64_t v = 0; v < n; ++v) nnz += b200at_init_body<1>(x, x_adv, b * n + v);
+    st[(int64_t)B200AT_ST_SP_ADV * B + b] = b200at_i2f(nnz);
+    st[(int64_t)B200AT_ST_STEP * B + b] = step0;
+    st[(int64_t)B200AT_ST_TOPK * B + b] = topk0;
+    st[(int64_t)B200AT_ST_SP_OLD * B + b] = (float)n;
+    st[(int64_t)B200AT_ST_REDUCED_LAST * B + b] = 1.0f;
+  }
+}
+
+void hc_linf_step(const float* x, float* x_adv, const float* x_old, float* x_new, const float* grad, float* x_best,
+                  float* grad_best, float* x_best_adv, const float* st, int64_t B, int64_t n, float eps, float a,
+                  int vec) {
+  B200atImages p{x, x_adv, x_old, x_new, grad, x_best, grad_best, x_best_adv, st, B, n};
+  const float oma = (float)(1.0 - (double)a);
+  if (vec == 4) linf_all<4>(p, eps, a, oma); else linf_all<1>(p, eps, a, oma);
+}
+
+void hc_flush(const float* x_adv, float* x_best, float* x_best_adv, const float* st, int64_t B, int64_t n, int vec) {
+  B200atImages p{nullptr, const_cast<float*>(x_adv), nullptr, nullptr, nullptr, x_best, nullptr, x_best_adv, st, B, n};
+  if (vec == 4) for (int64_t v = 0; v < B * n / 4; ++v) b200at_flush_body<4>(p, v);
+  else for (int64_t v = 0; v < B * n; ++v) b200at_flush_body<1>(p, v);
+}
+
+void hc_bookkeep(float* st, float* loss_steps, int64_t B, const float* loss, const int* pred, int iter, int n_iter,
+                 int ckpt_k, int norm_kind, float step_full, float step_min, int64_t n_fts) {
+  for (int64_t b = 0; b < B; ++b)
+    b200at_bookkeep_sample(st, loss_steps, (int)B, (int)b, loss[b], pred[b], iter, n_iter, ckpt_k, norm_kind,
+                           step_full, step_min, (float)n_fts);
+}
+
+void hc_fgsm_start(const float* x, const float* noise, float* x_adv, int64_t total, float eps, float nl, int skip,
+                   int vec) {
+  if (vec == 4) for (int64_t v = 0; v < total / 4; ++v) b200at_fgsm_start_body<4>(x, noise, x_adv, v, eps, nl, skip);
+  else for (int64_t v = 0; v < total; ++v) b200at_fgsm_start_body<1>(x, noise, x_adv, v, eps, nl, skip);
+}
+
+void hc_fgsm_step(const float* x, const float* x_adv, const float* grad, float* out, int64_t total, float eps,
+                  float step, int skip, int vec) {
+  if (vec == 4) for (int64_t v = 0; v < total / 4; ++v) b200at_fgsm_step_body<4>(x, x_adv, grad, out, v, eps, step, skip);
+  else for (int64_t v = 0; v < total; ++v) b200at_fgsm_step_body<1>(x, x_adv, grad, out, v, eps, step, skip);
+}
+
+}  // extern "C"

@@ -1,0 +1,71 @@
+"""CPU: the product's host-side state machine (`attack.run_apgd`) driven through the host-compiled
+kernel bodies reproduces the reference's golden trajectories bit-exactly (l-inf path)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden, golden_names, same
+from oracle.scripted_model import ScriptedModel
+from hostcheck.backend import HostBackend
+import revisiting_at_b200
+from revisiting_at_b200 import attack
+
+
+def _t(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+LINF = [n for n in golden_names('scripted_linf')]
+
+
+@pytest.mark.parametrize('vec', [4, 1])
+@pytest.mark.parametrize('name', LINF)
+def test_linf_host_path_bit_exact(name, vec):
+    g = golden(name)
+    model = ScriptedModel(_t(g['logits']), _t(g['grads']))
+    out = attack.run_apgd(HostBackend(vec), model, _t(g['x']), _t(g['y']), str(g['norm']), float(g['eps']),
+                          n_iter=int(g['n_iter']), loss=str(g['loss']),
+                          mixup=(object() if bool(g['soft']) else None))
+    assert same(torch.stack(model.seen), _t(g['x_calls'])), 'iterate trajectory differs'
+    for got, key in zip(out, ('x_best', 'acc', 'loss_best', 'x_best_adv')):
+        assert same(got, _t(g[key])), key
+
+
+def test_schedule_equals_oracle():
+    from oracle.apgd_oracle import checkpoint_schedule as ref
+    for norm in ('Linf', 'L2', 'L1'):
+        for n in (0, 1, 2, 3, 5, 10, 17, 50, 100):
+            assert attack.checkpoint_schedule(norm, n) == ref(norm, n)
+
+
+def test_product_path_refuses_cpu_tensors():
+    class M:
+        training = False
+    with pytest.raises(RuntimeError):
+        attack.apgd_train(M(), torch.rand(2, 3, 4, 4), torch.zeros(2, dtype=torch.long), 'Linf', 0.1)
+
+
+def test_error_behaviour_matches_reference():
+    class M:
+        training = True
+    x, y = torch.rand(2, 3, 4, 4), torch.zeros(2, dtype=torch.long)
+    with pytest.raises(AssertionError):
+        attack.run_apgd(HostBackend(), M(), x, y, 'Linf', 0.1)
+    M.training = False
+    with pytest.raises(KeyError):
+        attack.run_apgd(HostBackend(), M(), x, y, 'Linf', 0.1, loss='nope')
+    with pytest.raises(TypeError):
+        attack.run_apgd(HostBackend(), M(), x, y, 'Linf', 0.1, use_rs=True)
+
+
+@pytest.mark.parametrize('vec', [4, 1])
+def test_fgsm_host_path_bit_exact(vec):
+    from oracle.small_cnn import from_fixture
+    from revisiting_at_b200 import fgsm
+    g = golden('fgsm_cnn')
+    model = from_fixture(g)
+    x, y, eps = _t(g['x']), _t(g['y']), float(g['eps'])
+    for tag, kw in (('plain', dict(use_rs=False)), ('rs', dict(use_rs=True, alpha=1.25, noise_level=1.)),
+                    ('rs_skip', dict(use_rs=True, alpha=1.0, noise_level=0.5, skip_projection=True))):
+        out = fgsm.run_fgsm(HostBackend(vec), model, x, y, eps, noise=_t(g['noise_' + tag]), **kw)
+        assert same(out, _t(g['out_' + tag])), tag
