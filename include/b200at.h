@@ -61,6 +61,22 @@ int b200at_linf_step(const float* x, float* x_adv, const float* x_old, float* x_
                      float* x_best, float* grad_best, float* x_best_adv, const float* state, int64_t B, int64_t n,
                      float eps, float a, void* stream);
 
+/* autopgd_train_clean.py:228-237 (+ the same pending image ops as b200at_linf_step): l2 move with
+ * momentum; the three dependent per-sample norms (||grad||, ||z-x||, ||w-x||) are deterministic
+ * two-level sums.  scratch: >= B200AT_L2_SCRATCH_FLOATS(B) floats, contents irrelevant on entry. */
+#define B200AT_L2_SCRATCH_FLOATS(B) (3 * 32 * (B))
+int b200at_l2_step(const float* x, float* x_adv, const float* x_old, float* x_new, const float* grad,
+                   float* x_best, float* grad_best, float* x_best_adv, const float* state, float* scratch,
+                   int64_t B, int64_t n, float eps, float a, void* stream);
+
+/* autopgd_train_clean.py:239-250 with L1_projection (:24-91) (+ the pending image ops): sparse sign step on
+ * the top-k |grad| coordinates (exact order statistic by radix select), then projection of x+delta onto the
+ * l1 ball of radius eps intersected with [0,1]^n.  No momentum, x_old is not read; x_new must NOT alias
+ * x_adv.  Writes nnz(x_new - x) to state[SP_ADV].  scratch: >= B200AT_L1_SCRATCH_WORDS(B) 4-byte words. */
+#define B200AT_L1_SCRATCH_WORDS(B) ((3 * 2048 + 16 + 32 * 2 + 32 * 32) * (B))
+int b200at_l1_step(const float* x, float* x_adv, float* x_new, const float* grad, float* x_best, float* grad_best,
+                   float* x_best_adv, float* state, void* scratch, int64_t B, int64_t n, float eps, void* stream);
+
 /* image side of autopgd_train_clean.py:304,:322 after the LAST forward: pending x_best / x_best_adv writes. */
 int b200at_flush_best(const float* x_adv, float* x_best, float* x_best_adv, const float* state, int64_t B,
                       int64_t n, void* stream);

@@ -25,12 +25,14 @@ OUT = os.path.join(ROOT, 'tests', 'golden')
 torch.set_num_threads(4)
 
 
-def scripted_inputs(seed, B, shape, C, n_calls, soft):
+def scripted_inputs(seed, B, shape, C, n_calls, soft, in_box=False):
     g = torch.Generator().manual_seed(seed)
     x = torch.rand(B, *shape, generator=g)
     flat = x.view(-1)
-    # edge pixels: exact 0/1, just outside the box (clamped on entry), denormal-ish
-    flat[0:6] = torch.tensor([0., 1., -0.25, 1.5, 1e-9, 1. - 1e-7])
+    # edge pixels: exact 0/1, just outside the box (clamped on entry), denormal-ish.  The l1 fixtures keep
+    # x inside [0,1]: L1_projection (:24-91) assumes an in-box centre, and its sparsity counts
+    # (`L0_norm(x_best - x)`, :353) flip on one-ulp ties that out-of-box / 1e-9 pixels provoke.
+    flat[0:6] = torch.tensor([0., 1., 0., 1., 0.5, 0.25]) if in_box else torch.tensor([0., 1., -0.25, 1.5, 1e-9, 1. - 1e-7])
     y = torch.randint(0, C, (B,), generator=g)
     logits = torch.randn(n_calls, B, C, generator=g) * 2.
     # true-class logit boosted on a random half of the calls so that predictions flip both ways
@@ -57,7 +59,7 @@ def scripted_inputs(seed, B, shape, C, n_calls, soft):
 
 def run_scripted(ref, name, norm, eps, n_iter, seed, soft=False, loss='ce', B=8, shape=(3, 12, 12), C=10,
                  is_train=True):
-    x, y, logits, grads = scripted_inputs(seed, B, shape, C, n_iter + 1, soft)
+    x, y, logits, grads = scripted_inputs(seed, B, shape, C, n_iter + 1, soft, in_box=(norm == 'L1'))
     model = ScriptedModel(logits, grads)
     out = ref.apgd_train(model, x, y, norm=norm, eps=eps, n_iter=n_iter, loss=loss,
                          mixup=(object() if soft else None), is_train=is_train)

@@ -77,6 +77,8 @@ def _declare(L):
         'b200at_apgd_init': [P, P, P, I64, I64, F, F, P],
         'b200at_linf_step': [P, P, P, P, P, P, P, P, P, I64, I64, F, F, P],
         'b200at_flush_best': [P, P, P, P, I64, I64, P],
+        'b200at_l2_step': [P, P, P, P, P, P, P, P, P, P, I64, I64, F, F, P],
+        'b200at_l1_step': [P, P, P, P, P, P, P, P, P, I64, I64, F, P],
         'b200at_loss_bookkeep': [P, I, P, P, P, P, P, P, I64, I64, I, I, I, I, I, F, F, I64, P],
         'b200at_fgsm_start': [P, P, P, I64, F, F, I, P],
         'b200at_fgsm_step': [P, P, P, P, I64, F, F, I, P],
@@ -188,3 +190,34 @@ def fgsm_step(x, x_adv, grad, out, eps, step, skip_projection):
         _check(lib().b200at_fgsm_step(_img(x, name='x'), _img(x_adv, x, 'x_adv'), _img(grad, x, 'grad'),
                                       _img(out, x, 'out'), x.numel(), eps, step, int(bool(skip_projection)),
                                       _stream()), 'fgsm_step')
+
+
+def l2_step(x, x_adv, x_old, x_new, grad, x_best, grad_best, x_best_adv, state, eps, a, scratch=None):
+    B, n = x.shape[0], x[0].numel() if x.shape[0] else 0
+    if scratch is None:
+        scratch = torch.empty(3 * 32 * max(B, 1), device=x.device, dtype=torch.float32)
+    args = (_img(x, name='x'), _img(x_adv, x, 'x_adv'), _img(x_old, x, 'x_old'), _img(x_new, x, 'x_new'),
+            _img(grad, x, 'grad'), _img(x_best, x, 'x_best'), _img(grad_best, x, 'grad_best'),
+            _img(x_best_adv, x, 'x_best_adv'), _p(state), _p(scratch), B, n, eps, a, _stream())
+    with _Timed('l2_step'):
+        _check(lib().b200at_l2_step(*args), 'l2_step')
+    LAUNCHES['count'] += 3
+    return scratch
+
+
+L1_LAUNCHES = 3 * 2 + 2 + 2 * 7 + 1
+
+
+def l1_step(x, x_adv, x_new, grad, x_best, grad_best, x_best_adv, state, eps, scratch=None):
+    B, n = x.shape[0], x[0].numel() if x.shape[0] else 0
+    if x_new.data_ptr() == x_adv.data_ptr():
+        raise B200atError('l1_step: x_new must not alias x_adv')
+    if scratch is None:
+        scratch = torch.empty((3 * 2048 + 16 + 64 + 1024) * max(B, 1), device=x.device, dtype=torch.int32)
+    args = (_img(x, name='x'), _img(x_adv, x, 'x_adv'), _img(x_new, x, 'x_new'), _img(grad, x, 'grad'),
+            _img(x_best, x, 'x_best'), _img(grad_best, x, 'grad_best'), _img(x_best_adv, x, 'x_best_adv'),
+            _p(state), _p(scratch), B, n, eps, _stream())
+    with _Timed('l1_step'):
+        _check(lib().b200at_l1_step(*args), 'l1_step')
+    LAUNCHES['count'] += L1_LAUNCHES - 1
+    return scratch

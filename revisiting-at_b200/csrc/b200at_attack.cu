@@ -56,6 +56,377 @@ __global__ void __launch_bounds__(kThreads) fgsm_step_kernel(const float* __rest
   if (vi < nvec) b200at_fgsm_step_body<VEC>(x, x_adv, grad, out, vi, eps, step, skip);
 }
 
+// ------------------------------------------------------------------------------------------------
+// K2: l2 update.  grid = (kChunks, B): a CTA reduces one contiguous chunk of one sample, so the three
+// dependent per-sample norms are two-level, fixed-order (deterministic) sums: thread -> warp -> CTA
+// partial in scratch[phase][b][chunk]; the next phase adds the kChunks partials with a warp butterfly.
+constexpr int kChunks = 32;
+
+__device__ __forceinline__ float cta_sum(float v, float* smem) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) smem[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.0f;
+  if (threadIdx.x < 32) {
+    t = threadIdx.x < (kThreads / 32) ? smem[threadIdx.x] : 0.0f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  }
+  __syncthreads();
+  return t;  // valid in warp 0
+}
+
+// sum of the kChunks partials of `row` (fixed butterfly order => same value in every CTA of the sample)
+__device__ __forceinline__ float chunk_total(const float* row) {
+  float t = row[threadIdx.x & 31];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  return t;
+}
+
+template <int PHASE, int VEC>
+__global__ void __launch_bounds__(kThreads) l2_phase_kernel(B200atImages p, float* __restrict__ scratch, float eps,
+                                                             float a, float one_minus_a) {
+  __shared__ float red[kThreads / 32];
+  const int b = blockIdx.y, c = blockIdx.x;
+  const int64_t nvec_row = p.n / VEC;
+  const int64_t per = (nvec_row + kChunks - 1) / kChunks;
+  const int64_t v0 = c * per, v1 = (v0 + per < nvec_row) ? v0 + per : nvec_row;
+  float sums[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int ph = 0; ph < PHASE; ++ph) sums[ph] = chunk_total(scratch + ((int64_t)ph * p.B + b) * kChunks);
+  float acc = 0.0f;
+  for (int64_t v = v0 + threadIdx.x; v < v1; v += kThreads)
+    acc += b200at_l2_body<PHASE, VEC>(p, (int64_t)b * nvec_row + v, eps, a, one_minus_a, sums);
+  if (PHASE < 3) {
+    const float t = cta_sum(acc, red);
+    if (threadIdx.x == 0) scratch[((int64_t)PHASE * p.B + b) * kChunks + c] = t;
+  }
+}
+
+template <int VEC>
+int launch_l2(const B200atImages& p, float* scratch, float eps, float a, float oma, cudaStream_t s) {
+  dim3 grid(kChunks, (unsigned)p.B);
+  l2_phase_kernel<0, VEC><<<grid, kThreads, 0, s>>>(p, scratch, eps, a, oma);
+  l2_phase_kernel<1, VEC><<<grid, kThreads, 0, s>>>(p, scratch, eps, a, oma);
+  l2_phase_kernel<2, VEC><<<grid, kThreads, 0, s>>>(p, scratch, eps, a, oma);
+  l2_phase_kernel<3, VEC><<<grid, kThreads, 0, s>>>(p, scratch, eps, a, oma);
+  return (int)cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3 + K4: l1 update.  Per sample: exact k-th order statistic of |grad| by a 3-level radix select
+// (11+11+9 bits, shared-memory histograms merged with integer atomics => deterministic), then the
+// l1-ball ∩ box projection by sectioning the bit pattern of the water level (7 passes x 31 candidates),
+// then the final write.  grid = (kChunks, B) for the image passes; tiny per-sample kernels in between.
+// Scratch words per sample: see B200AT_L1_SCRATCH_WORDS in include/b200at.h.
+constexpr int kHistBins = 2048;
+constexpr int kMetaWords = 16;
+enum { M_PREFIX = 0, M_RANK = 1, M_COUNT_LT = 2, M_NAN = 3, M_ZERO = 4, M_THR = 5, M_NNZ = 6, M_C = 7, M_NEED = 8,
+       M_ALPHA = 9 };
+
+struct L1Scratch {
+  int* hist;      // [3][B][kHistBins]
+  int* meta;      // [B][kMetaWords]
+  float* sums;    // [B][kChunks][2]
+  float* sect;    // [B][kChunks][32]
+};
+__host__ __device__ inline L1Scratch l1_scratch(void* base, int64_t B) {
+  L1Scratch s;
+  s.hist = reinterpret_cast<int*>(base);
+  s.meta = s.hist + 3 * B * kHistBins;
+  s.sums = reinterpret_cast<float*>(s.meta + B * kMetaWords);
+  s.sect = s.sums + B * kChunks * 2;
+  return s;
+}
+
+struct L1Sel {  // per-sample selection of the current iterate / gradient (pending restore)
+  const float* xc; const float* g; bool improved, write_adv, restore; float step;
+};
+__device__ __forceinline__ L1Sel l1_select(const B200atImages& p, int b) {
+  const int32_t fl = b200at_f2i(p.st[(int64_t)B200AT_ST_FLAGS * p.B + b]);
+  L1Sel s;
+  s.improved = fl & B200AT_F_IMPROVED;
+  s.write_adv = fl & B200AT_F_WRITE_ADV;
+  s.restore = (fl & B200AT_F_RESTORE) && !s.improved;
+  s.xc = s.restore ? p.x_best : p.x_adv;
+  s.g = s.restore ? p.grad_best : p.grad;
+  s.step = p.st[(int64_t)B200AT_ST_STEP * p.B + b];
+  return s;
+}
+
+template <int LEVEL, int VEC>
+__global__ void __launch_bounds__(kThreads) l1_hist_kernel(B200atImages p, void* scratch) {
+  __shared__ int h[kHistBins];
+  const int b = blockIdx.y, c = blockIdx.x;
+  const L1Scratch S = l1_scratch(scratch, p.B);
+  const L1Sel sel = l1_select(p, b);
+  for (int i = threadIdx.x; i < kHistBins; i += kThreads) h[i] = 0;
+  __syncthreads();
+  const uint32_t prefix = (uint32_t)S.meta[b * kMetaWords + M_PREFIX];
+  const int64_t nvec_row = p.n / VEC;
+  const int64_t per = (nvec_row + kChunks - 1) / kChunks;
+  const int64_t v0 = c * per, v1 = (v0 + per < nvec_row) ? v0 + per : nvec_row;
+  int nan_cnt = 0, zero_cnt = 0;
+  for (int64_t v = v0 + threadIdx.x; v < v1; v += kThreads) {
+    const B200atVec<VEC> g = b200at_ld_stream<VEC>(sel.g + ((int64_t)b * nvec_row + v) * VEC);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      const uint32_t key = b200at_l1_key(g.v[i]);
+      if (LEVEL == 0) {
+        atomicAdd(&h[key >> 20], 1);
+        nan_cnt += key > 0x7f800000u;
+        zero_cnt += key == 0u;
+      } else if (LEVEL == 1) {
+        if ((key >> 20) == prefix) atomicAdd(&h[(key >> 9) & 0x7ff], 1);
+      } else {
+        if ((key >> 9) == prefix) atomicAdd(&h[key & 0x1ff], 1);
+      }
+    }
+  }
+  __syncthreads();
+  int* gh = S.hist + ((int64_t)LEVEL * p.B + b) * kHistBins;
+  for (int i = threadIdx.x; i < kHistBins; i += kThreads)
+    if (h[i]) atomicAdd(&gh[i], h[i]);
+  if (LEVEL == 0) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      nan_cnt += __shfl_xor_sync(0xffffffffu, nan_cnt, o);
+      zero_cnt += __shfl_xor_sync(0xffffffffu, zero_cnt, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      if (nan_cnt) atomicAdd(&S.meta[b * kMetaWords + M_NAN], nan_cnt);
+      if (zero_cnt) atomicAdd(&S.meta[b * kMetaWords + M_ZERO], zero_cnt);
+    }
+  }
+}
+
+// one CTA per sample: locate the bin holding the wanted rank; after the last level derive thr and nnz
+template <int LEVEL>
+__global__ void __launch_bounds__(kThreads) l1_scan_kernel(const float* __restrict__ st, void* scratch, int64_t B,
+                                                            int64_t n) {
+  __shared__ int warp_tot[kThreads / 32];
+  __shared__ int found_bin, found_excl;
+  const int b = blockIdx.x;
+  const L1Scratch S = l1_scratch(scratch, B);
+  int* meta = S.meta + b * kMetaWords;
+  const int* gh = S.hist + ((int64_t)LEVEL * B + b) * kHistBins;
+  int rank;
+  if (LEVEL == 0) rank = (int)b200at_l1_rank(st[(int64_t)B200AT_ST_TOPK * B + b], n);
+  else rank = meta[M_RANK];
+  constexpr int per = kHistBins / kThreads;  // 8 consecutive bins per thread
+  int loc[per], tot = 0;
+#pragma unroll
+  for (int i = 0; i < per; ++i) { loc[i] = gh[threadIdx.x * per + i]; tot += loc[i]; }
+  int incl = tot;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if ((threadIdx.x & 31) >= o) incl += t;
+  }
+  if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = incl;
+  if (threadIdx.x == 0) found_bin = -1;
+  __syncthreads();
+  int base = 0;
+  for (int w = 0; w < (threadIdx.x >> 5); ++w) base += warp_tot[w];
+  int excl = base + incl - tot;
+  if (rank >= excl && rank < excl + tot) {
+#pragma unroll
+    for (int i = 0; i < per; ++i) {
+      if (rank < excl + loc[i]) { found_bin = threadIdx.x * per + i; found_excl = excl; break; }
+      excl += loc[i];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int bin = found_bin < 0 ? 0 : found_bin;
+    const int ex = found_bin < 0 ? 0 : found_excl;
+    const uint32_t prev = LEVEL == 0 ? 0u : (uint32_t)meta[M_PREFIX];
+    const uint32_t prefix = LEVEL == 0 ? (uint32_t)bin : (LEVEL == 1 ? ((prev << 11) | bin) : ((prev << 9) | bin));
+    meta[M_PREFIX] = (int)prefix;
+    meta[M_RANK] = rank - ex;
+    meta[M_COUNT_LT] = (LEVEL == 0 ? 0 : meta[M_COUNT_LT]) + ex;
+    if (LEVEL == 2) {
+      const float thr = b200at_i2f((int32_t)prefix);
+      float nnz = 0.0f;
+      if (prefix <= 0x7f800000u)
+        nnz = (float)((int)n - meta[M_COUNT_LT] - meta[M_NAN] - (prefix == 0u ? meta[M_ZERO] : 0));
+      meta[M_THR] = b200at_f2i(thr);
+      meta[M_NNZ] = b200at_f2i(nnz);
+    }
+  }
+}
+
+// sum|y| and sum(a) partials
+template <int VEC>
+__global__ void __launch_bounds__(kThreads) l1_sums_kernel(B200atImages p, void* scratch) {
+  __shared__ float red[kThreads / 32];
+  const int b = blockIdx.y, c = blockIdx.x;
+  const L1Scratch S = l1_scratch(scratch, p.B);
+  const L1Sel sel = l1_select(p, b);
+  const float thr = b200at_i2f(S.meta[b * kMetaWords + M_THR]), nnz = b200at_i2f(S.meta[b * kMetaWords + M_NNZ]);
+  const int64_t nvec_row = p.n / VEC;
+  const int64_t per = (nvec_row + kChunks - 1) / kChunks;
+  const int64_t v0 = c * per, v1 = (v0 + per < nvec_row) ? v0 + per : nvec_row;
+  float sb = 0.0f, sa = 0.0f;
+  for (int64_t v = v0 + threadIdx.x; v < v1; v += kThreads) {
+    const int64_t e = ((int64_t)b * nvec_row + v) * VEC;
+    const B200atVec<VEC> x = b200at_ld_stream<VEC>(p.x + e), xc = b200at_ld_stream<VEC>(sel.xc + e),
+                         g = b200at_ld_stream<VEC>(sel.g + e);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      const float y = b200at_l1_y(x.v[i], xc.v[i], g.v[i], sel.step, thr, nnz);
+      sb += fabsf(y);
+      sa -= b200at_l1_u(x.v[i], y);
+    }
+  }
+  const float tb = cta_sum(sb, red);
+  const float ta = cta_sum(sa, red);
+  if (threadIdx.x == 0) {
+    S.sums[((int64_t)b * kChunks + c) * 2 + 0] = tb;
+    S.sums[((int64_t)b * kChunks + c) * 2 + 1] = ta;
+  }
+}
+
+// per sample: c = eps - sum|y|, need = (sum(a) + c < 0)  (:49-52);  one warp per sample
+__global__ void l1_need_kernel(void* scratch, int64_t B, float eps) {
+  const int b = blockIdx.x;
+  const L1Scratch S = l1_scratch(scratch, B);
+  float tb = S.sums[((int64_t)b * kChunks + threadIdx.x) * 2 + 0];
+  float ta = S.sums[((int64_t)b * kChunks + threadIdx.x) * 2 + 1];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    tb += __shfl_xor_sync(0xffffffffu, tb, o);
+    ta += __shfl_xor_sync(0xffffffffu, ta, o);
+  }
+  if (threadIdx.x == 0) {
+    const float c = eps - tb;
+    S.meta[b * kMetaWords + M_C] = b200at_f2i(c);
+    S.meta[b * kMetaWords + M_NEED] = (ta + c < 0.0f) ? 1 : 0;
+    S.meta[b * kMetaWords + M_ALPHA] = 0;
+  }
+}
+
+// g(alpha_k) = sum_i clamp(alpha_k, a_i, b_i) for the 31 candidates of this pass
+template <int VEC>
+__global__ void __launch_bounds__(kThreads) l1_section_kernel(B200atImages p, void* scratch, int pass) {
+  __shared__ float red[kThreads / 32];
+  const int b = blockIdx.y, c = blockIdx.x;
+  const L1Scratch S = l1_scratch(scratch, p.B);
+  if (!S.meta[b * kMetaWords + M_NEED]) return;
+  const L1Sel sel = l1_select(p, b);
+  const float thr = b200at_i2f(S.meta[b * kMetaWords + M_THR]), nnz = b200at_i2f(S.meta[b * kMetaWords + M_NNZ]);
+  const uint32_t prefix = (uint32_t)S.meta[b * kMetaWords + M_ALPHA];
+  const int ncand = b200at_l1_ncand(pass);
+  float cand[31], acc[31];
+#pragma unroll
+  for (int k = 0; k < 31; ++k) { cand[k] = b200at_l1_cand(prefix, k + 1, pass); acc[k] = 0.0f; }
+  const int64_t nvec_row = p.n / VEC;
+  const int64_t per = (nvec_row + kChunks - 1) / kChunks;
+  const int64_t v0 = c * per, v1 = (v0 + per < nvec_row) ? v0 + per : nvec_row;
+  for (int64_t v = v0 + threadIdx.x; v < v1; v += kThreads) {
+    const int64_t e = ((int64_t)b * nvec_row + v) * VEC;
+    const B200atVec<VEC> x = b200at_ld_stream<VEC>(p.x + e), xc = b200at_ld_stream<VEC>(sel.xc + e),
+                         g = b200at_ld_stream<VEC>(sel.g + e);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      const float y = b200at_l1_y(x.v[i], xc.v[i], g.v[i], sel.step, thr, nnz);
+      const float a = -b200at_l1_u(x.v[i], y), bb = fabsf(y);
+#pragma unroll
+      for (int k = 0; k < 31; ++k) acc[k] += b200at_l1_level(cand[k], a, bb);
+    }
+  }
+  float* out = S.sect + ((int64_t)b * kChunks + c) * 32;
+#pragma unroll
+  for (int k = 0; k < 31; ++k) {
+    if (k < ncand) {
+      const float t = cta_sum(acc[k], red);
+      if (threadIdx.x == 0) out[k] = t;
+    }
+  }
+}
+
+// per sample (one warp, lane k = candidate k+1): keep the candidates below the water level (:71-88)
+__global__ void l1_decide_kernel(void* scratch, int64_t B, int pass) {
+  const int b = blockIdx.x, k = threadIdx.x;
+  const L1Scratch S = l1_scratch(scratch, B);
+  if (!S.meta[b * kMetaWords + M_NEED]) return;
+  const int ncand = b200at_l1_ncand(pass);
+  float gk = 0.0f;
+  if (k < ncand)
+    for (int c = 0; c < kChunks; ++c) gk += S.sect[((int64_t)b * kChunks + c) * 32 + k];
+  const float cc = b200at_i2f(S.meta[b * kMetaWords + M_C]);
+  const bool below = (k < ncand) && (gk + cc < 0.0f);
+  const unsigned m = __ballot_sync(0xffffffffu, below);
+  const int kstar = __ffs(~m) - 1;  // number of leading candidates still below the level
+  if (k == 0) S.meta[b * kMetaWords + M_ALPHA] |= (int)((uint32_t)kstar << b200at_l1_shift(pass));
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(kThreads) l1_final_kernel(B200atImages p, void* scratch, float* st_rw) {
+  const int b = blockIdx.y, c = blockIdx.x;
+  const L1Scratch S = l1_scratch(scratch, p.B);
+  const L1Sel sel = l1_select(p, b);
+  const float thr = b200at_i2f(S.meta[b * kMetaWords + M_THR]), nnz = b200at_i2f(S.meta[b * kMetaWords + M_NNZ]);
+  const int need = S.meta[b * kMetaWords + M_NEED];
+  const float alpha = b200at_i2f(S.meta[b * kMetaWords + M_ALPHA]);
+  const int64_t nvec_row = p.n / VEC;
+  const int64_t per = (nvec_row + kChunks - 1) / kChunks;
+  const int64_t v0 = c * per, v1 = (v0 + per < nvec_row) ? v0 + per : nvec_row;
+  int moved = 0;
+  for (int64_t v = v0 + threadIdx.x; v < v1; v += kThreads) {
+    const int64_t e = ((int64_t)b * nvec_row + v) * VEC;
+    const B200atVec<VEC> x = b200at_ld_stream<VEC>(p.x + e), xc = b200at_ld_stream<VEC>(sel.xc + e),
+                         g = b200at_ld_stream<VEC>(sel.g + e);
+    if (!sel.restore) {
+      if (sel.write_adv) b200at_st_stream<VEC>(p.x_best_adv + e, xc);
+      if (sel.improved) {
+        b200at_st_stream<VEC>(p.x_best + e, xc);
+        b200at_st_stream<VEC>(p.grad_best + e, g);
+      }
+    } else if (sel.write_adv) {
+      b200at_st_stream<VEC>(p.x_best_adv + e, b200at_ld_stream<VEC>(p.x_adv + e));
+    }
+    B200atVec<VEC> o;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      const float y = b200at_l1_y(x.v[i], xc.v[i], g.v[i], sel.step, thr, nnz);
+      o.v[i] = b200at_l1_out(x.v[i], y, b200at_l1_u(x.v[i], y), need, alpha);
+      moved += (B200AT_SUB(o.v[i], x.v[i]) != 0.0f);
+    }
+    b200at_st_keep<VEC>(p.x_new + e, o);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) moved += __shfl_xor_sync(0xffffffffu, moved, o);
+  if ((threadIdx.x & 31) == 0 && moved)
+    atomicAdd(reinterpret_cast<int*>(st_rw + (int64_t)B200AT_ST_SP_ADV * p.B + b), moved);
+}
+
+template <int VEC>
+int launch_l1(const B200atImages& p, void* scratch, float* st_rw, float eps, cudaStream_t s) {
+  const L1Scratch S = l1_scratch(scratch, p.B);
+  cudaError_t e = cudaMemsetAsync(S.hist, 0, sizeof(int) * (3 * kHistBins + kMetaWords) * p.B, s);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaMemsetAsync(st_rw + (int64_t)B200AT_ST_SP_ADV * p.B, 0, sizeof(int) * p.B, s);
+  if (e != cudaSuccess) return (int)e;
+  dim3 grid(kChunks, (unsigned)p.B);
+  l1_hist_kernel<0, VEC><<<grid, kThreads, 0, s>>>(p, scratch);
+  l1_scan_kernel<0><<<(unsigned)p.B, kThreads, 0, s>>>(p.st, scratch, p.B, p.n);
+  l1_hist_kernel<1, VEC><<<grid, kThreads, 0, s>>>(p, scratch);
+  l1_scan_kernel<1><<<(unsigned)p.B, kThreads, 0, s>>>(p.st, scratch, p.B, p.n);
+  l1_hist_kernel<2, VEC><<<grid, kThreads, 0, s>>>(p, scratch);
+  l1_scan_kernel<2><<<(unsigned)p.B, kThreads, 0, s>>>(p.st, scratch, p.B, p.n);
+  l1_sums_kernel<VEC><<<grid, kThreads, 0, s>>>(p, scratch);
+  l1_need_kernel<<<(unsigned)p.B, 32, 0, s>>>(scratch, p.B, eps);
+  for (int pass = 0; pass < B200AT_L1_PASSES; ++pass) {
+    l1_section_kernel<VEC><<<grid, kThreads, 0, s>>>(p, scratch, pass);
+    l1_decide_kernel<<<(unsigned)p.B, 32, 0, s>>>(scratch, p.B, pass);
+  }
+  l1_final_kernel<VEC><<<grid, kThreads, 0, s>>>(p, scratch, st_rw);
+  return (int)cudaGetLastError();
+}
+
 // One CTA never straddles two samples (grid.y = sample), so the nnz count reduces per CTA.
 template <int VEC>
 __global__ void __launch_bounds__(kThreads) init_kernel(const float* __restrict__ x, float* __restrict__ x_adv,
@@ -242,6 +613,30 @@ int b200at_linf_step(const float* x, float* x_adv, const float* x_old, float* x_
   if (v4) linf_step_kernel<4><<<grid_for(nvec, kThreads), kThreads, 0, s>>>(p, nvec, eps, a, oma);
   else linf_step_kernel<1><<<grid_for(nvec, kThreads), kThreads, 0, s>>>(p, nvec, eps, a, oma);
   return (int)cudaGetLastError();
+}
+
+int b200at_l2_step(const float* x, float* x_adv, const float* x_old, float* x_new, const float* grad,
+                   float* x_best, float* grad_best, float* x_best_adv, const float* state, float* scratch,
+                   int64_t B, int64_t n, float eps, float a, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if (B <= 0 || n <= 0) return (int)cudaSuccess;
+  if (B > 65535) return (int)cudaErrorInvalidValue;
+  B200atImages p{x, x_adv, x_old, x_new, grad, x_best, grad_best, x_best_adv, state, B, n};
+  const float oma = (float)(1.0 - (double)a);
+  const bool v4 = (n % 4 == 0) && aligned16(x) && aligned16(x_adv) && aligned16(x_old) && aligned16(x_new) &&
+                  aligned16(grad) && aligned16(x_best) && aligned16(grad_best) && aligned16(x_best_adv);
+  return v4 ? launch_l2<4>(p, scratch, eps, a, oma, s) : launch_l2<1>(p, scratch, eps, a, oma, s);
+}
+
+int b200at_l1_step(const float* x, float* x_adv, float* x_new, const float* grad, float* x_best, float* grad_best,
+                   float* x_best_adv, float* state, void* scratch, int64_t B, int64_t n, float eps, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if (B <= 0 || n <= 0) return (int)cudaSuccess;
+  if (B > 65535 || n >= (int64_t)1 << 31) return (int)cudaErrorInvalidValue;
+  B200atImages p{x, x_adv, nullptr, x_new, grad, x_best, grad_best, x_best_adv, state, B, n};
+  const bool v4 = (n % 4 == 0) && aligned16(x) && aligned16(x_adv) && aligned16(x_new) && aligned16(grad) &&
+                  aligned16(x_best) && aligned16(grad_best) && aligned16(x_best_adv);
+  return v4 ? launch_l1<4>(p, scratch, state, eps, s) : launch_l1<1>(p, scratch, state, eps, s);
 }
 
 int b200at_flush_best(const float* x_adv, float* x_best, float* x_best_adv, const float* state, int64_t B,

@@ -171,3 +171,51 @@ B200AT_HD void b200at_fgsm_step_body(const float* x, const float* x_adv, const f
   }
   b200at_st_keep<VEC>(out + e, o);
 }
+
+// ---- K2: l2 update, one phase per call (autopgd_train_clean.py:228-237).  Phases 0..2 return the
+// partial sum of squares of this vector; phase 3 writes the new iterate and applies the pending ops
+// exactly like the l-inf body.  `sums` = {||g||^2, ||z-x||^2, ||w-x||^2} of this sample so far.
+template <int PHASE, int VEC>
+B200AT_HD float b200at_l2_body(const B200atImages& p, int64_t vi, float eps, float a, float one_minus_a,
+                               const float* sums) {
+  const int64_t e = vi * VEC;
+  const int b = (int)(e / p.n);
+  const int32_t fl = b200at_f2i(p.st[(int64_t)B200AT_ST_FLAGS * p.B + b]);
+  const float step = p.st[(int64_t)B200AT_ST_STEP * p.B + b];
+  const bool improved = fl & B200AT_F_IMPROVED;
+  const bool write_adv = fl & B200AT_F_WRITE_ADV;
+  const bool restore = (fl & B200AT_F_RESTORE) && !improved;
+  const float gnorm = PHASE > 0 ? sqrtf(sums[0]) : 0.0f;
+  const float n1 = PHASE > 1 ? sqrtf(sums[1]) : 0.0f;
+  const float n2 = PHASE > 2 ? sqrtf(sums[2]) : 0.0f;
+
+  B200atVec<VEC> x, xo, xc, g;
+  g = b200at_ld_stream<VEC>((restore ? p.grad_best : p.grad) + e);
+  if (PHASE > 0) {
+    x = b200at_ld_stream<VEC>(p.x + e);
+    xc = b200at_ld_stream<VEC>((restore ? p.x_best : p.x_adv) + e);
+  }
+  if (PHASE > 1) xo = b200at_ld_stream<VEC>(p.x_old + e);
+  if (PHASE == 3) {
+    if (!restore) {
+      if (write_adv) b200at_st_stream<VEC>(p.x_best_adv + e, xc);
+      if (improved) {
+        b200at_st_stream<VEC>(p.x_best + e, xc);
+        b200at_st_stream<VEC>(p.grad_best + e, g);
+      }
+    } else {
+      if (write_adv) b200at_st_stream<VEC>(p.x_best_adv + e, b200at_ld_stream<VEC>(p.x_adv + e));
+      b200at_st_stream<VEC>(p.x_adv + e, xc);
+    }
+  }
+  B200atVec<VEC> o;
+  float acc = 0.0f;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) {
+    o.v[i] = b200at_l2_elem<PHASE>(PHASE > 0 ? x.v[i] : 0.0f, PHASE > 0 ? xc.v[i] : 0.0f, PHASE > 1 ? xo.v[i] : 0.0f,
+                                   g.v[i], step, eps, a, one_minus_a, gnorm, n1, n2);
+    acc = B200AT_ADD(acc, B200AT_MUL(o.v[i], o.v[i]));
+  }
+  if (PHASE == 3) b200at_st_keep<VEC>(p.x_new + e, o);
+  return acc;
+}

@@ -145,3 +145,70 @@ B200AT_HD void b200at_bookkeep_sample(float* st, float* loss_steps, int B, int b
   }
   *flags = b200at_i2f(fl);
 }
+
+// ------------------------------------------------------------------------------------------------
+// l2 move (autopgd_train_clean.py:228-237).  Three dependent per-sample norms:
+// ||g||, ||z - x||, ||w - x||; each phase recomputes the elementwise chain up to its reduction.
+B200AT_HD float b200at_l2_z(float xc, float g, float step, float gnorm) {
+  return B200AT_ADD(xc, B200AT_DIV(B200AT_MUL(step, g), B200AT_ADD(gnorm, 1e-12f)));
+}
+// clamp(x + d / (||d|| + 1e-12) * min(eps, ||d||), 0, 1)
+B200AT_HD float b200at_l2_ball(float x, float d, float nrm, float eps) {
+  const float q = B200AT_DIV(d, B200AT_ADD(nrm, 1e-12f));
+  return b200at_clamp01(B200AT_ADD(x, B200AT_MUL(q, b200at_min(eps, nrm))));
+}
+B200AT_HD float b200at_momentum(float xc, float z, float xo, float a, float one_minus_a) {
+  const float w = B200AT_ADD(xc, B200AT_MUL(B200AT_SUB(z, xc), a));
+  return B200AT_ADD(w, B200AT_MUL(B200AT_SUB(xc, xo), one_minus_a));
+}
+// value whose square is accumulated in phase 0/1/2, or the new iterate in phase 3
+template <int PHASE>
+B200AT_HD float b200at_l2_elem(float x, float xc, float xo, float g, float step, float eps, float a,
+                               float one_minus_a, float gnorm, float n1, float n2) {
+  if (PHASE == 0) return g;
+  const float d1 = B200AT_SUB(b200at_l2_z(xc, g, step, gnorm), x);
+  if (PHASE == 1) return d1;
+  const float z1 = b200at_l2_ball(x, d1, n1, eps);
+  const float d2 = B200AT_SUB(b200at_momentum(xc, z1, xo, a, one_minus_a), x);
+  if (PHASE == 2) return d2;
+  return b200at_l2_ball(x, d2, n2, eps);
+}
+
+// ------------------------------------------------------------------------------------------------
+// l1 move (autopgd_train_clean.py:239-250) + projection onto {||.||_1 <= eps} ∩ box (:24-91).
+//   thr  = k-th smallest |grad| (exact order statistic, radix select on the fp32 bit pattern)
+//   y    = (xc + step * s / (nnz + 1e-10)) - x,  s = sign(grad) where |grad| >= thr else 0
+//   a    = box excess of x+y (>= 0), b = |y|;  if sum(a) + eps - sum(b) < 0 the water level alpha with
+//          sum_i clamp(alpha, a_i, b_i) = sum(b) - eps is found by sectioning alpha's bit pattern
+//   out  = (x + y) + sign(y) * d,  d = -clamp(alpha, a, b)  (or -a when no l1 shrink is needed)
+B200AT_HD uint32_t b200at_l1_key(float g) { return (uint32_t)b200at_f2i(g) & 0x7fffffffu; }
+
+B200AT_HD int64_t b200at_l1_rank(float topk, int64_t n) {  // clamp((1-topk)*n, 0, n-1).long()  (:241)
+  float r = B200AT_MUL(B200AT_SUB(1.0f, topk), (float)n);
+  r = b200at_min(b200at_max(r, 0.0f), (float)(n - 1));
+  return (int64_t)r;
+}
+
+B200AT_HD float b200at_l1_y(float x, float xc, float g, float step, float thr, float nnz) {
+  const float ag = fabsf(g);
+  const float s = (ag >= thr) ? b200at_sign(g) : 0.0f;
+  const float moved = B200AT_ADD(xc, B200AT_DIV(B200AT_MUL(step, s), B200AT_ADD(nnz, 1e-10f)));
+  return B200AT_SUB(moved, x);
+}
+// u = min(0, min(1 - x - y, x + y)) <= 0  (:37-39);  a = -u, b = |y|
+B200AT_HD float b200at_l1_u(float x, float y) {
+  const float t = b200at_min(B200AT_SUB(B200AT_SUB(1.0f, x), y), B200AT_ADD(x, y));
+  return b200at_min(0.0f, t);
+}
+B200AT_HD float b200at_l1_level(float alpha, float a, float b) { return b200at_min(b200at_max(a, alpha), b); }
+B200AT_HD float b200at_l1_out(float x, float y, float u, int need, float alpha) {
+  const float d = need ? -b200at_l1_level(alpha, -u, fabsf(y)) : u;
+  return B200AT_ADD(B200AT_ADD(x, y), B200AT_MUL(b200at_sign(y), d));
+}
+// sectioning of alpha's bit pattern: 31 value bits, 5 per pass (shifts 26,21,...,1) then the last bit
+#define B200AT_L1_PASSES 7
+B200AT_HD int b200at_l1_shift(int pass) { return pass < 6 ? 26 - 5 * pass : 0; }
+B200AT_HD int b200at_l1_ncand(int pass) { return pass < 6 ? 31 : 1; }
+B200AT_HD float b200at_l1_cand(uint32_t prefix, int k, int pass) {
+  return b200at_i2f((int32_t)(prefix | ((uint32_t)k << b200at_l1_shift(pass))));
+}

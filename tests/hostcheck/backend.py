@@ -31,6 +31,10 @@ class HostBackend:
         self.L.hc_linf_step.argtypes = [P] * 9 + [I64, I64, Fl, Fl, I]
         self.L.hc_flush.argtypes = [P, P, P, P, I64, I64, I]
         self.L.hc_bookkeep.argtypes = [P, P, I64, P, P, I, I, I, I, Fl, Fl, I64]
+        self.L.hc_l2_step.argtypes = [P] * 10 + [I64, I64, Fl, Fl, I]
+        self.L.hc_l2_step.restype = None
+        self.L.hc_l1_step.argtypes = [P] * 8 + [I64, I64, Fl]
+        self.L.hc_l1_step.restype = None
         self.L.hc_fgsm_start.argtypes = [P, P, P, I64, Fl, Fl, I, I]
         self.L.hc_fgsm_step.argtypes = [P, P, P, P, I64, Fl, Fl, I, I]
         for f in ('hc_init', 'hc_linf_step', 'hc_flush', 'hc_bookkeep', 'hc_fgsm_start', 'hc_fgsm_step'):
@@ -51,6 +55,21 @@ class HostBackend:
         assert grad.is_contiguous()
         self.L.hc_linf_step(_p(x), _p(x_adv), _p(x_old), _p(x_new), _p(grad), _p(x_best), _p(grad_best),
                             _p(x_best_adv), _p(state), B, n, eps, a, self._vec(n))
+
+    def l2_step(self, x, x_adv, x_old, x_new, grad, x_best, grad_best, x_best_adv, state, eps, a, scratch):
+        B, n = x.shape[0], x[0].numel()
+        if scratch is None:
+            scratch = torch.zeros(B, 3)
+        self.L.hc_l2_step(_p(x), _p(x_adv), _p(x_old), _p(x_new), _p(grad.contiguous()), _p(x_best), _p(grad_best),
+                          _p(x_best_adv), _p(state), _p(scratch), B, n, eps, a, self._vec(n))
+        return scratch
+
+    def l1_step(self, x, x_adv, x_new, grad, x_best, grad_best, x_best_adv, state, eps, scratch):
+        B, n = x.shape[0], x[0].numel()
+        assert x_new.data_ptr() != x_adv.data_ptr()
+        self.L.hc_l1_step(_p(x), _p(x_adv), _p(x_new), _p(grad.contiguous()), _p(x_best), _p(grad_best),
+                          _p(x_best_adv), _p(state), B, n, eps)
+        return scratch
 
     def flush_best(self, x_adv, x_best, x_best_adv, state):
         B, n = x_adv.shape[0], x_adv[0].numel()

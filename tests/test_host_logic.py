@@ -31,6 +31,32 @@ def test_linf_host_path_bit_exact(name, vec):
         assert same(got, _t(g[key])), key
 
 
+@pytest.mark.parametrize('vec', [4, 1])
+@pytest.mark.parametrize('name', golden_names('scripted_l2'))
+def test_l2_host_path_within_tolerance(name, vec):
+    g = golden(name)
+    model = ScriptedModel(_t(g['logits']), _t(g['grads']))
+    out = attack.run_apgd(HostBackend(vec), model, _t(g['x']), _t(g['y']), 'L2', float(g['eps']),
+                          n_iter=int(g['n_iter']))
+    assert (torch.stack(model.seen) - _t(g['x_calls'])).abs().max() <= 1e-6
+    assert (out[0] - _t(g['x_best'])).abs().max() <= 1e-6
+    assert (out[3] - _t(g['x_best_adv'])).abs().max() <= 1e-6
+    assert same(out[1], _t(g['acc'])) and same(out[2], _t(g['loss_best']))
+
+
+@pytest.mark.parametrize('name', golden_names('scripted_l1'))
+def test_l1_host_path_within_tolerance(name):
+    g = golden(name)
+    model = ScriptedModel(_t(g['logits']), _t(g['grads']))
+    out = attack.run_apgd(HostBackend(4), model, _t(g['x']), _t(g['y']), 'L1', float(g['eps']),
+                          n_iter=int(g['n_iter']), is_train=bool(g['is_train']))
+    err = (torch.stack(model.seen) - _t(g['x_calls'])).abs().max().item()
+    assert err <= 1e-6, err
+    assert (out[0] - _t(g['x_best'])).abs().max() <= 1e-6
+    assert (out[3] - _t(g['x_best_adv'])).abs().max() <= 1e-6
+    assert same(out[1], _t(g['acc'])) and same(out[2], _t(g['loss_best']))
+
+
 def test_schedule_equals_oracle():
     from oracle.apgd_oracle import checkpoint_schedule as ref
     for norm in ('Linf', 'L2', 'L1'):
