@@ -245,7 +245,12 @@ def run_b200(args):
     launches0 = _abi.LAUNCHES['count']
     _abi.TIMING['enabled'] = True
     _abi.TIMING['events'].clear()
+    profile_range = os.environ.get('B200AT_PROFILE_RANGE') == '1'      # ncu --profile-from-start off
+    if profile_range:
+        torch.cuda.profiler.start()
     ms = timed(resident_step, args.steps)
+    if profile_range:
+        torch.cuda.profiler.stop()
     _abi.TIMING['enabled'] = False
     launches = _abi.LAUNCHES['count'] - launches0
     k1 = [a.elapsed_time(b) for name, a, b in _abi.TIMING['events'] if name == 'linf_step']

@@ -85,9 +85,10 @@ class AdvTrainStep:
 
     def __init__(self, base_model, attack='apgd', norm='Linf', eps=4. / 255., n_iter=2, lr=1e-3, weight_decay=0.05,
                  label_smoothing=0., ema=False, distributed=False, device=None, autocast_dtype=torch.bfloat16,
-                 channels_last=True, mixup_fn=None):
+                 channels_last=True, mixup_fn=None, perturb=None):
         self.device = device
-        perturb = make_attack(attack, norm, eps, n_iter, mixup_fn=mixup_fn)
+        # `perturb` overrides the attack callable (same (model, x, y) contract as main.py:283)
+        perturb = perturb if perturb is not None else make_attack(attack, norm, eps, n_iter, mixup_fn=mixup_fn)
         if channels_last:
             base_model = base_model.to(memory_format=torch.channels_last)      # misc.use_channel_last (main.py:815-817)
         model = WrappedModel(base_model, perturb) if perturb is not None else base_model
@@ -95,7 +96,8 @@ class AdvTrainStep:
         self.raw = model
         self.ema = DeviceEma(model) if ema else None                           # created before the DDP wrap (main.py:884)
         if distributed:
-            model = nn.parallel.DistributedDataParallel(model, device_ids=[device.index])   # main.py:890
+            ids = [device.index] if (device is not None and device.type == 'cuda') else None
+            model = nn.parallel.DistributedDataParallel(model, device_ids=ids)   # main.py:890
         self.model = model
         self.perturb = perturb is not None
         decay, no_decay = [], []
