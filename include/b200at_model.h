@@ -1,0 +1,53 @@
+/* b200at_model -- C ABI of the memory-bound ConvNeXt-CvSt layer kernels (libb200at.so).
+ *
+ * The reference runs these layers as eager torch ops (timm ConvNeXtBlock == the vendored
+ * /root/reference/models/convnext.py:37-50; stem/downsample LayerNorm = utils_architecture.py:57-81);
+ * each entry point cites what it replaces.  Conventions as in b200at.h: raw device pointers, caller's
+ * stream, no allocation / synchronisation, returns the cudaError_t of the launch.
+ * Activations: NHWC, bf16 (`void*`), M = B*H*W pixel rows of C channels.  Parameters and statistics: fp32.
+ */
+#ifndef B200AT_MODEL_H
+#define B200AT_MODEL_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* F.layer_norm over C per pixel (models/convnext.py:29,41 `self.norm`; utils_architecture.py:76-81 on NHWC
+ * memory), optionally followed by GELU (the stems' LN -> GELU, utils_architecture.py:205-211).
+ * Saves mean/rstd [M] for the backward.  C % 4 == 0, C <= 1536. */
+int b200at_ln_fwd(const void* x, const float* w, const float* b, void* y, float* mean, float* rstd, int64_t M,
+                  int64_t C, float eps, int fuse_gelu, void* stream);
+
+/* input gradient of the above (autograd of F.layer_norm [+ GELU]); if dw/db are non-null also ACCUMULATES
+ * the gamma/beta gradients into them (fp32 [C], caller zeroes). */
+int b200at_ln_bwd(const void* dy, const void* x, const float* w, const float* b, const float* mean, const float* rstd,
+                  void* dx, float* dw, float* db, int64_t M, int64_t C, int fuse_gelu, void* stream);
+
+/* models/convnext.py:30-31: h = GELU(z + bias) on the 4C hidden (z = x @ W1^T from the GEMM), N % 8 == 0 */
+int b200at_bias_gelu_fwd(const void* z, const float* bias, void* h, int64_t M, int64_t N, void* stream);
+/* dz = dh * GELU'(z + bias) */
+int b200at_bias_gelu_bwd(const void* dh, const void* z, const float* bias, void* dz, int64_t M, int64_t N, void* stream);
+
+/* models/convnext.py:45-49: out = res + gamma * (z + bias)  (layer scale + residual), N % 8 == 0 */
+int b200at_scale_residual_fwd(const void* z, const float* bias, const float* gamma, const void* res, void* out,
+                              int64_t M, int64_t N, void* stream);
+/* dz = dout * gamma */
+int b200at_scale_bwd(const void* dout, const float* gamma, void* dz, int64_t M, int64_t N, void* stream);
+/* c = a + b (bf16): join of the residual and branch gradients */
+int b200at_add_bf16(const void* a, const void* b, void* c, int64_t total, void* stream);
+
+/* models/convnext.py:28,39 `self.dwconv` (7x7 depthwise, pad 3) on NHWC bf16.  wt is tap-major fp32 [49][C]
+ * (wt[i*7+j][c] = weight[c,0,i,j]); bias may be null.  The input gradient is the same call with the taps
+ * flipped (wt'[i*7+j] = wt[(6-i)*7+(6-j)]) and bias = null.  C % 32 == 0. */
+int b200at_dwconv7_fwd(const void* x, const float* wt, const float* bias, void* y, int64_t B, int64_t H, int64_t W,
+                       int64_t C, void* stream);
+/* weight / bias gradients, ACCUMULATED into dw [49][C] and db [C] (fp32, caller zeroes) */
+int b200at_dwconv7_wgrad(const void* x, const void* dy, float* dw, float* db, int64_t B, int64_t H, int64_t W,
+                         int64_t C, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200AT_MODEL_H */

@@ -83,6 +83,17 @@ def _declare(L):
         'b200at_fgsm_start': [P, P, P, I64, F, F, I, P],
         'b200at_fgsm_step': [P, P, P, P, I64, F, F, I, P],
     }
+    sig.update({
+        'b200at_ln_fwd': [P, P, P, P, P, P, I64, I64, F, I, P],
+        'b200at_ln_bwd': [P, P, P, P, P, P, P, P, P, I64, I64, I, P],
+        'b200at_bias_gelu_fwd': [P, P, P, I64, I64, P],
+        'b200at_bias_gelu_bwd': [P, P, P, P, I64, I64, P],
+        'b200at_scale_residual_fwd': [P, P, P, P, P, I64, I64, P],
+        'b200at_scale_bwd': [P, P, P, I64, I64, P],
+        'b200at_add_bf16': [P, P, P, I64, P],
+        'b200at_dwconv7_fwd': [P, P, P, P, I64, I64, I64, I64, P],
+        'b200at_dwconv7_wgrad': [P, P, P, P, I64, I64, I64, I64, P],
+    })
     for name, args in sig.items():
         fn = getattr(L, name)
         fn.argtypes = args
@@ -98,11 +109,15 @@ OPTIONAL = {}
 
 
 def exported_symbols():
-    """Names include/b200at.h declares; tests check each one resolves in the .so."""
+    """Names include/*.h declare; tests check each one resolves in the .so."""
     import re
-    hdr = os.path.join(os.path.dirname(_HERE), 'include', 'b200at.h')
-    with open(hdr) as f:
-        return sorted(set(re.findall(r'^\s*int\s+(b200at_\w+)\s*\(', f.read(), flags=re.M)))
+    names = set()
+    inc = os.path.join(os.path.dirname(_HERE), 'include')
+    for h in sorted(os.listdir(inc)):
+        if h.endswith('.h'):
+            with open(os.path.join(inc, h)) as f:
+                names |= set(re.findall(r'^\s*int\s+(b200at_\w+)\s*\(', f.read(), flags=re.M))
+    return sorted(names)
 
 
 def _check(err, what):
@@ -221,3 +236,83 @@ def l1_step(x, x_adv, x_new, grad, x_best, grad_best, x_best_adv, state, eps, sc
         _check(lib().b200at_l1_step(*args), 'l1_step')
     LAUNCHES['count'] += L1_LAUNCHES - 1
     return scratch
+
+
+# ---------------------------------------------------------------------------------------------------
+# model-op kernels (include/b200at_model.h).  Activations: contiguous CUDA bf16; parameters: fp32.
+def _act(t, name):
+    if not t.is_cuda or t.dtype != torch.bfloat16 or not t.is_contiguous():
+        raise B200atError(f'{name} must be a contiguous CUDA bf16 tensor, got {t.dtype} {tuple(t.shape)} '
+                          f'strides {t.stride()} on {t.device} (no CPU path)')
+    return c_void_p(t.data_ptr())
+
+
+def _par(t, name, n=None):
+    if t is None:
+        return c_void_p(0)
+    if not t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous() or (n is not None and t.numel() != n):
+        raise B200atError(f'{name} must be a contiguous CUDA fp32 tensor' + (f' of {n} elements' if n else ''))
+    return c_void_p(t.data_ptr())
+
+
+def ln_fwd(x, w, b, y, mean, rstd, eps, gelu):
+    C = x.shape[-1]
+    M = x.numel() // C
+    with _Timed('ln_fwd'):
+        _check(lib().b200at_ln_fwd(_act(x, 'x'), _par(w, 'w', C), _par(b, 'b', C), _act(y, 'y'), _par(mean, 'mean', M),
+                                   _par(rstd, 'rstd', M), M, C, eps, int(gelu), _stream()), 'ln_fwd')
+
+
+def ln_bwd(dy, x, w, b, mean, rstd, dx, dw, db, gelu):
+    C = x.shape[-1]
+    M = x.numel() // C
+    with _Timed('ln_bwd'):
+        _check(lib().b200at_ln_bwd(_act(dy, 'dy'), _act(x, 'x'), _par(w, 'w', C), _par(b, 'b', C), _par(mean, 'mean', M),
+                                   _par(rstd, 'rstd', M), _act(dx, 'dx'), _par(dw, 'dw', C), _par(db, 'db', C), M, C,
+                                   int(gelu), _stream()), 'ln_bwd')
+
+
+def bias_gelu_fwd(z, bias, h):
+    M, N = z.shape
+    with _Timed('bias_gelu_fwd'):
+        _check(lib().b200at_bias_gelu_fwd(_act(z, 'z'), _par(bias, 'bias', N), _act(h, 'h'), M, N, _stream()), 'bias_gelu_fwd')
+
+
+def bias_gelu_bwd(dh, z, bias, dz):
+    M, N = z.shape
+    with _Timed('bias_gelu_bwd'):
+        _check(lib().b200at_bias_gelu_bwd(_act(dh, 'dh'), _act(z, 'z'), _par(bias, 'bias', N), _act(dz, 'dz'), M, N,
+                                          _stream()), 'bias_gelu_bwd')
+
+
+def scale_residual_fwd(z, bias, gamma, res, out):
+    M, N = z.shape
+    with _Timed('scale_residual_fwd'):
+        _check(lib().b200at_scale_residual_fwd(_act(z, 'z'), _par(bias, 'bias', N), _par(gamma, 'gamma', N),
+                                               _act(res, 'res'), _act(out, 'out'), M, N, _stream()), 'scale_residual_fwd')
+
+
+def scale_bwd(dout, gamma, dz):
+    M, N = dout.shape
+    with _Timed('scale_bwd'):
+        _check(lib().b200at_scale_bwd(_act(dout, 'dout'), _par(gamma, 'gamma', N), _act(dz, 'dz'), M, N, _stream()),
+               'scale_bwd')
+
+
+def add_bf16(a, b, c):
+    with _Timed('add_bf16'):
+        _check(lib().b200at_add_bf16(_act(a, 'a'), _act(b, 'b'), _act(c, 'c'), a.numel(), _stream()), 'add_bf16')
+
+
+def dwconv7_fwd(x, wt, bias, y):
+    B, H, W, C = x.shape
+    with _Timed('dwconv7'):
+        _check(lib().b200at_dwconv7_fwd(_act(x, 'x'), _par(wt, 'wt', 49 * C), _par(bias, 'bias', C), _act(y, 'y'),
+                                        B, H, W, C, _stream()), 'dwconv7_fwd')
+
+
+def dwconv7_wgrad(x, dy, dw, db):
+    B, H, W, C = x.shape
+    with _Timed('dwconv7_wgrad'):
+        _check(lib().b200at_dwconv7_wgrad(_act(x, 'x'), _act(dy, 'dy'), _par(dw, 'dw', 49 * C), _par(db, 'db', C),
+                                          B, H, W, C, _stream()), 'dwconv7_wgrad')

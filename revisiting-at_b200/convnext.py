@@ -7,7 +7,8 @@ Architecture the reference builds through timm + its conv stems (utils_architect
 (`normalize.mean/std`, `model.*`, utils_architecture.py:86-117) is `with_normalizer=True`.
 
 Every layer goes through `ops.py`, which is where the hand-written sm_100a kernels plug in
-(NHWC depthwise conv, LayerNorm, GELU, layer-scale, tcgen05 GEMMs); this module is only shape plumbing.
+(NHWC depthwise conv, LayerNorm, GELU, layer-scale); this module is only shape plumbing.  Activations
+are NHWC bf16 from the first stem layer to the head, whatever the caller's autocast state.
 """
 import torch
 import torch.nn as nn
@@ -97,7 +98,7 @@ class _Stem(nn.Module):
     def forward(self, x, mean=None, std=None):
         for j, s in enumerate(self.strides):
             conv, ln = self.stem[3 * j], self.stem[3 * j + 1]
-            x = ops.stem_layer(x, conv.weight, conv.bias, ln.weight, ln.bias, s,
+            x = ops.stem_layer(x, conv.weight, conv.bias, ln.weight, ln.bias, s, j == 0,
                                mean if j == 0 else None, std if j == 0 else None)
         return x
 

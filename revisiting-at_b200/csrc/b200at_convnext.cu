@@ -1,0 +1,568 @@
+// sm_100a kernels for the memory-bound ConvNeXt-CvSt layer ops (include/b200at_model.h):
+//   K7  depthwise 7x7 conv, NHWC bf16: forward, input-gradient (same kernel, flipped taps), weight-gradient
+//   K8  per-pixel LayerNorm over C (channels-last; also the stems' "channels_first" LN, which on NHWC
+//       memory is the same op): forward (+optional fused GELU), input-gradient, gamma/beta gradients
+//   K9  bias+GELU(erf) forward/backward on the 4C hidden, layer-scale + residual
+// Reference math: /root/reference/models/convnext.py:37-50, utils_architecture.py:57-81.
+// Activations are NHWC bf16 with fp32 statistics / accumulation.  Every pass is 8- or 16-byte vectorised
+// and coalesced along C; the depthwise conv stages its halo tile through shared memory and is register
+// tiled (a thread slides one output column through 7 input columns) because at bf16 it is FMA-issue
+// bound rather than HBM bound on B200.  Entry points never allocate or synchronise.
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+#include "../../include/b200at_model.h"
+
+namespace {
+
+typedef __nv_bfloat16 bf16;
+typedef __nv_bfloat162 bf162;
+
+__device__ __forceinline__ float gelu_f(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_grad_f(float v) {
+  const float cdf = 0.5f * (1.0f + erff(v * 0.70710678118654752f));
+  const float pdf = 0.3989422804014327f * __expf(-0.5f * v * v);
+  return cdf + v * pdf;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ void unpack4(const uint2& u, float* f) {
+  const float2 a = __bfloat1622float2(*reinterpret_cast<const bf162*>(&u.x));
+  const float2 b = __bfloat1622float2(*reinterpret_cast<const bf162*>(&u.y));
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y;
+}
+__device__ __forceinline__ uint2 pack4(const float* f) {
+  uint2 u;
+  bf162 a = __floats2bfloat162_rn(f[0], f[1]), b = __floats2bfloat162_rn(f[2], f[3]);
+  u.x = *reinterpret_cast<uint32_t*>(&a);
+  u.y = *reinterpret_cast<uint32_t*>(&b);
+  return u;
+}
+
+// ------------------------------------------------------------------------------------------------ K8
+// One warp per pixel row of C channels; lane holds VPL 8-byte vectors (4 bf16 each) in registers.
+constexpr int kLnWarps = 8;
+
+template <int VPL, bool GELU>
+__global__ void __launch_bounds__(kLnWarps * 32) ln_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ w,
+                                                               const float* __restrict__ b, bf16* __restrict__ y,
+                                                               float* __restrict__ mean, float* __restrict__ rstd,
+                                                               int64_t M, int C, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int nv = C >> 2;
+  float wr[VPL][4], br[VPL][4];
+#pragma unroll
+  for (int j = 0; j < VPL; ++j) {
+    const int v = lane + 32 * j;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      wr[j][k] = v < nv ? w[v * 4 + k] : 0.f;
+      br[j][k] = v < nv ? b[v * 4 + k] : 0.f;
+    }
+  }
+  const float inv_c = 1.0f / (float)C;
+  for (int64_t row = (int64_t)blockIdx.x * kLnWarps + (threadIdx.x >> 5); row < M; row += (int64_t)gridDim.x * kLnWarps) {
+    const uint2* xr = reinterpret_cast<const uint2*>(x + row * C);
+    float f[VPL][4];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+      const int v = lane + 32 * j;
+      if (v < nv) {
+        unpack4(__ldcs(xr + v), f[j]);
+        s += (f[j][0] + f[j][1]) + (f[j][2] + f[j][3]);
+      } else {
+        f[j][0] = f[j][1] = f[j][2] = f[j][3] = 0.f;
+      }
+    }
+    const float mu = warp_sum(s) * inv_c;
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+      const int v = lane + 32 * j;
+      if (v < nv) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { const float d = f[j][k] - mu; q += d * d; }
+      }
+    }
+    const float rs = rsqrtf(warp_sum(q) * inv_c + eps);
+    uint2* yr = reinterpret_cast<uint2*>(y + row * C);
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+      const int v = lane + 32 * j;
+      if (v < nv) {
+        float o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          o[k] = (f[j][k] - mu) * rs * wr[j][k] + br[j][k];
+          if (GELU) o[k] = gelu_f(o[k]);
+        }
+        yr[v] = pack4(o);
+      }
+    }
+    if (lane == 0) { mean[row] = mu; rstd[row] = rs; }
+  }
+}
+
+// dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * w  (dy first multiplied by gelu'(pre) if GELU)
+template <int VPL, bool GELU, bool PGRAD>
+__global__ void __launch_bounds__(kLnWarps * 32) ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
+                                                               const float* __restrict__ w, const float* __restrict__ b,
+                                                               const float* __restrict__ mean,
+                                                               const float* __restrict__ rstd, bf16* __restrict__ dx,
+                                                               float* __restrict__ dw, float* __restrict__ db,
+                                                               int64_t M, int C) {
+  extern __shared__ float red[];  // PGRAD: [kLnWarps][2][C]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nv = C >> 2;
+  float wr[VPL][4], br[VPL][4], aw[VPL][4], ab[VPL][4];
+#pragma unroll
+  for (int j = 0; j < VPL; ++j) {
+    const int v = lane + 32 * j;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      wr[j][k] = v < nv ? w[v * 4 + k] : 0.f;
+      br[j][k] = (GELU && v < nv) ? b[v * 4 + k] : 0.f;
+      aw[j][k] = 0.f; ab[j][k] = 0.f;
+    }
+  }
+  const float inv_c = 1.0f / (float)C;
+  for (int64_t row = (int64_t)blockIdx.x * kLnWarps + warp; row < M; row += (int64_t)gridDim.x * kLnWarps) {
+    const uint2* xr = reinterpret_cast<const uint2*>(x + row * C);
+    const uint2* gr = reinterpret_cast<const uint2*>(dy + row * C);
+    const float mu = mean[row], rs = rstd[row];
+    float xh[VPL][4], g[VPL][4];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+      const int v = lane + 32 * j;
+      if (v < nv) {
+        float xv[4], dv[4];
+        unpack4(__ldcs(xr + v), xv);
+        unpack4(__ldcs(gr + v), dv);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          xh[j][k] = (xv[k] - mu) * rs;
+          float d = dv[k];
+          if (GELU) d *= gelu_grad_f(xh[j][k] * wr[j][k] + br[j][k]);
+          if (PGRAD) { aw[j][k] += d * xh[j][k]; ab[j][k] += d; }
+          g[j][k] = d * wr[j][k];
+          s1 += g[j][k];
+          s2 += g[j][k] * xh[j][k];
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { xh[j][k] = 0.f; g[j][k] = 0.f; }
+      }
+    }
+    const float m1 = warp_sum(s1) * inv_c, m2 = warp_sum(s2) * inv_c;
+    uint2* dr = reinterpret_cast<uint2*>(dx + row * C);
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+      const int v = lane + 32 * j;
+      if (v < nv) {
+        float o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) o[k] = rs * (g[j][k] - m1 - xh[j][k] * m2);
+        dr[v] = pack4(o);
+      }
+    }
+  }
+  if (PGRAD) {
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+      const int v = lane + 32 * j;
+      if (v < nv) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          red[(warp * 2 + 0) * C + v * 4 + k] = aw[j][k];
+          red[(warp * 2 + 1) * C + v * 4 + k] = ab[j][k];
+        }
+      }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      float tw = 0.f, tb = 0.f;
+#pragma unroll
+      for (int q = 0; q < kLnWarps; ++q) { tw += red[(q * 2 + 0) * C + c]; tb += red[(q * 2 + 1) * C + c]; }
+      atomicAdd(dw + c, tw);
+      atomicAdd(db + c, tb);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ K9
+// h = gelu(z + bias) on [M][N] bf16, 16 bytes per thread per iteration
+__global__ void __launch_bounds__(256) bias_gelu_fwd_kernel(const bf16* __restrict__ z, const float* __restrict__ bias,
+                                                            bf16* __restrict__ h, int64_t total8, int n8) {
+  for (int64_t q = (int64_t)blockIdx.x * 256 + threadIdx.x; q < total8; q += (int64_t)gridDim.x * 256) {
+    const int c0 = (int)(q % n8) * 8;
+    const uint4 u = __ldcs(reinterpret_cast<const uint4*>(z) + q);
+    float f[8];
+    unpack4(make_uint2(u.x, u.y), f); unpack4(make_uint2(u.z, u.w), f + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(bias + c0), b1 = *reinterpret_cast<const float4*>(bias + c0 + 4);
+    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] = gelu_f(f[k] + bb[k]);
+    const uint2 lo = pack4(f), hi = pack4(f + 4);
+    reinterpret_cast<uint4*>(h)[q] = make_uint4(lo.x, lo.y, hi.x, hi.y);
+  }
+}
+
+// dz = dh * gelu'(z + bias)
+__global__ void __launch_bounds__(256) bias_gelu_bwd_kernel(const bf16* __restrict__ dh, const bf16* __restrict__ z,
+                                                            const float* __restrict__ bias, bf16* __restrict__ dz,
+                                                            int64_t total8, int n8) {
+  for (int64_t q = (int64_t)blockIdx.x * 256 + threadIdx.x; q < total8; q += (int64_t)gridDim.x * 256) {
+    const int c0 = (int)(q % n8) * 8;
+    const uint4 u = __ldcs(reinterpret_cast<const uint4*>(z) + q);
+    const uint4 d = __ldcs(reinterpret_cast<const uint4*>(dh) + q);
+    float f[8], g[8];
+    unpack4(make_uint2(u.x, u.y), f); unpack4(make_uint2(u.z, u.w), f + 4);
+    unpack4(make_uint2(d.x, d.y), g); unpack4(make_uint2(d.z, d.w), g + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(bias + c0), b1 = *reinterpret_cast<const float4*>(bias + c0 + 4);
+    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) g[k] *= gelu_grad_f(f[k] + bb[k]);
+    const uint2 lo = pack4(g), hi = pack4(g + 4);
+    reinterpret_cast<uint4*>(dz)[q] = make_uint4(lo.x, lo.y, hi.x, hi.y);
+  }
+}
+
+// out = res + gamma * (z + bias)   (layer scale + residual; models/convnext.py:45-49)
+__global__ void __launch_bounds__(256) scale_residual_kernel(const bf16* __restrict__ z, const float* __restrict__ bias,
+                                                             const float* __restrict__ gamma,
+                                                             const bf16* __restrict__ res, bf16* __restrict__ out,
+                                                             int64_t total8, int n8) {
+  for (int64_t q = (int64_t)blockIdx.x * 256 + threadIdx.x; q < total8; q += (int64_t)gridDim.x * 256) {
+    const int c0 = (int)(q % n8) * 8;
+    const uint4 u = __ldcs(reinterpret_cast<const uint4*>(z) + q);
+    const uint4 r = __ldcs(reinterpret_cast<const uint4*>(res) + q);
+    float f[8], g[8];
+    unpack4(make_uint2(u.x, u.y), f); unpack4(make_uint2(u.z, u.w), f + 4);
+    unpack4(make_uint2(r.x, r.y), g); unpack4(make_uint2(r.z, r.w), g + 4);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) g[k] += gamma[c0 + k] * (f[k] + bias[c0 + k]);
+    const uint2 lo = pack4(g), hi = pack4(g + 4);
+    reinterpret_cast<uint4*>(out)[q] = make_uint4(lo.x, lo.y, hi.x, hi.y);
+  }
+}
+
+// dz = dout * gamma  [, dres_out = dres_in + ... handled by the caller]
+__global__ void __launch_bounds__(256) scale_bwd_kernel(const bf16* __restrict__ dout, const float* __restrict__ gamma,
+                                                        bf16* __restrict__ dz, int64_t total8, int n8) {
+  for (int64_t q = (int64_t)blockIdx.x * 256 + threadIdx.x; q < total8; q += (int64_t)gridDim.x * 256) {
+    const int c0 = (int)(q % n8) * 8;
+    const uint4 d = __ldcs(reinterpret_cast<const uint4*>(dout) + q);
+    float g[8];
+    unpack4(make_uint2(d.x, d.y), g); unpack4(make_uint2(d.z, d.w), g + 4);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) g[k] *= gamma[c0 + k];
+    const uint2 lo = pack4(g), hi = pack4(g + 4);
+    reinterpret_cast<uint4*>(dz)[q] = make_uint4(lo.x, lo.y, hi.x, hi.y);
+  }
+}
+
+// c = a + b  (bf16, residual-gradient join)
+__global__ void __launch_bounds__(256) add_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b,
+                                                  bf16* __restrict__ c, int64_t total8) {
+  for (int64_t q = (int64_t)blockIdx.x * 256 + threadIdx.x; q < total8; q += (int64_t)gridDim.x * 256) {
+    const uint4 u = __ldcs(reinterpret_cast<const uint4*>(a) + q);
+    const uint4 d = __ldcs(reinterpret_cast<const uint4*>(b) + q);
+    float f[8], g[8];
+    unpack4(make_uint2(u.x, u.y), f); unpack4(make_uint2(u.z, u.w), f + 4);
+    unpack4(make_uint2(d.x, d.y), g); unpack4(make_uint2(d.z, d.w), g + 4);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) g[k] += f[k];
+    const uint2 lo = pack4(g), hi = pack4(g + 4);
+    reinterpret_cast<uint4*>(c)[q] = make_uint4(lo.x, lo.y, hi.x, hi.y);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ K7
+// Depthwise 7x7, stride 1, pad 3, NHWC bf16.  CTA = (TILE x TILE output pixels) x 32 channels of one image.
+// Thread (cp, t): channel pair cp (16 per CTA), output column t (TILE <= 16 columns).  The thread slides its
+// output column through the 7 input columns; each shared-memory load (one bf16x2) feeds up to 7 x 2 FMAs.
+constexpr int kDwTile = 14;
+constexpr int kDwIn = kDwTile + 6;   // 20
+constexpr int kDwCh = 32;            // channels per CTA (16 bf16x2 lanes)
+
+template <bool BIAS>
+__global__ void __launch_bounds__(256) dwconv7_kernel(const bf16* __restrict__ x, const float* __restrict__ wt,
+                                                      const float* __restrict__ bias, bf16* __restrict__ y, int H,
+                                                      int W, int C, int tiles_w, int tiles_h) {
+  __shared__ bf162 tile[kDwIn][kDwIn][kDwCh / 2];
+  __shared__ float2 wsm[49][kDwCh / 2];
+  const int cp = threadIdx.x & 15, t = threadIdx.x >> 4;
+  const int cgroups = C / kDwCh;
+  int bid = blockIdx.x;
+  const int cg = bid % cgroups; bid /= cgroups;
+  const int tw = bid % tiles_w; bid /= tiles_w;
+  const int th = bid % tiles_h; bid /= tiles_h;
+  const int n = bid;
+  const int h0 = th * kDwTile, w0 = tw * kDwTile, c0 = cg * kDwCh;
+  const bf16* xin = x + (int64_t)n * H * W * C;
+  // stage the (20 x 20) halo tile: 16 consecutive lanes fetch the 64 contiguous bytes of one pixel
+  for (int p = t; p < kDwIn * kDwIn; p += 16) {
+    const int r = p / kDwIn, c = p % kDwIn;
+    const int hh = h0 + r - 3, ww = w0 + c - 3;
+    bf162 v = __floats2bfloat162_rn(0.f, 0.f);
+    if (hh >= 0 && hh < H && ww >= 0 && ww < W)
+      v = *reinterpret_cast<const bf162*>(xin + ((int64_t)hh * W + ww) * C + c0 + cp * 2);
+    tile[r][c][cp] = v;
+  }
+  for (int k = t; k < 49; k += 16) wsm[k][cp] = make_float2(wt[k * C + c0 + cp * 2], wt[k * C + c0 + cp * 2 + 1]);
+  __syncthreads();
+  if (t >= kDwTile || w0 + t >= W) return;
+  float2 acc[kDwTile];
+  const float2 b2 = BIAS ? make_float2(bias[c0 + cp * 2], bias[c0 + cp * 2 + 1]) : make_float2(0.f, 0.f);
+#pragma unroll
+  for (int r = 0; r < kDwTile; ++r) acc[r] = b2;
+#pragma unroll
+  for (int j = 0; j < 7; ++j) {
+    float2 wj[7];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) wj[i] = wsm[i * 7 + j][cp];
+#pragma unroll
+    for (int r = 0; r < kDwIn; ++r) {
+      const float2 v = __bfloat1622float2(tile[r][t + j][cp]);
+#pragma unroll
+      for (int i = 0; i < 7; ++i) {
+        const int o = r - i;  // output row fed by input row r through tap row i
+        if (o >= 0 && o < kDwTile) {
+          acc[o].x = fmaf(v.x, wj[i].x, acc[o].x);
+          acc[o].y = fmaf(v.y, wj[i].y, acc[o].y);
+        }
+      }
+    }
+  }
+  bf16* yout = y + (int64_t)n * H * W * C;
+#pragma unroll
+  for (int r = 0; r < kDwTile; ++r) {
+    if (h0 + r < H)
+      *reinterpret_cast<bf162*>(yout + ((int64_t)(h0 + r) * W + w0 + t) * C + c0 + cp * 2) =
+          __floats2bfloat162_rn(acc[r].x, acc[r].y);
+  }
+}
+
+// weight gradient: dw[tap][c] += sum_{pixels} dy[p][c] * x[p + tap][c];  db[c] += sum dy
+__global__ void __launch_bounds__(256) dwconv7_wgrad_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy,
+                                                            float* __restrict__ dw, float* __restrict__ db, int H,
+                                                            int W, int C, int tiles_w, int tiles_h) {
+  __shared__ bf162 tile[kDwIn][kDwIn][kDwCh / 2];
+  __shared__ float2 red[16][kDwCh / 2];
+  const int cp = threadIdx.x & 15, t = threadIdx.x >> 4;
+  const int cgroups = C / kDwCh;
+  int bid = blockIdx.x;
+  const int cg = bid % cgroups; bid /= cgroups;
+  const int tw = bid % tiles_w; bid /= tiles_w;
+  const int th = bid % tiles_h; bid /= tiles_h;
+  const int n = bid;
+  const int h0 = th * kDwTile, w0 = tw * kDwTile, c0 = cg * kDwCh;
+  const bf16* xin = x + (int64_t)n * H * W * C;
+  const bf16* gin = dy + (int64_t)n * H * W * C;
+  for (int p = t; p < kDwIn * kDwIn; p += 16) {
+    const int r = p / kDwIn, c = p % kDwIn;
+    const int hh = h0 + r - 3, ww = w0 + c - 3;
+    bf162 v = __floats2bfloat162_rn(0.f, 0.f);
+    if (hh >= 0 && hh < H && ww >= 0 && ww < W)
+      v = *reinterpret_cast<const bf162*>(xin + ((int64_t)hh * W + ww) * C + c0 + cp * 2);
+    tile[r][c][cp] = v;
+  }
+  __syncthreads();
+  // this thread's dy column (zero outside the image)
+  float2 g[kDwTile];
+  float2 gsum = make_float2(0.f, 0.f);
+  const bool active = t < kDwTile && w0 + t < W;
+#pragma unroll
+  for (int r = 0; r < kDwTile; ++r) {
+    g[r] = make_float2(0.f, 0.f);
+    if (active && h0 + r < H)
+      g[r] = __bfloat1622float2(*reinterpret_cast<const bf162*>(gin + ((int64_t)(h0 + r) * W + w0 + t) * C + c0 + cp * 2));
+    gsum.x += g[r].x; gsum.y += g[r].y;
+  }
+  // taps are produced one tap-column j at a time; reduce over the 16 column-threads through shared memory
+  for (int j = 0; j < 7; ++j) {
+    float2 a[7];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) a[i] = make_float2(0.f, 0.f);
+    if (active) {
+#pragma unroll
+      for (int r = 0; r < kDwIn; ++r) {
+        const float2 v = __bfloat1622float2(tile[r][t + j][cp]);
+#pragma unroll
+        for (int i = 0; i < 7; ++i) {
+          const int o = r - i;
+          if (o >= 0 && o < kDwTile) {
+            a[i].x = fmaf(v.x, g[o].x, a[i].x);
+            a[i].y = fmaf(v.y, g[o].y, a[i].y);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 7; ++i) {
+      __syncthreads();
+      red[t][cp] = a[i];
+      __syncthreads();
+      if (t == 0) {
+        float2 s = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) { s.x += red[q][cp].x; s.y += red[q][cp].y; }
+        atomicAdd(dw + (i * 7 + j) * C + c0 + cp * 2, s.x);
+        atomicAdd(dw + (i * 7 + j) * C + c0 + cp * 2 + 1, s.y);
+      }
+    }
+  }
+  __syncthreads();
+  red[t][cp] = gsum;
+  __syncthreads();
+  if (t == 0) {
+    float2 s = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int q = 0; q < 16; ++q) { s.x += red[q][cp].x; s.y += red[q][cp].y; }
+    atomicAdd(db + c0 + cp * 2, s.x);
+    atomicAdd(db + c0 + cp * 2 + 1, s.y);
+  }
+}
+
+inline int ln_grid(int64_t M) {
+  int64_t g = (M + kLnWarps - 1) / kLnWarps;
+  const int64_t cap = 148 * 8;
+  return (int)(g < cap ? (g < 1 ? 1 : g) : cap);
+}
+inline int flat_grid(int64_t total8) {
+  int64_t g = (total8 + 255) / 256;
+  const int64_t cap = 148 * 16;
+  return (int)(g < cap ? (g < 1 ? 1 : g) : cap);
+}
+
+template <bool GELU>
+int launch_ln_fwd(const bf16* x, const float* w, const float* b, bf16* y, float* mean, float* rstd, int64_t M, int C,
+                  float eps, cudaStream_t s) {
+  const int vpl = (C / 4 + 31) / 32, g = ln_grid(M), th = kLnWarps * 32;
+  switch (vpl) {
+#define B200AT_CASE(V) case V: ln_fwd_kernel<V, GELU><<<g, th, 0, s>>>(x, w, b, y, mean, rstd, M, C, eps); break;
+    B200AT_CASE(1) B200AT_CASE(2) B200AT_CASE(3) B200AT_CASE(4) B200AT_CASE(5) B200AT_CASE(6) B200AT_CASE(7)
+    B200AT_CASE(8) B200AT_CASE(9) B200AT_CASE(10) B200AT_CASE(11) B200AT_CASE(12)
+#undef B200AT_CASE
+    default: return (int)cudaErrorInvalidValue;
+  }
+  return (int)cudaGetLastError();
+}
+
+template <bool GELU, bool PGRAD>
+int launch_ln_bwd(const bf16* dy, const bf16* x, const float* w, const float* b, const float* mean, const float* rstd,
+                  bf16* dx, float* dw, float* db, int64_t M, int C, cudaStream_t s) {
+  const int vpl = (C / 4 + 31) / 32, g = ln_grid(M), th = kLnWarps * 32;
+  const size_t sm = PGRAD ? sizeof(float) * kLnWarps * 2 * C : 0;
+  switch (vpl) {
+#define B200AT_CASE(V)                                                                                          \
+  case V: {                                                                                                     \
+    if (sm > 48 * 1024)                                                                                         \
+      cudaFuncSetAttribute(ln_bwd_kernel<V, GELU, PGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); \
+    ln_bwd_kernel<V, GELU, PGRAD><<<g, th, sm, s>>>(dy, x, w, b, mean, rstd, dx, dw, db, M, C);                  \
+  } break;
+    B200AT_CASE(1) B200AT_CASE(2) B200AT_CASE(3) B200AT_CASE(4) B200AT_CASE(5) B200AT_CASE(6) B200AT_CASE(7)
+    B200AT_CASE(8) B200AT_CASE(9) B200AT_CASE(10) B200AT_CASE(11) B200AT_CASE(12)
+#undef B200AT_CASE
+    default: return (int)cudaErrorInvalidValue;
+  }
+  return (int)cudaGetLastError();
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200at_ln_fwd(const void* x, const float* w, const float* b, void* y, float* mean, float* rstd, int64_t M,
+                  int64_t C, float eps, int fuse_gelu, void* stream) {
+  if (M <= 0) return 0;
+  if (C % 4 || C > 1536) return (int)cudaErrorInvalidValue;
+  cudaStream_t s = (cudaStream_t)stream;
+  return fuse_gelu ? launch_ln_fwd<true>((const bf16*)x, w, b, (bf16*)y, mean, rstd, M, (int)C, eps, s)
+                   : launch_ln_fwd<false>((const bf16*)x, w, b, (bf16*)y, mean, rstd, M, (int)C, eps, s);
+}
+
+int b200at_ln_bwd(const void* dy, const void* x, const float* w, const float* b, const float* mean, const float* rstd,
+                  void* dx, float* dw, float* db, int64_t M, int64_t C, int fuse_gelu, void* stream) {
+  if (M <= 0) return 0;
+  if (C % 4 || C > 1536) return (int)cudaErrorInvalidValue;
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool pg = dw != nullptr;
+  if (pg != (db != nullptr)) return (int)cudaErrorInvalidValue;
+#define B200AT_GO(G, P) launch_ln_bwd<G, P>((const bf16*)dy, (const bf16*)x, w, b, mean, rstd, (bf16*)dx, dw, db, M, (int)C, s)
+  if (fuse_gelu) return pg ? B200AT_GO(true, true) : B200AT_GO(true, false);
+  return pg ? B200AT_GO(false, true) : B200AT_GO(false, false);
+#undef B200AT_GO
+}
+
+int b200at_bias_gelu_fwd(const void* z, const float* bias, void* h, int64_t M, int64_t N, void* stream) {
+  if (M <= 0) return 0;
+  if (N % 8) return (int)cudaErrorInvalidValue;
+  const int64_t total8 = M * N / 8;
+  bias_gelu_fwd_kernel<<<flat_grid(total8), 256, 0, (cudaStream_t)stream>>>((const bf16*)z, bias, (bf16*)h, total8, (int)(N / 8));
+  return (int)cudaGetLastError();
+}
+
+int b200at_bias_gelu_bwd(const void* dh, const void* z, const float* bias, void* dz, int64_t M, int64_t N, void* stream) {
+  if (M <= 0) return 0;
+  if (N % 8) return (int)cudaErrorInvalidValue;
+  const int64_t total8 = M * N / 8;
+  bias_gelu_bwd_kernel<<<flat_grid(total8), 256, 0, (cudaStream_t)stream>>>((const bf16*)dh, (const bf16*)z, bias, (bf16*)dz, total8, (int)(N / 8));
+  return (int)cudaGetLastError();
+}
+
+int b200at_scale_residual_fwd(const void* z, const float* bias, const float* gamma, const void* res, void* out,
+                              int64_t M, int64_t N, void* stream) {
+  if (M <= 0) return 0;
+  if (N % 8) return (int)cudaErrorInvalidValue;
+  const int64_t total8 = M * N / 8;
+  scale_residual_kernel<<<flat_grid(total8), 256, 0, (cudaStream_t)stream>>>((const bf16*)z, bias, gamma, (const bf16*)res, (bf16*)out, total8, (int)(N / 8));
+  return (int)cudaGetLastError();
+}
+
+int b200at_scale_bwd(const void* dout, const float* gamma, void* dz, int64_t M, int64_t N, void* stream) {
+  if (M <= 0) return 0;
+  if (N % 8) return (int)cudaErrorInvalidValue;
+  const int64_t total8 = M * N / 8;
+  scale_bwd_kernel<<<flat_grid(total8), 256, 0, (cudaStream_t)stream>>>((const bf16*)dout, gamma, (bf16*)dz, total8, (int)(N / 8));
+  return (int)cudaGetLastError();
+}
+
+int b200at_add_bf16(const void* a, const void* b, void* c, int64_t total, void* stream) {
+  if (total <= 0) return 0;
+  if (total % 8) return (int)cudaErrorInvalidValue;
+  add_kernel<<<flat_grid(total / 8), 256, 0, (cudaStream_t)stream>>>((const bf16*)a, (const bf16*)b, (bf16*)c, total / 8);
+  return (int)cudaGetLastError();
+}
+
+int b200at_dwconv7_fwd(const void* x, const float* wt, const float* bias, void* y, int64_t B, int64_t H, int64_t W,
+                       int64_t C, void* stream) {
+  if (B <= 0) return 0;
+  if (C % kDwCh) return (int)cudaErrorInvalidValue;
+  const int tw = (int)((W + kDwTile - 1) / kDwTile), th = (int)((H + kDwTile - 1) / kDwTile);
+  const int64_t grid = B * th * tw * (C / kDwCh);
+  if (grid > 0x7fffffff) return (int)cudaErrorInvalidValue;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (bias) dwconv7_kernel<true><<<(unsigned)grid, 256, 0, s>>>((const bf16*)x, wt, bias, (bf16*)y, (int)H, (int)W, (int)C, tw, th);
+  else dwconv7_kernel<false><<<(unsigned)grid, 256, 0, s>>>((const bf16*)x, wt, nullptr, (bf16*)y, (int)H, (int)W, (int)C, tw, th);
+  return (int)cudaGetLastError();
+}
+
+int b200at_dwconv7_wgrad(const void* x, const void* dy, float* dw, float* db, int64_t B, int64_t H, int64_t W,
+                         int64_t C, void* stream) {
+  if (B <= 0) return 0;
+  if (C % kDwCh) return (int)cudaErrorInvalidValue;
+  const int tw = (int)((W + kDwTile - 1) / kDwTile), th = (int)((H + kDwTile - 1) / kDwTile);
+  const int64_t grid = B * th * tw * (C / kDwCh);
+  if (grid > 0x7fffffff) return (int)cudaErrorInvalidValue;
+  dwconv7_wgrad_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)dy, dw, db, (int)H, (int)W, (int)C, tw, th);
+  return (int)cudaGetLastError();
+}
+
+}  // extern "C"

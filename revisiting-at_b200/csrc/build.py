@@ -16,12 +16,13 @@ COMMON = ['-O3', '-lineinfo', '-std=c++17', '-Xcompiler', '-fPIC', '--expt-relax
 UNITS = [
     # (source, extra flags)
     ('b200at_attack.cu', ['-fmad=false']),
+    ('b200at_convnext.cu', []),
 ]
 
 
 def _deps():
     return [os.path.join(HERE, f) for f in os.listdir(HERE) if f.endswith(('.cu', '.cuh', '.h', '.py'))] + \
-           [os.path.join(HERE, '..', '..', 'include', 'b200at.h')]
+           [os.path.join(HERE, '..', '..', 'include', h) for h in ('b200at.h', 'b200at_model.h')]
 
 
 def build(force=False, verbose=False):

@@ -1,0 +1,135 @@
+"""GPU: the hand-written ConvNeXt layer kernels against plain PyTorch fp32 references of the same op
+(bf16 storage tolerance written at each assert), and the whole ConvNeXt-T-CvSt engine against the CPU
+model oracle."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+BF16 = torch.bfloat16
+
+
+@pytest.fixture(scope='module')
+def ops(cuda_dev):
+    import revisiting_at_b200  # noqa: F401
+    from revisiting_at_b200 import ops as o
+    return o
+
+
+def _close(a, b, atol, rtol=2e-2):
+    a, b = a.float(), b.float()
+    err = (a - b).abs()
+    ok = err <= atol + rtol * b.abs()
+    assert bool(ok.all()), f'max err {err.max().item():.4g} (atol {atol}, rtol {rtol}), frac bad {(~ok).float().mean().item():.2e}'
+
+
+@pytest.mark.parametrize('C', [48, 96, 144, 192, 384, 768, 1536])
+@pytest.mark.parametrize('gelu', [False, True])
+def test_layernorm_fwd_bwd(ops, cuda_dev, C, gelu):
+    g = torch.Generator(device='cuda').manual_seed(C)
+    M = 1031
+    x = (torch.randn(M, C, generator=g, device=cuda_dev) * 2 + 0.5).to(BF16)
+    w = torch.randn(C, generator=g, device=cuda_dev).requires_grad_()
+    b = torch.randn(C, generator=g, device=cuda_dev).requires_grad_()
+    dy = torch.randn(M, C, generator=g, device=cuda_dev).to(BF16)
+    xr = x.float().requires_grad_()
+    ref = F.layer_norm(xr, (C,), w, b, 1e-6)
+    if gelu:
+        ref = F.gelu(ref)
+    rdx, rdw, rdb = torch.autograd.grad(ref, [xr, w, b], dy.float())
+    xt = x.clone().requires_grad_()
+    out = ops.layer_norm(xt, w, b, 1e-6, gelu)
+    _close(out, ref, atol=2e-2)                    # bf16 output: half an ulp at |y| ~ 4 is 1.6e-2
+    dx, dw, db = torch.autograd.grad(out, [xt, w, b], dy)
+    _close(dx, rdx, atol=3e-2)
+    _close(dw, rdw, atol=0.5, rtol=1e-2)           # sums of 1031 bf16-rounded products
+    _close(db, rdb, atol=0.5, rtol=1e-2)
+    (dx2,) = torch.autograd.grad(ops.layer_norm(xt, w, b, 1e-6, gelu), [xt], dy)   # input-grad only path
+    assert torch.equal(dx2, dx)
+
+
+@pytest.mark.parametrize('shape', [(2, 56, 56, 96), (3, 28, 28, 192), (2, 14, 14, 384), (5, 7, 7, 768), (1, 20, 23, 32)])
+def test_dwconv7_fwd_dgrad_wgrad(ops, cuda_dev, shape):
+    B, H, W, C = shape
+    g = torch.Generator(device='cuda').manual_seed(H * C)
+    x = torch.randn(B, H, W, C, generator=g, device=cuda_dev).to(BF16)
+    w = (torch.randn(C, 1, 7, 7, generator=g, device=cuda_dev) * 0.1).requires_grad_()
+    b = torch.randn(C, generator=g, device=cuda_dev).requires_grad_()
+    dy = torch.randn(B, H, W, C, generator=g, device=cuda_dev).to(BF16)
+    xr = x.float().permute(0, 3, 1, 2).requires_grad_()
+    ref = F.conv2d(xr, w, b, padding=3, groups=C)
+    rdx, rdw, rdb = torch.autograd.grad(ref, [xr, w, b], dy.float().permute(0, 3, 1, 2))
+    xt = x.clone().requires_grad_()
+    out = ops._DwConv7.apply(xt, w, b)
+    _close(out, ref.permute(0, 2, 3, 1), atol=2e-2)
+    dx, dw, db = torch.autograd.grad(out, [xt, w, b], dy)
+    _close(dx, rdx.permute(0, 2, 3, 1), atol=2e-2)
+    _close(dw, rdw, atol=1e-2 * (B * H * W) ** 0.5, rtol=1e-2)
+    _close(db, rdb, atol=1e-2 * (B * H * W) ** 0.5, rtol=1e-2)
+
+
+def test_bias_gelu_and_scale_residual(ops, cuda_dev):
+    g = torch.Generator(device='cuda').manual_seed(1)
+    M, N = 999, 384
+    z = (torch.randn(M, N, generator=g, device=cuda_dev) * 2).to(BF16)
+    bias = torch.randn(N, generator=g, device=cuda_dev).requires_grad_()
+    dh = torch.randn(M, N, generator=g, device=cuda_dev).to(BF16)
+    zr = z.float().requires_grad_()
+    ref = F.gelu(zr + bias)
+    rdz, rdb = torch.autograd.grad(ref, [zr, bias], dh.float())
+    zt = z.clone().requires_grad_()
+    out = ops._BiasGelu.apply(zt, bias)
+    _close(out, ref, atol=1e-2)
+    dz, db = torch.autograd.grad(out, [zt, bias], dh)
+    _close(dz, rdz, atol=1e-2)
+    _close(db, rdb, atol=0.3, rtol=1e-2)
+
+    gamma = torch.randn(N, generator=g, device=cuda_dev).requires_grad_()
+    res = torch.randn(M, N, generator=g, device=cuda_dev).to(BF16)
+    rr = res.float().requires_grad_()
+    ref = rr + gamma * (zr + bias)
+    rg = torch.autograd.grad(ref, [zr, bias, gamma, rr], dh.float())
+    rt = res.clone().requires_grad_()
+    out = ops._ScaleResidual.apply(zt, bias, gamma, rt)
+    _close(out, ref, atol=3e-2)
+    got = torch.autograd.grad(out, [zt, bias, gamma, rt], dh)
+    _close(got[0], rg[0], atol=2e-2)
+    _close(got[1], rg[1], atol=0.5, rtol=1e-2)
+    _close(got[2], rg[2], atol=0.5, rtol=1e-2)
+    _close(got[3], rg[3], atol=1e-6)
+
+
+def test_convnext_engine_matches_oracle(cuda_dev):
+    """ConvNeXt-T-CvSt, same seed-0 weights: bf16 engine on the GPU vs fp32 oracle on the CPU.
+    Tolerances: logits 5e-2 absolute (|logit| ~ 1, ~40 bf16 layers); input gradient cosine >= 0.98."""
+    from revisiting_at_b200 import convnext
+    from oracle import convnext_oracle as co
+    o = co.build('convnext_tiny', normalize=True, seed=0)
+    m = convnext.build('convnext_tiny', normalize=True, seed=1)
+    m.load_state_dict(o.state_dict())
+    m = m.to(cuda_dev).eval()
+    g = torch.Generator().manual_seed(3)
+    x = torch.rand(4, 3, 64, 64, generator=g)
+    y = torch.randint(0, 1000, (4,), generator=g)
+    xo = x.clone().requires_grad_()
+    lo = o(xo)
+    (go,) = torch.autograd.grad(F.cross_entropy(lo, y, reduction='sum'), xo)
+    xm = x.to(cuda_dev).requires_grad_()
+    lm = m(xm)
+    (gm,) = torch.autograd.grad(F.cross_entropy(lm.float(), y.to(cuda_dev), reduction='sum'), xm)
+    assert (lm.float().cpu() - lo).abs().max() <= 5e-2, (lm.float().cpu() - lo).abs().max()
+    cos = F.cosine_similarity(gm.cpu().flatten(1), go.flatten(1)).min().item()
+    assert cos >= 0.98, cos
+    assert all(p.grad is None for p in m.parameters())
+    # full backward (outer training step): every parameter receives a finite gradient
+    m.train()
+    loss = F.cross_entropy(m(x.to(cuda_dev)).float(), y.to(cuda_dev))
+    loss.backward()
+    o.train()
+    F.cross_entropy(o(x), y).backward()
+    od = dict(o.named_parameters())
+    for n, p in m.named_parameters():
+        assert p.grad is not None and bool(torch.isfinite(p.grad).all()), n
+        ref = od[n].grad
+        cs = F.cosine_similarity(p.grad.flatten().cpu().float(), ref.flatten(), dim=0).item()
+        assert cs >= 0.95 or ref.abs().max() < 1e-7, (n, cs)
