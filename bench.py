@@ -253,7 +253,10 @@ def run_b200(args):
         torch.cuda.profiler.stop()
     _abi.TIMING['enabled'] = False
     launches = _abi.LAUNCHES['count'] - launches0
-    k1 = [a.elapsed_time(b) for name, a, b in _abi.TIMING['events'] if name == 'linf_step']
+    # algorithmic bytes per element of each timed K1 launch (20 B = read x, x_adv, x_adv_old, grad +
+    # write x_adv; the first move of a call has x_adv_old == x_adv, one stream fewer => credited 16 B)
+    credit = {'linf_step': 20.0, 'linf_step_log': 20.0, 'linf_step_log_first': 16.0}
+    k1 = [(a.elapsed_time(b), credit[name]) for name, a, b in _abi.TIMING['events'] if name in credit]
     _abi.TIMING['events'].clear()
     for i in range(2):
         e2e_step(i)
@@ -270,10 +273,8 @@ def run_b200(args):
         peak, peak_src = json.load(open(peaks_path))['hbm_gbs'], 'MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)'
     else:
         peak, peak_src = FALLBACK_HBM_GBS, 'fallback (B200_PROFILING.md)'
-    k1_ms = sum(k1) / len(k1) if k1 else float('nan')
-    # the first move of each call has x_old == x_adv (one stream fewer) but seeds x_best/grad_best/x_best_adv;
-    # all launches are credited with the same 20 B/element figure
-    alg_bytes = 20.0 * batch * N_FTS
+    k1_ms = sum(t for t, _ in k1) / len(k1) if k1 else float('nan')
+    alg_bytes = sum(c for _, c in k1) / len(k1) * batch * N_FTS if k1 else float('nan')   # mean per launch
     achieved = alg_bytes / (k1_ms * 1e-3) / 1e9
     traffic = None
     tp = os.path.join(ROOT, 'profiles', 'k1_linf_step_traffic.json')
@@ -287,12 +288,14 @@ def run_b200(args):
                 'h2d_bytes_per_step': batch * N_FTS * 4 + batch * 8, 'd2h_bytes_per_step': 4,
                 'ms_per_step': ms_e2e / args.steps},
         'gpu_launches': launches,
-        'roofline': {'kernel': 'b200at_linf_step (fused l-inf APGD update)', 'bound': 'hbm', 'achieved': achieved,
+        'roofline': {'kernel': 'b200at_linf_step_log (fused l-inf APGD update, iterate-log form)', 'bound': 'hbm',
+                     'achieved': achieved,
                      'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic,
                      'algorithmic_bytes_per_launch': alg_bytes, 'launch_ms_mean': k1_ms, 'launches_timed': len(k1),
                      'peak_source': peak_src, 'frac_of_nominal_8TBps': achieved / 8000.0},
         'clocks': clocks,
-        'model_engine': 'torch library kernels (cuDNN/cuBLAS) for the network in round 1; attack kernels hand-written',
+        'model_engine': 'hand-written NHWC bf16 kernels for dwconv7/LayerNorm/GELU/layer-scale; cuBLAS GEMMs and '
+                        'cuDNN strided convs (stem, downsample) through torch',
     }
     if world == 1 and not args.no_cpu_baseline:
         torch.cuda.empty_cache()

@@ -61,6 +61,19 @@ int b200at_linf_step(const float* x, float* x_adv, const float* x_old, float* x_
                      float* x_best, float* grad_best, float* x_best_adv, const float* state, int64_t B, int64_t n,
                      float eps, float a, void* stream);
 
+/* Iterate-log form of b200at_linf_step for short attacks (n_iter + 1 <= B200AT_LOG_MAX_SLOTS = 8, the training
+ * configuration): every iterate x_adv^(k) and gradient stays in its own buffer ("slot"), and the masked
+ * copies of autopgd_train_clean.py:304,:321-324,:345-346 are replaced by per-sample slot indices kept by
+ * b200at_loss_bookkeep in state[IDX_*].  One launch moves exactly 20 B/element (16 on the first move).
+ * x_slots / g_slots: HOST arrays of n_slots device pointers (slot k = iterate k / gradient at iterate k;
+ * unused gradient slots may repeat a valid pointer). */
+#define B200AT_LOG_MAX_SLOTS 8
+int b200at_linf_step_log(const float* x, const float* const* x_slots, const float* const* g_slots, int n_slots,
+                         float* x_new, const float* state, int64_t B, int64_t n, float eps, float a, void* stream);
+/* end of an iterate-log attack: x_best[b] = x_slots[IDX_BEST[b]][b], x_best_adv[b] = x_slots[IDX_BEST_ADV[b]][b] */
+int b200at_gather_best(const float* const* x_slots, int n_slots, float* x_best, float* x_best_adv,
+                       const float* state, int64_t B, int64_t n, void* stream);
+
 /* autopgd_train_clean.py:228-237 (+ the same pending image ops as b200at_linf_step): l2 move with
  * momentum; the three dependent per-sample norms (||grad||, ||z-x||, ||w-x||) are deterministic
  * two-level sums.  scratch: >= B200AT_L2_SCRATCH_FLOATS(B) floats, contents irrelevant on entry. */

@@ -56,6 +56,21 @@ def main():
     timeit('linf_step_first(seed best: 12B rd + 16B wr)', lambda: _abi.linf_step(x, xa, xa, xo, gr, xb, gb, xba, st, eps, 1.0), 28. * B * n)
     flags.copy_(torch.arange(B, device=dev, dtype=torch.int32) % 8)
     timeit('linf_step_mixed_flags(20B/elt credited)', lambda: _abi.linf_step(x, xa, xo, xo, gr, xb, gb, xba, st, eps, 0.75), 20. * B * n)
+    xs = [xa, xo, xb]
+    gs = [gr, gb]
+    for r, v in ((_abi.ST_IDX_CUR, 1), (_abi.ST_IDX_OLD, 0), (_abi.ST_GIDX_CUR, 1)):
+        st[r].view(torch.int32).fill_(v)
+    gb.copy_(gr)
+    timeit('linf_step_log_steady(20B/elt)', lambda: _abi.linf_step_log(x, xs, gs, xba, st, eps, 0.75), 20. * B * n)
+    st[_abi.ST_IDX_OLD].view(torch.int32).fill_(1)
+    timeit('linf_step_log_first(16B/elt)', lambda: _abi.linf_step_log(x, xs, gs, xba, st, eps, 1.0), 16. * B * n)
+    st[_abi.ST_IDX_CUR].view(torch.int32).copy_(torch.arange(B, device=dev, dtype=torch.int32) % 2)
+    st[_abi.ST_IDX_OLD].view(torch.int32).copy_((torch.arange(B, device=dev, dtype=torch.int32) + 1) % 2)
+    timeit('linf_step_log_mixed_slots(20B/elt)', lambda: _abi.linf_step_log(x, xs, gs, xba, st, eps, 0.75), 20. * B * n)
+    st[_abi.ST_IDX_BEST].view(torch.int32).copy_(torch.arange(B, device=dev, dtype=torch.int32) % 3)
+    st[_abi.ST_IDX_BEST_ADV].view(torch.int32).copy_((torch.arange(B, device=dev, dtype=torch.int32) // 3) % 3)
+    out1, out2 = torch.empty_like(x), torch.empty_like(x)
+    timeit('gather_best(16B/elt)', lambda: _abi.gather_best(xs, out1, out2, st), 16. * B * n)
     flags.fill_(3)
     timeit('flush_best(all flagged, 12B/elt)', lambda: _abi.flush_best(xa, xb, xba, st), 12. * B * n)
     timeit('apgd_init(8B/elt)', lambda: _abi.apgd_init(x, xa, st, 2 * eps, 0.), 8. * B * n)

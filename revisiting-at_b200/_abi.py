@@ -17,7 +17,9 @@ ABI_VERSION = 1
 # state rows (csrc/b200at_math.cuh)
 ST_STEP, ST_LOSS_BEST, ST_LOSS_BEST_LAST, ST_REDUCED_LAST, ST_ACC, ST_FLAGS, ST_LOSS_CUR = range(7)
 ST_TOPK, ST_SP_OLD, ST_SP_BEST, ST_SP_ADV, ST_PRED = 7, 8, 9, 10, 11
-ST_ROWS = 16
+ST_IDX_CUR, ST_IDX_OLD, ST_IDX_BEST, ST_IDX_BEST_ADV, ST_GIDX_CUR, ST_GIDX_BEST = 12, 13, 14, 15, 16, 17
+ST_ROWS = 20
+LOG_MAX_SLOTS = 8
 F_IMPROVED, F_WRITE_ADV, F_RESTORE = 1, 2, 4
 NORMS = {'Linf': 0, 'L2': 1, 'L1': 2}
 LOSSES = {'ce': 0, 'dlr': 1}
@@ -77,6 +79,8 @@ def _declare(L):
         'b200at_apgd_init': [P, P, P, I64, I64, F, F, P],
         'b200at_linf_step': [P, P, P, P, P, P, P, P, P, I64, I64, F, F, P],
         'b200at_flush_best': [P, P, P, P, I64, I64, P],
+        'b200at_linf_step_log': [P, P, P, I, P, P, I64, I64, F, F, P],
+        'b200at_gather_best': [P, I, P, P, P, I64, I64, P],
         'b200at_l2_step': [P, P, P, P, P, P, P, P, P, P, I64, I64, F, F, P],
         'b200at_l1_step': [P, P, P, P, P, P, P, P, P, I64, I64, F, P],
         'b200at_loss_bookkeep': [P, I, P, P, P, P, P, P, I64, I64, I, I, I, I, I, F, F, I64, P],
@@ -316,3 +320,25 @@ def dwconv7_wgrad(x, dy, dw, db):
     with _Timed('dwconv7_wgrad'):
         _check(lib().b200at_dwconv7_wgrad(_act(x, 'x'), _act(dy, 'dy'), _par(dw, 'dw', 49 * C), _par(db, 'db', C),
                                           B, H, W, C, _stream()), 'dwconv7_wgrad')
+
+
+def _slot_ptrs(ts, like, name):
+    return (c_void_p * len(ts))(*[_img(t, like, f'{name}[{i}]').value for i, t in enumerate(ts)])
+
+
+def linf_step_log(x, x_slots, g_slots, x_new, state, eps, a):
+    """x_slots / g_slots: python lists of the iterate / gradient tensors, slot k first."""
+    B, n = x.shape[0], x[0].numel() if x.shape[0] else 0
+    g_full = list(g_slots) + [g_slots[0]] * (len(x_slots) - len(g_slots))
+    args = (_img(x, name='x'), _slot_ptrs(x_slots, x, 'x_slots'), _slot_ptrs(g_full, x, 'g_slots'), len(x_slots),
+            _img(x_new, x, 'x_new'), _p(state), B, n, eps, a, _stream())
+    with _Timed('linf_step_log_first' if a == 1.0 else 'linf_step_log'):
+        _check(lib().b200at_linf_step_log(*args), 'linf_step_log')
+
+
+def gather_best(x_slots, x_best, x_best_adv, state):
+    B, n = x_best.shape[0], x_best[0].numel() if x_best.shape[0] else 0
+    with _Timed('gather_best'):
+        _check(lib().b200at_gather_best(_slot_ptrs(x_slots, x_best, 'x_slots'), len(x_slots), _img(x_best, name='x_best'),
+                                        _img(x_best_adv, x_best, 'x_best_adv'), _p(state), B, n, _stream()),
+               'gather_best')

@@ -24,8 +24,14 @@ import time
 import torch
 
 from . import _abi
+from .ops import input_grad_only
+
+import os
 
 _SUPPORTED_LOSS = ('ce', 'dlr')
+# l-inf attacks with n_iter + 1 <= LOG_SLOTS keep every iterate/gradient in its own buffer and replace all
+# masked image copies by per-sample slot indices (b200at_linf_step_log); longer attacks use the copying kernel.
+LOG_SLOTS = int(os.environ.get('B200AT_APGD_LOG_SLOTS', str(_abi.LOG_MAX_SLOTS)))
 
 
 def checkpoint_schedule(norm: str, n_iter: int):
@@ -58,6 +64,8 @@ class CudaBackend:
 
     init = staticmethod(_abi.apgd_init)
     linf_step = staticmethod(_abi.linf_step)
+    linf_step_log = staticmethod(_abi.linf_step_log)
+    gather_best = staticmethod(_abi.gather_best)
     flush_best = staticmethod(_abi.flush_best)
     loss_bookkeep = staticmethod(_abi.loss_bookkeep)
 
@@ -80,7 +88,7 @@ def _dense_like_input(x):
 
 
 def run_apgd(be, model, x, y, norm, eps, n_iter=10, use_rs=False, loss='ce', verbose=False, mixup=None,
-             is_train=True):
+             is_train=True, log_slots=None):
     assert not model.training                                     # autopgd_train_clean.py:125
     if use_rs:
         raise TypeError('exceptions must derive from BaseException')   # `raise NotImplemented` (:137)
@@ -109,23 +117,21 @@ def run_apgd(be, model, x, y, norm, eps, n_iter=10, use_rs=False, loss='ce', ver
     if loss == 'dlr' and (soft or y.dim() != 1):
         raise _abi.B200atError("loss 'dlr' needs hard labels")
 
-    buf_a, buf_b = torch.empty_like(x), torch.empty_like(x)
-    x_best, x_best_adv, grad_best = torch.empty_like(x), torch.empty_like(x), torch.empty_like(x)
+    log_slots = LOG_SLOTS if log_slots is None else log_slots
+    use_log = norm == 'Linf' and 1 <= n_iter and n_iter + 1 <= min(log_slots, _abi.LOG_MAX_SLOTS)
     grad_buf = None
     state = torch.empty(_abi.ST_ROWS, B, device=dev, dtype=torch.float32)
     loss_steps = torch.zeros(max(n_iter, 1), B, device=dev, dtype=torch.float32)
     scratch = None
-    be.init(x, buf_a, state, step_full, topk0)
-
     times = {'fp': 0., 'bp': 0.}
 
-    def evaluate(x_cur, it, need_grad):
+    def evaluate(x_cur, it, need_grad, own_grad=False):
         nonlocal grad_buf
         xin = x_cur.detach()
         if need_grad:
             xin.requires_grad_()
         t0 = time.time()
-        with torch.enable_grad():
+        with (torch.enable_grad() if need_grad else torch.no_grad()), input_grad_only():
             logits = model(xin)
         times['fp'] += time.time() - t0
         lg = logits.detach()
@@ -141,12 +147,38 @@ def run_apgd(be, model, x, y, norm, eps, n_iter=10, use_rs=False, loss='ce', ver
         times['bp'] += time.time() - t0
         if g.dtype != torch.float32 or g.shape != x.shape or g.stride() != x.stride():
             # backward handed back another layout (e.g. channels_last from a cuDNN dgrad): one dense copy
-            if grad_buf is None:
+            if grad_buf is None or own_grad:
                 grad_buf = torch.empty_like(x)
             grad_buf.copy_(g)
             g = grad_buf
         return g
 
+    def finish(x_best, x_best_adv):
+        acc = state[_abi.ST_ACC].view(torch.int32) != 0
+        loss_best = state[_abi.ST_LOSS_BEST].clone()
+        if verbose:
+            times['total'] = time.time() - t_total
+            print(' '.join(f'{k}={v:.5f} s' for k, v in times.items()))
+        return x_best, acc, loss_best, x_best_adv
+
+    if use_log:
+        xs = [torch.empty_like(x) for _ in range(n_iter + 1)]       # slot k = iterate k
+        be.init(x, xs[0], state, step_full, topk0)
+        gs = [evaluate(xs[0], -1, True, own_grad=True)]             # slot k = gradient at iterate k
+        for i in range(n_iter):
+            be.linf_step_log(x, xs, gs, xs[i + 1], state, eps, 0.75 if i > 0 else 1.0)
+            g = evaluate(xs[i + 1], i, i < n_iter - 1, own_grad=True)
+            if g is not None:
+                gs.append(g)
+            if verbose:
+                _report(state, i, norm, n_fts)
+        x_best, x_best_adv = torch.empty_like(x), torch.empty_like(x)
+        be.gather_best(xs, x_best, x_best_adv, state)
+        return finish(x_best, x_best_adv)
+
+    buf_a, buf_b = torch.empty_like(x), torch.empty_like(x)
+    x_best, x_best_adv, grad_best = torch.empty_like(x), torch.empty_like(x), torch.empty_like(x)
+    be.init(x, buf_a, state, step_full, topk0)
     grad = evaluate(buf_a, -1, True)
     cur, old, first = buf_a, buf_a, True
     for i in range(n_iter):
@@ -165,13 +197,7 @@ def run_apgd(be, model, x, y, norm, eps, n_iter=10, use_rs=False, loss='ce', ver
         if verbose:
             _report(state, i, norm, n_fts)
     be.flush_best(cur, x_best, x_best_adv, state)
-
-    acc = state[_abi.ST_ACC].view(torch.int32) != 0
-    loss_best = state[_abi.ST_LOSS_BEST].clone()
-    if verbose:
-        times['total'] = time.time() - t_total
-        print(' '.join(f'{k}={v:.5f} s' for k, v in times.items()))
-    return x_best, acc, loss_best, x_best_adv
+    return finish(x_best, x_best_adv)
 
 
 def _report(state, i, norm, n_fts):

@@ -34,6 +34,24 @@ __global__ void __launch_bounds__(kThreads) linf_step_kernel(B200atImages p, int
 }
 
 template <int VEC>
+__global__ void __launch_bounds__(kThreads) linf_log_kernel(B200atSlots sl, const float* __restrict__ x,
+                                                             float* __restrict__ x_new, const float* __restrict__ st,
+                                                             int64_t B, int64_t n, int64_t nvec, float eps, float a,
+                                                             float one_minus_a) {
+  const int64_t vi = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (vi < nvec) b200at_linf_log_body<VEC>(sl, x, x_new, st, B, n, vi, eps, a, one_minus_a);
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(kThreads) gather_kernel(B200atSlots sl, float* __restrict__ x_best,
+                                                           float* __restrict__ x_best_adv,
+                                                           const float* __restrict__ st, int64_t B, int64_t n,
+                                                           int64_t nvec) {
+  const int64_t vi = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (vi < nvec) b200at_gather_body<VEC>(sl, x_best, x_best_adv, st, B, n, vi);
+}
+
+template <int VEC>
 __global__ void __launch_bounds__(kThreads) flush_kernel(B200atImages p, int64_t nvec) {
   const int64_t vi = (int64_t)blockIdx.x * kThreads + threadIdx.x;
   if (vi < nvec) b200at_flush_body<VEC>(p, vi);
@@ -573,7 +591,7 @@ __global__ void __launch_bounds__(128) loss_bookkeep_kernel(LossArgs p) {
   if (lane == 0) {
     if (p.loss_out) p.loss_out[b] = loss;
     b200at_bookkeep_sample(p.st, p.loss_steps, p.B, b, loss, pred, p.iter, p.n_iter, p.ckpt_k, p.norm_kind,
-                           p.step_full, p.step_min, p.n_fts);
+                           p.step_full, p.step_min, p.n_fts, p.dlogits != nullptr);
   }
 }
 
@@ -612,6 +630,43 @@ int b200at_linf_step(const float* x, float* x_adv, const float* x_old, float* x_
   const int64_t nvec = v4 ? B * n / 4 : B * n;
   if (v4) linf_step_kernel<4><<<grid_for(nvec, kThreads), kThreads, 0, s>>>(p, nvec, eps, a, oma);
   else linf_step_kernel<1><<<grid_for(nvec, kThreads), kThreads, 0, s>>>(p, nvec, eps, a, oma);
+  return (int)cudaGetLastError();
+}
+
+static bool fill_slots(B200atSlots& sl, const float* const* xs, const float* const* gs, int n_slots, bool& v4) {
+  if (n_slots < 1 || n_slots > B200AT_LOG_MAX_SLOTS) return false;
+  for (int i = 0; i < B200AT_LOG_MAX_SLOTS; ++i) {
+    sl.x[i] = xs[i < n_slots ? i : 0];
+    sl.g[i] = gs ? gs[i < n_slots ? i : 0] : nullptr;
+    v4 = v4 && aligned16(sl.x[i]) && (!gs || aligned16(sl.g[i]));
+  }
+  return true;
+}
+
+int b200at_linf_step_log(const float* x, const float* const* x_slots, const float* const* g_slots, int n_slots,
+                         float* x_new, const float* state, int64_t B, int64_t n, float eps, float a, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if (B <= 0 || n <= 0) return (int)cudaSuccess;
+  B200atSlots sl;
+  bool v4 = (n % 4 == 0) && aligned16(x) && aligned16(x_new);
+  if (!fill_slots(sl, x_slots, g_slots, n_slots, v4)) return (int)cudaErrorInvalidValue;
+  const float oma = (float)(1.0 - (double)a);
+  const int64_t nvec = v4 ? B * n / 4 : B * n;
+  if (v4) linf_log_kernel<4><<<grid_for(nvec, kThreads), kThreads, 0, s>>>(sl, x, x_new, state, B, n, nvec, eps, a, oma);
+  else linf_log_kernel<1><<<grid_for(nvec, kThreads), kThreads, 0, s>>>(sl, x, x_new, state, B, n, nvec, eps, a, oma);
+  return (int)cudaGetLastError();
+}
+
+int b200at_gather_best(const float* const* x_slots, int n_slots, float* x_best, float* x_best_adv,
+                       const float* state, int64_t B, int64_t n, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if (B <= 0 || n <= 0) return (int)cudaSuccess;
+  B200atSlots sl;
+  bool v4 = (n % 4 == 0) && aligned16(x_best) && aligned16(x_best_adv);
+  if (!fill_slots(sl, x_slots, nullptr, n_slots, v4)) return (int)cudaErrorInvalidValue;
+  const int64_t nvec = v4 ? B * n / 4 : B * n;
+  if (v4) gather_kernel<4><<<grid_for(nvec, kThreads), kThreads, 0, s>>>(sl, x_best, x_best_adv, state, B, n, nvec);
+  else gather_kernel<1><<<grid_for(nvec, kThreads), kThreads, 0, s>>>(sl, x_best, x_best_adv, state, B, n, nvec);
   return (int)cudaGetLastError();
 }
 

@@ -219,3 +219,43 @@ B200AT_HD float b200at_l2_body(const B200atImages& p, int64_t vi, float eps, flo
   if (PHASE == 3) b200at_st_keep<VEC>(p.x_new + e, o);
   return acc;
 }
+
+// ---- iterate-log variants (n_iter + 1 <= B200AT_LOG_MAX_SLOTS): no image copies at all -------------
+struct B200atSlots {
+  const float* x[B200AT_LOG_MAX_SLOTS];   // iterates x_adv^(0..)
+  const float* g[B200AT_LOG_MAX_SLOTS];   // gradients at those iterates
+};
+
+// K1 (log): x_new = move(x, x_adv, x_adv_old, grad) with the three operands picked per sample by slot
+// index.  Exactly 20 B/element (16 on the first move, where x_old and x_adv are the same slot).
+template <int VEC>
+B200AT_HD void b200at_linf_log_body(const B200atSlots& sl, const float* x, float* x_new, const float* st, int64_t B,
+                                    int64_t n, int64_t vi, float eps, float a, float one_minus_a) {
+  const int64_t e = vi * VEC;
+  const int b = (int)(e / n);
+  const float step = st[(int64_t)B200AT_ST_STEP * B + b];
+  const int ic = b200at_f2i(st[(int64_t)B200AT_ST_IDX_CUR * B + b]) & (B200AT_LOG_MAX_SLOTS - 1);
+  const int io = b200at_f2i(st[(int64_t)B200AT_ST_IDX_OLD * B + b]) & (B200AT_LOG_MAX_SLOTS - 1);
+  const int ig = b200at_f2i(st[(int64_t)B200AT_ST_GIDX_CUR * B + b]) & (B200AT_LOG_MAX_SLOTS - 1);
+  const B200atVec<VEC> xv = b200at_ld_stream<VEC>(x + e);
+  const B200atVec<VEC> xc = b200at_ld_stream<VEC>(sl.x[ic] + e);
+  const B200atVec<VEC> xo = (io == ic) ? xc : b200at_ld_stream<VEC>(sl.x[io] + e);
+  const B200atVec<VEC> g = b200at_ld_stream<VEC>(sl.g[ig] + e);
+  B200atVec<VEC> o;
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) o.v[i] = b200at_linf_elem(xv.v[i], xc.v[i], xo.v[i], g.v[i], step, eps, a, one_minus_a);
+  b200at_st_keep<VEC>(x_new + e, o);
+}
+
+// final assembly: x_best[b] = slot[idx_best[b]][b], x_best_adv[b] = slot[idx_best_adv[b]][b]
+template <int VEC>
+B200AT_HD void b200at_gather_body(const B200atSlots& sl, float* x_best, float* x_best_adv, const float* st,
+                                  int64_t B, int64_t n, int64_t vi) {
+  const int64_t e = vi * VEC;
+  const int b = (int)(e / n);
+  const int ib = b200at_f2i(st[(int64_t)B200AT_ST_IDX_BEST * B + b]) & (B200AT_LOG_MAX_SLOTS - 1);
+  const int ia = b200at_f2i(st[(int64_t)B200AT_ST_IDX_BEST_ADV * B + b]) & (B200AT_LOG_MAX_SLOTS - 1);
+  const B200atVec<VEC> vb = b200at_ld_stream<VEC>(sl.x[ib] + e);
+  b200at_st_keep<VEC>(x_best + e, vb);
+  b200at_st_stream<VEC>(x_best_adv + e, (ia == ib) ? vb : b200at_ld_stream<VEC>(sl.x[ia] + e));
+}

@@ -45,8 +45,17 @@ enum {
   B200AT_ST_SP_BEST = 9,         // int32 l1: nnz(x_best - x)
   B200AT_ST_SP_ADV = 10,         // int32 l1: nnz(x_adv - x), written by the step kernel
   B200AT_ST_PRED = 11,           // int32 0/1 prediction correct at the current iterate
-  B200AT_ST_ROWS = 16
+  // iterate-log protocol (small n_iter): every iterate / gradient stays in its own slot and the
+  // image ops of :304,:321-324,:345-346 become per-sample slot indices (int32) instead of copies
+  B200AT_ST_IDX_CUR = 12,        // slot holding this sample's x_adv (differs from the newest slot after a restore)
+  B200AT_ST_IDX_OLD = 13,        // slot holding x_adv_old
+  B200AT_ST_IDX_BEST = 14,       // slot holding x_best
+  B200AT_ST_IDX_BEST_ADV = 15,   // slot holding x_best_adv
+  B200AT_ST_GIDX_CUR = 16,       // slot holding grad
+  B200AT_ST_GIDX_BEST = 17,      // slot holding grad_best
+  B200AT_ST_ROWS = 20
 };
+#define B200AT_LOG_MAX_SLOTS 8
 enum {
   B200AT_F_IMPROVED = 1,   // x_best <- x_adv, grad_best <- grad   (:321-324)
   B200AT_F_WRITE_ADV = 2,  // x_best_adv <- x_adv                  (:304)
@@ -79,9 +88,10 @@ B200AT_HD float b200at_linf_elem(float x, float xc, float xo, float g, float ste
 // Per-sample bookkeeping after a forward pass (:194-205 for iter < 0, :291-364 otherwise).
 // `loss_steps` is [n_iter][B].  ckpt_k > 0 marks a checkpoint iteration with window k.
 // step_full = float32(alpha*eps), step_min = float32(alpha*eps/10) (l1 only).
+// has_grad: a new gradient is being computed at this iterate (false on the last iteration, :281-283).
 B200AT_HD void b200at_bookkeep_sample(float* st, float* loss_steps, int B, int b, float loss, int pred,
                                       int iter, int n_iter, int ckpt_k, int norm_kind, float step_full,
-                                      float step_min, float n_fts) {
+                                      float step_min, float n_fts, int has_grad) {
   float* step = st + (int64_t)B200AT_ST_STEP * B + b;
   float* loss_best = st + (int64_t)B200AT_ST_LOSS_BEST * B + b;
   float* loss_best_last = st + (int64_t)B200AT_ST_LOSS_BEST_LAST * B + b;
@@ -92,8 +102,20 @@ B200AT_HD void b200at_bookkeep_sample(float* st, float* loss_steps, int B, int b
   const float* sp_adv = st + (int64_t)B200AT_ST_SP_ADV * B + b;
   st[(int64_t)B200AT_ST_LOSS_CUR * B + b] = loss;
   st[(int64_t)B200AT_ST_PRED * B + b] = b200at_i2f(pred);
+  float* idx_cur = st + (int64_t)B200AT_ST_IDX_CUR * B + b;
+  float* idx_old = st + (int64_t)B200AT_ST_IDX_OLD * B + b;
+  float* idx_best = st + (int64_t)B200AT_ST_IDX_BEST * B + b;
+  float* idx_best_adv = st + (int64_t)B200AT_ST_IDX_BEST_ADV * B + b;
+  float* gidx_cur = st + (int64_t)B200AT_ST_GIDX_CUR * B + b;
+  float* gidx_best = st + (int64_t)B200AT_ST_GIDX_BEST * B + b;
+  // the iterate just evaluated lives in slot iter+1; the move that produced it read x_adv from idx_cur
+  const float slot = b200at_i2f(iter + 1);
+  if (iter >= 0) *idx_old = *idx_cur;
+  *idx_cur = slot;
+  if (has_grad) *gidx_cur = slot;
 
-  if (iter < 0) {  // first evaluation: everything "improves" so the next pass seeds x_best/grad_best/x_best_adv
+  if (iter < 0) {
+    *idx_old = slot; *idx_best = slot; *idx_best_adv = slot; *gidx_best = slot;  // first evaluation: everything "improves" so the next pass seeds x_best/grad_best/x_best_adv
     *acc = b200at_i2f(pred);
     *loss_best = loss;
     *loss_best_last = loss;
@@ -104,12 +126,14 @@ B200AT_HD void b200at_bookkeep_sample(float* st, float* loss_steps, int B, int b
   }
   int32_t fl = 0;
   *acc = b200at_i2f(b200at_f2i(*acc) & pred);
-  if (!pred) fl |= B200AT_F_WRITE_ADV;
+  if (!pred) { fl |= B200AT_F_WRITE_ADV; *idx_best_adv = slot; }
   loss_steps[(int64_t)iter * B + b] = loss;
   if (loss > *loss_best) {  // strict; false for NaN
     fl |= B200AT_F_IMPROVED;
     *loss_best = loss;
     *sp_best = *sp_adv;
+    *idx_best = slot;
+    *gidx_best = *gidx_cur;  // the gradient just computed, or the stale one on the last iteration (:323)
   }
   if (ckpt_k > 0) {
     if (norm_kind != B200AT_NORM_L1) {
@@ -143,6 +167,7 @@ B200AT_HD void b200at_bookkeep_sample(float* st, float* loss_steps, int B, int b
       if (red) fl |= B200AT_F_RESTORE;
     }
   }
+  if (fl & B200AT_F_RESTORE) { *idx_cur = *idx_best; *gidx_cur = *gidx_best; }
   *flags = b200at_i2f(fl);
 }
 

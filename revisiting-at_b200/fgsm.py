@@ -4,6 +4,7 @@ binds it with partial(eps, use_rs=True, alpha, noise_level, skip_projection)).""
 import torch
 
 from . import _abi
+from .ops import input_grad_only
 
 
 class CudaFgsmBackend:
@@ -36,7 +37,7 @@ def run_fgsm(be, model, x, y, eps, loss='ce', alpha=1.25, use_rs=False, noise_le
     else:
         x_adv.copy_(x)
     xin = x_adv.requires_grad_()
-    with torch.enable_grad():
+    with torch.enable_grad(), input_grad_only():
         logits = model(xin)
     lg = logits.detach().contiguous()
     dl = torch.empty_like(lg)

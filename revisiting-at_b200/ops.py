@@ -18,6 +18,26 @@ from . import _abi
 
 BF16 = torch.bfloat16
 
+# Custom autograd Functions cannot see which gradients a particular torch.autograd.grad call wants
+# (`needs_input_grad` only says which inputs require grad), so the attack -- whose backward is input-grad
+# only (autopgd_train_clean.py:185,283) -- declares it here and the Functions skip every weight gradient.
+_INPUT_GRAD_ONLY = [False]
+
+
+class input_grad_only:
+    """Context manager: forwards run under it promise that only dL/dx will be asked of their graph."""
+    def __enter__(self):
+        self.prev = _INPUT_GRAD_ONLY[0]
+        _INPUT_GRAD_ONLY[0] = True
+
+    def __exit__(self, *exc):
+        _INPUT_GRAD_ONLY[0] = self.prev
+        return False
+
+
+def _wants(ctx, *idx):
+    return ctx.param_grads and any(ctx.needs_input_grad[i] for i in idx)
+
 
 def _need_cuda(x):
     if not x.is_cuda:
@@ -36,6 +56,7 @@ class _LayerNorm(Function):
         _abi.ln_fwd(x, wf, bf, y, mean, rstd, eps, gelu)
         ctx.save_for_backward(x, wf, bf, mean, rstd)
         ctx.gelu = gelu
+        ctx.param_grads = not _INPUT_GRAD_ONLY[0]
         return y
 
     @staticmethod
@@ -43,7 +64,7 @@ class _LayerNorm(Function):
         x, wf, bf, mean, rstd = ctx.saved_tensors
         dy = dy.contiguous()
         dx = torch.empty_like(x)
-        pg = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
+        pg = _wants(ctx, 1, 2)
         dw = torch.zeros_like(wf) if pg else None
         db = torch.zeros_like(bf) if pg else None
         _abi.ln_bwd(dy, x, wf, bf, mean, rstd, dx, dw, db, ctx.gelu)
@@ -64,6 +85,7 @@ class _DwConv7(Function):
         y = torch.empty_like(x)
         _abi.dwconv7_fwd(x, wt, b.detach().float().contiguous(), y)
         ctx.save_for_backward(x, wt)
+        ctx.param_grads = not _INPUT_GRAD_ONLY[0]
         return y
 
     @staticmethod
@@ -74,7 +96,7 @@ class _DwConv7(Function):
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
             _abi.dwconv7_fwd(dy, wt.flip(0).contiguous(), None, dx)        # correlation with the flipped taps
-        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+        if _wants(ctx, 1, 2):
             C = x.shape[-1]
             dwt = torch.zeros(49, C, device=x.device, dtype=torch.float32)
             db = torch.zeros(C, device=x.device, dtype=torch.float32)
@@ -91,6 +113,7 @@ class _BiasGelu(Function):
         h = torch.empty_like(z)
         _abi.bias_gelu_fwd(z, bf, h)
         ctx.save_for_backward(z, bf)
+        ctx.param_grads = not _INPUT_GRAD_ONLY[0]
         return h
 
     @staticmethod
@@ -98,7 +121,7 @@ class _BiasGelu(Function):
         z, bf = ctx.saved_tensors
         dz = torch.empty_like(z)
         _abi.bias_gelu_bwd(dh.contiguous(), z, bf, dz)
-        db = dz.sum(0, dtype=torch.float32) if ctx.needs_input_grad[1] else None
+        db = dz.sum(0, dtype=torch.float32) if _wants(ctx, 1) else None
         return dz, db
 
 
@@ -110,8 +133,8 @@ class _ScaleResidual(Function):
         bf, gf = bias.detach().float().contiguous(), gamma.detach().float().contiguous()
         out = torch.empty_like(z)
         _abi.scale_residual_fwd(z, bf, gf, res, out)
-        pg = bias.requires_grad or gamma.requires_grad
-        ctx.save_for_backward(z if pg else None, bf, gf)
+        ctx.param_grads = (not _INPUT_GRAD_ONLY[0]) and (bias.requires_grad or gamma.requires_grad)
+        ctx.save_for_backward(z if ctx.param_grads else None, bf, gf)
         return out
 
     @staticmethod
@@ -121,7 +144,7 @@ class _ScaleResidual(Function):
         dz = torch.empty_like(dout)
         _abi.scale_bwd(dout, gf, dz)
         dbias = dgamma = None
-        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+        if _wants(ctx, 1, 2):
             d32 = dout.float()
             col = d32.sum(0)
             dbias = col * gf

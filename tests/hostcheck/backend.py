@@ -30,7 +30,11 @@ class HostBackend:
         self.L.hc_init.argtypes = [P, P, P, I64, I64, Fl, Fl, I]
         self.L.hc_linf_step.argtypes = [P] * 9 + [I64, I64, Fl, Fl, I]
         self.L.hc_flush.argtypes = [P, P, P, P, I64, I64, I]
-        self.L.hc_bookkeep.argtypes = [P, P, I64, P, P, I, I, I, I, Fl, Fl, I64]
+        self.L.hc_bookkeep.argtypes = [P, P, I64, P, P, I, I, I, I, Fl, Fl, I64, I]
+        self.L.hc_linf_step_log.argtypes = [P, P, P, I, P, P, I64, I64, Fl, Fl, I]
+        self.L.hc_linf_step_log.restype = None
+        self.L.hc_gather_best.argtypes = [P, I, P, P, P, I64, I64, I]
+        self.L.hc_gather_best.restype = None
         self.L.hc_l2_step.argtypes = [P] * 10 + [I64, I64, Fl, Fl, I]
         self.L.hc_l2_step.restype = None
         self.L.hc_l1_step.argtypes = [P] * 8 + [I64, I64, Fl]
@@ -71,6 +75,21 @@ class HostBackend:
                           _p(x_best_adv), _p(state), B, n, eps)
         return scratch
 
+    @staticmethod
+    def _ptrs(ts):
+        return (c_void_p * len(ts))(*[t.data_ptr() for t in ts])
+
+    def linf_step_log(self, x, x_slots, g_slots, x_new, state, eps, a):
+        B, n = x.shape[0], x[0].numel()
+        assert all(t.is_contiguous() for t in list(x_slots) + list(g_slots))
+        self.L.hc_linf_step_log(_p(x), self._ptrs(x_slots), self._ptrs(g_slots), len(x_slots), _p(x_new), _p(state),
+                                B, n, eps, a, self._vec(n))
+
+    def gather_best(self, x_slots, x_best, x_best_adv, state):
+        B, n = x_best.shape[0], x_best[0].numel()
+        self.L.hc_gather_best(self._ptrs(x_slots), len(x_slots), _p(x_best), _p(x_best_adv), _p(state), B, n,
+                              self._vec(n))
+
     def flush_best(self, x_adv, x_best, x_best_adv, state):
         B, n = x_adv.shape[0], x_adv[0].numel()
         self.L.hc_flush(_p(x_adv), _p(x_best), _p(x_best_adv), _p(state), B, n, self._vec(n))
@@ -89,7 +108,7 @@ class HostBackend:
         pred = (z.detach().max(1)[1] == label).to(torch.int32).contiguous()
         li = li.detach().contiguous()
         self.L.hc_bookkeep(_p(state), _p(loss_steps), logits.shape[0], _p(li), _p(pred), it, n_iter, ckpt_k,
-                           NORMS[norm], step_full, step_min, n_fts)
+                           NORMS[norm], step_full, step_min, n_fts, int(dlogits is not None))
 
     # fgsm backend surface
     def start(self, x, noise, x_adv, eps, noise_level, skip):

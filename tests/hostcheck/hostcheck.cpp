@@ -124,10 +124,32 @@ void hc_flush(const float* x_adv, float* x_best, float* x_best_adv, const float*
 }
 
 void hc_bookkeep(float* st, float* loss_steps, int64_t B, const float* loss, const int* pred, int iter, int n_iter,
-                 int ckpt_k, int norm_kind, float step_full, float step_min, int64_t n_fts) {
+                 int ckpt_k, int norm_kind, float step_full, float step_min, int64_t n_fts, int has_grad) {
   for (int64_t b = 0; b < B; ++b)
     b200at_bookkeep_sample(st, loss_steps, (int)B, (int)b, loss[b], pred[b], iter, n_iter, ckpt_k, norm_kind,
-                           step_full, step_min, (float)n_fts);
+                           step_full, step_min, (float)n_fts, has_grad);
+}
+
+static void fill(B200atSlots& sl, const float* const* xs, const float* const* gs, int n_slots) {
+  for (int i = 0; i < B200AT_LOG_MAX_SLOTS; ++i) {
+    sl.x[i] = xs[i < n_slots ? i : 0];
+    sl.g[i] = gs ? gs[i < n_slots ? i : 0] : nullptr;
+  }
+}
+
+void hc_linf_step_log(const float* x, const float* const* xs, const float* const* gs, int n_slots, float* x_new,
+                      const float* st, int64_t B, int64_t n, float eps, float a, int vec) {
+  B200atSlots sl; fill(sl, xs, gs, n_slots);
+  const float oma = (float)(1.0 - (double)a);
+  if (vec == 4) for (int64_t v = 0; v < B * n / 4; ++v) b200at_linf_log_body<4>(sl, x, x_new, st, B, n, v, eps, a, oma);
+  else for (int64_t v = 0; v < B * n; ++v) b200at_linf_log_body<1>(sl, x, x_new, st, B, n, v, eps, a, oma);
+}
+
+void hc_gather_best(const float* const* xs, int n_slots, float* x_best, float* x_best_adv, const float* st, int64_t B,
+                    int64_t n, int vec) {
+  B200atSlots sl; fill(sl, xs, nullptr, n_slots);
+  if (vec == 4) for (int64_t v = 0; v < B * n / 4; ++v) b200at_gather_body<4>(sl, x_best, x_best_adv, st, B, n, v);
+  else for (int64_t v = 0; v < B * n; ++v) b200at_gather_body<1>(sl, x_best, x_best_adv, st, B, n, v);
 }
 
 void hc_fgsm_start(const float* x, const float* noise, float* x_adv, int64_t total, float eps, float nl, int skip,

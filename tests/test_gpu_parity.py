@@ -82,6 +82,46 @@ def test_cnn_loop_fp32(product, cuda_dev, name):
     assert all(p.grad is None for p in model.parameters())
 
 
+@pytest.mark.parametrize('name', golden_names('scripted_linf'))
+def test_scripted_bit_exact_copying_kernels(cuda_dev, name):
+    """same fixtures forced through the copying kernels (b200at_linf_step + flush), the path of long attacks"""
+    from revisiting_at_b200 import attack
+    g = golden(name)
+    model = ScriptedModel(_t(g['logits'], cuda_dev), _t(g['grads'], cuda_dev))
+    out = attack.run_apgd(attack._CUDA, model, _t(g['x'], cuda_dev), _t(g['y'], cuda_dev), 'Linf', float(g['eps']),
+                          n_iter=int(g['n_iter']), loss=str(g['loss']),
+                          mixup=(object() if bool(g['soft']) else None), log_slots=0)
+    assert same(torch.stack(model.seen), _t(g['x_calls']))
+    assert same(out[0], _t(g['x_best'])) and same(out[3], _t(g['x_best_adv'])) and same(out[1], _t(g['acc']))
+
+
+def test_raw_log_kernels_vs_host_bodies(cuda_dev):
+    """b200at_linf_step_log / b200at_gather_best with every slot combination against the host build."""
+    from hostcheck.backend import HostBackend
+    from revisiting_at_b200 import _abi
+    hb = HostBackend(4)
+    B, shape, eps = 27, (3, 32, 32), 4 / 255.
+    g = torch.Generator().manual_seed(9)
+    x = torch.rand(B, *shape, generator=g)
+    xs = [(x + (torch.rand(B, *shape, generator=g) * 2 - 1) * eps).clamp(0, 1) for _ in range(3)]
+    gs = [torch.randn(B, *shape, generator=g) * 1e-3 for _ in range(2)]
+    st = torch.zeros(_abi.ST_ROWS, B)
+    st[_abi.ST_STEP] = torch.tensor([2 * eps, eps, eps / 2] * 9)
+    idx = torch.arange(B, dtype=torch.int32)
+    for row, v in ((_abi.ST_IDX_CUR, idx % 3), (_abi.ST_IDX_OLD, (idx // 3) % 3), (_abi.ST_GIDX_CUR, (idx // 9) % 2),
+                   (_abi.ST_IDX_BEST, (idx + 1) % 3), (_abi.ST_IDX_BEST_ADV, (idx // 2) % 3)):
+        st[row] = v.view(torch.float32)
+    want, wb, wa = torch.empty_like(x), torch.empty_like(x), torch.empty_like(x)
+    hb.linf_step_log(x, xs, gs + [gs[0]], want, st, eps, 0.75)
+    hb.gather_best(xs, wb, wa, st)
+    d = lambda t: t.to(cuda_dev)
+    got, gb_, ga = torch.empty_like(x, device=cuda_dev), torch.empty_like(x, device=cuda_dev), torch.empty_like(x, device=cuda_dev)
+    _abi.linf_step_log(d(x), [d(t) for t in xs], [d(t) for t in gs], got, d(st), eps, 0.75)
+    _abi.gather_best([d(t) for t in xs], gb_, ga, d(st))
+    torch.cuda.synchronize()
+    assert torch.equal(got.cpu(), want) and torch.equal(gb_.cpu(), wb) and torch.equal(ga.cpu(), wa)
+
+
 def test_raw_linf_kernel_vs_host_bodies_all_flag_combinations(cuda_dev):
     """Raw C ABI, 16 x 3x224x224, every pending-flag combination, against the host build of the bodies."""
     from hostcheck.backend import HostBackend
