@@ -21,8 +21,13 @@ def main():
         except (KeyError, ValueError):
             continue
         v *= {'ns': 1.0, 'us': 1e3, 'ms': 1e6, 's': 1e9}.get(row['Metric Unit'], 1.0)
-        name = re.sub(r'\(.*', '', re.sub(r'<.*', '', row['Kernel Name']))
-        name = name.replace('void ', '').strip()[:80]
+        name = row['Kernel Name'].replace('void ', '').replace('<unnamed>::', '')
+        if name.startswith('at::'):
+            m = re.search(r'(reduce_kernel|vectorized_layer_norm_kernel|layer_norm_grad\w*|GammaBeta\w*|\w+Functor\w*|'
+                          r'\w*copy_kernel\w*|\w*[Gg]elu\w*|\w+_kernel_cuda\w*|index\w+|multi_tensor\w*)', name)
+            name = 'at::' + (m.group(1) if m else name[4:64])
+        else:
+            name = re.sub(r'\(.*', '', name)[:80]
         agg[name][0] += 1
         agg[name][1] += v
         tot += v
