@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(kThreads) linf_step_kernel(B200atImages p, int
 }
 
 template <int VEC>
-__global__ void __launch_bounds__(kThreads) linf_log_kernel(B200atSlots sl, const float* __restrict__ x,
+__global__ void __launch_bounds__(kThreads, 8) linf_log_kernel(B200atSlots sl, const float* __restrict__ x,
                                                              float* __restrict__ x_new, const float* __restrict__ st,
                                                              int64_t B, int64_t n, int64_t nvec, float eps, float a,
                                                              float one_minus_a) {

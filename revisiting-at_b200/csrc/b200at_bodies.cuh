@@ -226,6 +226,18 @@ struct B200atSlots {
   const float* g[B200AT_LOG_MAX_SLOTS];   // gradients at those iterates
 };
 
+// Slot pick without dynamic indexing of the kernel-parameter struct (that would spill the struct to local
+// memory): 3-level select tree over the 8 constant-indexed pointers.
+B200AT_HD const float* b200at_pick(const float* const* a, int i) {
+  const float* a01 = (i & 1) ? a[1] : a[0];
+  const float* a23 = (i & 1) ? a[3] : a[2];
+  const float* a45 = (i & 1) ? a[5] : a[4];
+  const float* a67 = (i & 1) ? a[7] : a[6];
+  const float* lo = (i & 2) ? a23 : a01;
+  const float* hi = (i & 2) ? a67 : a45;
+  return (i & 4) ? hi : lo;
+}
+
 // K1 (log): x_new = move(x, x_adv, x_adv_old, grad) with the three operands picked per sample by slot
 // index.  Exactly 20 B/element (16 on the first move, where x_old and x_adv are the same slot).
 template <int VEC>
@@ -238,9 +250,9 @@ B200AT_HD void b200at_linf_log_body(const B200atSlots& sl, const float* x, float
   const int io = b200at_f2i(st[(int64_t)B200AT_ST_IDX_OLD * B + b]) & (B200AT_LOG_MAX_SLOTS - 1);
   const int ig = b200at_f2i(st[(int64_t)B200AT_ST_GIDX_CUR * B + b]) & (B200AT_LOG_MAX_SLOTS - 1);
   const B200atVec<VEC> xv = b200at_ld_stream<VEC>(x + e);
-  const B200atVec<VEC> xc = b200at_ld_stream<VEC>(sl.x[ic] + e);
-  const B200atVec<VEC> xo = (io == ic) ? xc : b200at_ld_stream<VEC>(sl.x[io] + e);
-  const B200atVec<VEC> g = b200at_ld_stream<VEC>(sl.g[ig] + e);
+  const B200atVec<VEC> xc = b200at_ld_stream<VEC>(b200at_pick(sl.x, ic) + e);
+  const B200atVec<VEC> xo = (io == ic) ? xc : b200at_ld_stream<VEC>(b200at_pick(sl.x, io) + e);
+  const B200atVec<VEC> g = b200at_ld_stream<VEC>(b200at_pick(sl.g, ig) + e);
   B200atVec<VEC> o;
 #pragma unroll
   for (int i = 0; i < VEC; ++i) o.v[i] = b200at_linf_elem(xv.v[i], xc.v[i], xo.v[i], g.v[i], step, eps, a, one_minus_a);
@@ -255,7 +267,7 @@ B200AT_HD void b200at_gather_body(const B200atSlots& sl, float* x_best, float* x
   const int b = (int)(e / n);
   const int ib = b200at_f2i(st[(int64_t)B200AT_ST_IDX_BEST * B + b]) & (B200AT_LOG_MAX_SLOTS - 1);
   const int ia = b200at_f2i(st[(int64_t)B200AT_ST_IDX_BEST_ADV * B + b]) & (B200AT_LOG_MAX_SLOTS - 1);
-  const B200atVec<VEC> vb = b200at_ld_stream<VEC>(sl.x[ib] + e);
+  const B200atVec<VEC> vb = b200at_ld_stream<VEC>(b200at_pick(sl.x, ib) + e);
   b200at_st_keep<VEC>(x_best + e, vb);
-  b200at_st_stream<VEC>(x_best_adv + e, (ia == ib) ? vb : b200at_ld_stream<VEC>(sl.x[ia] + e));
+  b200at_st_stream<VEC>(x_best_adv + e, (ia == ib) ? vb : b200at_ld_stream<VEC>(b200at_pick(sl.x, ia) + e));
 }
