@@ -40,9 +40,10 @@ int b200at_add_bf16(const void* a, const void* b, void* c, int64_t total, void* 
 
 /* models/convnext.py:28,39 `self.dwconv` (7x7 depthwise, pad 3) on NHWC bf16.  wt is tap-major fp32 [49][C]
  * (wt[i*7+j][c] = weight[c,0,i,j]); bias may be null.  The input gradient is the same call with the taps
- * flipped (wt'[i*7+j] = wt[(6-i)*7+(6-j)]) and bias = null.  C % 32 == 0. */
-int b200at_dwconv7_fwd(const void* x, const float* wt, const float* bias, void* y, int64_t B, int64_t H, int64_t W,
-                       int64_t C, void* stream);
+ * flipped (wt'[i*7+j] = wt[(6-i)*7+(6-j)]) and bias = null; `add` (nullable, same shape as y) is summed into
+ * the result -- the residual-gradient join of the block (models/convnext.py:49).  C % 32 == 0. */
+int b200at_dwconv7_fwd(const void* x, const float* wt, const float* bias, const void* add, void* y, int64_t B,
+                       int64_t H, int64_t W, int64_t C, void* stream);
 /* weight / bias gradients, ACCUMULATED into dw [49][C] and db [C] (fp32, caller zeroes) */
 int b200at_dwconv7_wgrad(const void* x, const void* dy, float* dw, float* db, int64_t B, int64_t H, int64_t W,
                          int64_t C, void* stream);

@@ -95,7 +95,7 @@ def _declare(L):
         'b200at_scale_residual_fwd': [P, P, P, P, P, I64, I64, P],
         'b200at_scale_bwd': [P, P, P, I64, I64, P],
         'b200at_add_bf16': [P, P, P, I64, P],
-        'b200at_dwconv7_fwd': [P, P, P, P, I64, I64, I64, I64, P],
+        'b200at_dwconv7_fwd': [P, P, P, P, P, I64, I64, I64, I64, P],
         'b200at_dwconv7_wgrad': [P, P, P, P, I64, I64, I64, I64, P],
     })
     for name, args in sig.items():
@@ -308,10 +308,11 @@ def add_bf16(a, b, c):
         _check(lib().b200at_add_bf16(_act(a, 'a'), _act(b, 'b'), _act(c, 'c'), a.numel(), _stream()), 'add_bf16')
 
 
-def dwconv7_fwd(x, wt, bias, y):
+def dwconv7_fwd(x, wt, bias, y, add=None):
     B, H, W, C = x.shape
     with _Timed('dwconv7'):
-        _check(lib().b200at_dwconv7_fwd(_act(x, 'x'), _par(wt, 'wt', 49 * C), _par(bias, 'bias', C), _act(y, 'y'),
+        _check(lib().b200at_dwconv7_fwd(_act(x, 'x'), _par(wt, 'wt', 49 * C), _par(bias, 'bias', C),
+                                        _act(add, 'add') if add is not None else c_void_p(0), _act(y, 'y'),
                                         B, H, W, C, _stream()), 'dwconv7_fwd')
 
 

@@ -44,20 +44,29 @@ __device__ __forceinline__ uint2 pack4(const float* f) {
 }
 
 // ------------------------------------------------------------------------------------------------ K8
-// One warp per pixel row of C channels; lane holds VPL 8-byte vectors (4 bf16 each) in registers.
-constexpr int kLnWarps = 8;
+// A group of G lanes (4/8/16/32) owns one pixel row of C channels; each lane holds VPL 8-byte vectors
+// (4 bf16) in registers, so a warp works on 32/G rows at once (small C: more rows in flight per warp).
+constexpr int kLnThreads = 256;
 
-template <int VPL, bool GELU>
-__global__ void __launch_bounds__(kLnWarps * 32) ln_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ w,
-                                                               const float* __restrict__ b, bf16* __restrict__ y,
-                                                               float* __restrict__ mean, float* __restrict__ rstd,
-                                                               int64_t M, int C, float eps) {
-  const int lane = threadIdx.x & 31;
+template <int G>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <int G, int VPL, bool GELU>
+__global__ void __launch_bounds__(kLnThreads) ln_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ w,
+                                                            const float* __restrict__ b, bf16* __restrict__ y,
+                                                            float* __restrict__ mean, float* __restrict__ rstd,
+                                                            int64_t M, int C, float eps) {
+  const int gl = threadIdx.x % G;                       // lane within the row group
   const int nv = C >> 2;
+  constexpr int kRows = kLnThreads / G;                 // rows per CTA iteration
   float wr[VPL][4], br[VPL][4];
 #pragma unroll
   for (int j = 0; j < VPL; ++j) {
-    const int v = lane + 32 * j;
+    const int v = gl + G * j;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       wr[j][k] = v < nv ? w[v * 4 + k] : 0.f;
@@ -65,35 +74,38 @@ __global__ void __launch_bounds__(kLnWarps * 32) ln_fwd_kernel(const bf16* __res
     }
   }
   const float inv_c = 1.0f / (float)C;
-  for (int64_t row = (int64_t)blockIdx.x * kLnWarps + (threadIdx.x >> 5); row < M; row += (int64_t)gridDim.x * kLnWarps) {
+  const int64_t rows_pad = (M + kRows - 1) / kRows * kRows;   // keep whole warps in the loop (shuffles)
+  for (int64_t row = (int64_t)blockIdx.x * kRows + threadIdx.x / G; row < rows_pad; row += (int64_t)gridDim.x * kRows) {
+    const bool live = row < M;
     const uint2* xr = reinterpret_cast<const uint2*>(x + row * C);
     float f[VPL][4];
     float s = 0.f;
 #pragma unroll
     for (int j = 0; j < VPL; ++j) {
-      const int v = lane + 32 * j;
-      if (v < nv) {
+      const int v = gl + G * j;
+      if (live && v < nv) {
         unpack4(__ldcs(xr + v), f[j]);
         s += (f[j][0] + f[j][1]) + (f[j][2] + f[j][3]);
       } else {
         f[j][0] = f[j][1] = f[j][2] = f[j][3] = 0.f;
       }
     }
-    const float mu = warp_sum(s) * inv_c;
+    const float mu = group_sum<G>(s) * inv_c;
     float q = 0.f;
 #pragma unroll
     for (int j = 0; j < VPL; ++j) {
-      const int v = lane + 32 * j;
+      const int v = gl + G * j;
       if (v < nv) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) { const float d = f[j][k] - mu; q += d * d; }
       }
     }
-    const float rs = rsqrtf(warp_sum(q) * inv_c + eps);
+    const float rs = rsqrtf(group_sum<G>(q) * inv_c + eps);
+    if (!live) continue;
     uint2* yr = reinterpret_cast<uint2*>(y + row * C);
 #pragma unroll
     for (int j = 0; j < VPL; ++j) {
-      const int v = lane + 32 * j;
+      const int v = gl + G * j;
       if (v < nv) {
         float o[4];
 #pragma unroll
@@ -104,25 +116,26 @@ __global__ void __launch_bounds__(kLnWarps * 32) ln_fwd_kernel(const bf16* __res
         yr[v] = pack4(o);
       }
     }
-    if (lane == 0) { mean[row] = mu; rstd[row] = rs; }
+    if (gl == 0) { mean[row] = mu; rstd[row] = rs; }
   }
 }
 
 // dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * w  (dy first multiplied by gelu'(pre) if GELU)
-template <int VPL, bool GELU, bool PGRAD>
-__global__ void __launch_bounds__(kLnWarps * 32) ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
-                                                               const float* __restrict__ w, const float* __restrict__ b,
-                                                               const float* __restrict__ mean,
-                                                               const float* __restrict__ rstd, bf16* __restrict__ dx,
-                                                               float* __restrict__ dw, float* __restrict__ db,
-                                                               int64_t M, int C) {
-  extern __shared__ float red[];  // PGRAD: [kLnWarps][2][C]
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+template <int G, int VPL, bool GELU, bool PGRAD>
+__global__ void __launch_bounds__(kLnThreads) ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
+                                                            const float* __restrict__ w, const float* __restrict__ b,
+                                                            const float* __restrict__ mean,
+                                                            const float* __restrict__ rstd, bf16* __restrict__ dx,
+                                                            float* __restrict__ dw, float* __restrict__ db,
+                                                            int64_t M, int C) {
+  extern __shared__ float red[];  // PGRAD: [2][C] accumulated with shared-memory atomics
+  const int gl = threadIdx.x % G;
   const int nv = C >> 2;
+  constexpr int kRows = kLnThreads / G;
   float wr[VPL][4], br[VPL][4], aw[VPL][4], ab[VPL][4];
 #pragma unroll
   for (int j = 0; j < VPL; ++j) {
-    const int v = lane + 32 * j;
+    const int v = gl + G * j;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       wr[j][k] = v < nv ? w[v * 4 + k] : 0.f;
@@ -130,17 +143,23 @@ __global__ void __launch_bounds__(kLnWarps * 32) ln_bwd_kernel(const bf16* __res
       aw[j][k] = 0.f; ab[j][k] = 0.f;
     }
   }
+  if (PGRAD) {
+    for (int c = threadIdx.x; c < 2 * C; c += kLnThreads) red[c] = 0.f;
+    __syncthreads();
+  }
   const float inv_c = 1.0f / (float)C;
-  for (int64_t row = (int64_t)blockIdx.x * kLnWarps + warp; row < M; row += (int64_t)gridDim.x * kLnWarps) {
+  const int64_t rows_pad = (M + kRows - 1) / kRows * kRows;
+  for (int64_t row = (int64_t)blockIdx.x * kRows + threadIdx.x / G; row < rows_pad; row += (int64_t)gridDim.x * kRows) {
+    const bool live = row < M;
     const uint2* xr = reinterpret_cast<const uint2*>(x + row * C);
     const uint2* gr = reinterpret_cast<const uint2*>(dy + row * C);
-    const float mu = mean[row], rs = rstd[row];
+    const float mu = live ? mean[row] : 0.f, rs = live ? rstd[row] : 0.f;
     float xh[VPL][4], g[VPL][4];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int j = 0; j < VPL; ++j) {
-      const int v = lane + 32 * j;
-      if (v < nv) {
+      const int v = gl + G * j;
+      if (live && v < nv) {
         float xv[4], dv[4];
         unpack4(__ldcs(xr + v), xv);
         unpack4(__ldcs(gr + v), dv);
@@ -159,11 +178,12 @@ __global__ void __launch_bounds__(kLnWarps * 32) ln_bwd_kernel(const bf16* __res
         for (int k = 0; k < 4; ++k) { xh[j][k] = 0.f; g[j][k] = 0.f; }
       }
     }
-    const float m1 = warp_sum(s1) * inv_c, m2 = warp_sum(s2) * inv_c;
+    const float m1 = group_sum<G>(s1) * inv_c, m2 = group_sum<G>(s2) * inv_c;
+    if (!live) continue;
     uint2* dr = reinterpret_cast<uint2*>(dx + row * C);
 #pragma unroll
     for (int j = 0; j < VPL; ++j) {
-      const int v = lane + 32 * j;
+      const int v = gl + G * j;
       if (v < nv) {
         float o[4];
 #pragma unroll
@@ -175,22 +195,19 @@ __global__ void __launch_bounds__(kLnWarps * 32) ln_bwd_kernel(const bf16* __res
   if (PGRAD) {
 #pragma unroll
     for (int j = 0; j < VPL; ++j) {
-      const int v = lane + 32 * j;
+      const int v = gl + G * j;
       if (v < nv) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          red[(warp * 2 + 0) * C + v * 4 + k] = aw[j][k];
-          red[(warp * 2 + 1) * C + v * 4 + k] = ab[j][k];
+          atomicAdd(&red[v * 4 + k], aw[j][k]);
+          atomicAdd(&red[C + v * 4 + k], ab[j][k]);
         }
       }
     }
     __syncthreads();
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      float tw = 0.f, tb = 0.f;
-#pragma unroll
-      for (int q = 0; q < kLnWarps; ++q) { tw += red[(q * 2 + 0) * C + c]; tb += red[(q * 2 + 1) * C + c]; }
-      atomicAdd(dw + c, tw);
-      atomicAdd(db + c, tb);
+    for (int c = threadIdx.x; c < C; c += kLnThreads) {
+      atomicAdd(dw + c, red[c]);
+      atomicAdd(db + c, red[C + c]);
     }
   }
 }
@@ -291,10 +308,11 @@ constexpr int kDwTile = 14;
 constexpr int kDwIn = kDwTile + 6;   // 20
 constexpr int kDwCh = 32;            // channels per CTA (16 bf16x2 lanes)
 
-template <bool BIAS>
+template <bool BIAS, bool ADD>
 __global__ void __launch_bounds__(256) dwconv7_kernel(const bf16* __restrict__ x, const float* __restrict__ wt,
-                                                      const float* __restrict__ bias, bf16* __restrict__ y, int H,
-                                                      int W, int C, int tiles_w, int tiles_h) {
+                                                      const float* __restrict__ bias, const bf16* __restrict__ add,
+                                                      bf16* __restrict__ y, int H, int W, int C, int tiles_w,
+                                                      int tiles_h) {
   __shared__ bf162 tile[kDwIn][kDwIn][kDwCh / 2];
   __shared__ float2 wsm[49][kDwCh / 2];
   const int cp = threadIdx.x & 15, t = threadIdx.x >> 4;
@@ -343,10 +361,16 @@ __global__ void __launch_bounds__(256) dwconv7_kernel(const bf16* __restrict__ x
   bf16* yout = y + (int64_t)n * H * W * C;
 #pragma unroll
   for (int r = 0; r < kDwTile; ++r) {
-    if (h0 + r < H)
-      *reinterpret_cast<bf162*>(yout + ((int64_t)(h0 + r) * W + w0 + t) * C + c0 + cp * 2) =
-          __floats2bfloat162_rn(acc[r].x, acc[r].y);
+    if (h0 + r < H) {
+      const int64_t off = (int64_t)n * H * W * C + ((int64_t)(h0 + r) * W + w0 + t) * C + c0 + cp * 2;
+      if (ADD) {  // residual-gradient join fused into the input-gradient pass
+        const float2 a = __bfloat1622float2(*reinterpret_cast<const bf162*>(add + off));
+        acc[r].x += a.x; acc[r].y += a.y;
+      }
+      *reinterpret_cast<bf162*>(y + off) = __floats2bfloat162_rn(acc[r].x, acc[r].y);
+    }
   }
+  (void)yout;
 }
 
 // weight gradient: dw[tap][c] += sum_{pixels} dy[p][c] * x[p + tap][c];  db[c] += sum dy
@@ -430,49 +454,58 @@ __global__ void __launch_bounds__(256) dwconv7_wgrad_kernel(const bf16* __restri
   }
 }
 
-inline int ln_grid(int64_t M) {
-  int64_t g = (M + kLnWarps - 1) / kLnWarps;
-  const int64_t cap = 148 * 8;
-  return (int)(g < cap ? (g < 1 ? 1 : g) : cap);
-}
 inline int flat_grid(int64_t total8) {
   int64_t g = (total8 + 255) / 256;
   const int64_t cap = 148 * 16;
   return (int)(g < cap ? (g < 1 ? 1 : g) : cap);
 }
 
+// (G, VPL) with the best lane utilisation for nv = C/4 vectors per row; ties go to the wider group
+inline void ln_shape(int nv, int& G, int& VPL) {
+  double best = -1.0;
+  G = 32; VPL = (nv + 31) / 32;
+  for (int g : {32, 16, 8, 4}) {
+    const int v = (nv + g - 1) / g;
+    if (v > 12) continue;
+    const double u = (double)nv / (double)(g * v);
+    if (u > best + 1e-9) { best = u; G = g; VPL = v; }
+  }
+}
+inline int ln_grid(int64_t M, int G) {
+  const int rows = kLnThreads / G;
+  int64_t g = (M + rows - 1) / rows;
+  const int64_t cap = 148 * 8;
+  return (int)(g < cap ? (g < 1 ? 1 : g) : cap);
+}
+
+#define B200AT_LN_FOR_VPL(G, X) X(G, 1) X(G, 2) X(G, 3) X(G, 4) X(G, 5) X(G, 6) X(G, 7) X(G, 8) X(G, 9) X(G, 10) X(G, 11) X(G, 12)
+#define B200AT_LN_FOR_ALL(X) B200AT_LN_FOR_VPL(32, X) B200AT_LN_FOR_VPL(16, X) B200AT_LN_FOR_VPL(8, X) B200AT_LN_FOR_VPL(4, X)
+
 template <bool GELU>
 int launch_ln_fwd(const bf16* x, const float* w, const float* b, bf16* y, float* mean, float* rstd, int64_t M, int C,
                   float eps, cudaStream_t s) {
-  const int vpl = (C / 4 + 31) / 32, g = ln_grid(M), th = kLnWarps * 32;
-  switch (vpl) {
-#define B200AT_CASE(V) case V: ln_fwd_kernel<V, GELU><<<g, th, 0, s>>>(x, w, b, y, mean, rstd, M, C, eps); break;
-    B200AT_CASE(1) B200AT_CASE(2) B200AT_CASE(3) B200AT_CASE(4) B200AT_CASE(5) B200AT_CASE(6) B200AT_CASE(7)
-    B200AT_CASE(8) B200AT_CASE(9) B200AT_CASE(10) B200AT_CASE(11) B200AT_CASE(12)
+  int G, VPL;
+  ln_shape(C / 4, G, VPL);
+  const int g = ln_grid(M, G);
+#define B200AT_CASE(GG, V) \
+  if (G == GG && VPL == V) { ln_fwd_kernel<GG, V, GELU><<<g, kLnThreads, 0, s>>>(x, w, b, y, mean, rstd, M, C, eps); return (int)cudaGetLastError(); }
+  B200AT_LN_FOR_ALL(B200AT_CASE)
 #undef B200AT_CASE
-    default: return (int)cudaErrorInvalidValue;
-  }
-  return (int)cudaGetLastError();
+  return (int)cudaErrorInvalidValue;
 }
 
 template <bool GELU, bool PGRAD>
 int launch_ln_bwd(const bf16* dy, const bf16* x, const float* w, const float* b, const float* mean, const float* rstd,
                   bf16* dx, float* dw, float* db, int64_t M, int C, cudaStream_t s) {
-  const int vpl = (C / 4 + 31) / 32, g = ln_grid(M), th = kLnWarps * 32;
-  const size_t sm = PGRAD ? sizeof(float) * kLnWarps * 2 * C : 0;
-  switch (vpl) {
-#define B200AT_CASE(V)                                                                                          \
-  case V: {                                                                                                     \
-    if (sm > 48 * 1024)                                                                                         \
-      cudaFuncSetAttribute(ln_bwd_kernel<V, GELU, PGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); \
-    ln_bwd_kernel<V, GELU, PGRAD><<<g, th, sm, s>>>(dy, x, w, b, mean, rstd, dx, dw, db, M, C);                  \
-  } break;
-    B200AT_CASE(1) B200AT_CASE(2) B200AT_CASE(3) B200AT_CASE(4) B200AT_CASE(5) B200AT_CASE(6) B200AT_CASE(7)
-    B200AT_CASE(8) B200AT_CASE(9) B200AT_CASE(10) B200AT_CASE(11) B200AT_CASE(12)
+  int G, VPL;
+  ln_shape(C / 4, G, VPL);
+  const int g = ln_grid(M, G);
+  const size_t sm = PGRAD ? sizeof(float) * 2 * C : 0;
+#define B200AT_CASE(GG, V) \
+  if (G == GG && VPL == V) { ln_bwd_kernel<GG, V, GELU, PGRAD><<<g, kLnThreads, sm, s>>>(dy, x, w, b, mean, rstd, dx, dw, db, M, C); return (int)cudaGetLastError(); }
+  B200AT_LN_FOR_ALL(B200AT_CASE)
 #undef B200AT_CASE
-    default: return (int)cudaErrorInvalidValue;
-  }
-  return (int)cudaGetLastError();
+  return (int)cudaErrorInvalidValue;
 }
 
 }  // namespace
@@ -541,16 +574,18 @@ int b200at_add_bf16(const void* a, const void* b, void* c, int64_t total, void* 
   return (int)cudaGetLastError();
 }
 
-int b200at_dwconv7_fwd(const void* x, const float* wt, const float* bias, void* y, int64_t B, int64_t H, int64_t W,
-                       int64_t C, void* stream) {
+int b200at_dwconv7_fwd(const void* x, const float* wt, const float* bias, const void* add, void* y, int64_t B,
+                       int64_t H, int64_t W, int64_t C, void* stream) {
   if (B <= 0) return 0;
   if (C % kDwCh) return (int)cudaErrorInvalidValue;
   const int tw = (int)((W + kDwTile - 1) / kDwTile), th = (int)((H + kDwTile - 1) / kDwTile);
   const int64_t grid = B * th * tw * (C / kDwCh);
   if (grid > 0x7fffffff) return (int)cudaErrorInvalidValue;
   cudaStream_t s = (cudaStream_t)stream;
-  if (bias) dwconv7_kernel<true><<<(unsigned)grid, 256, 0, s>>>((const bf16*)x, wt, bias, (bf16*)y, (int)H, (int)W, (int)C, tw, th);
-  else dwconv7_kernel<false><<<(unsigned)grid, 256, 0, s>>>((const bf16*)x, wt, nullptr, (bf16*)y, (int)H, (int)W, (int)C, tw, th);
+#define B200AT_DW(BI, AD) dwconv7_kernel<BI, AD><<<(unsigned)grid, 256, 0, s>>>((const bf16*)x, wt, bias, (const bf16*)add, (bf16*)y, (int)H, (int)W, (int)C, tw, th)
+  if (bias) { if (add) B200AT_DW(true, true); else B200AT_DW(true, false); }
+  else { if (add) B200AT_DW(false, true); else B200AT_DW(false, false); }
+#undef B200AT_DW
   return (int)cudaGetLastError();
 }
 

@@ -152,15 +152,92 @@ class _ScaleResidual(Function):
         return dz, dbias, dgamma, dout
 
 
+def _f32(t):
+    return t.detach().float().contiguous()
+
+
+def _gemm_nt(a, w):
+    """a [M,K] bf16 @ w[N,K]^T -> [M,N] bf16 (pwconv GEMM; cuBLAS in this round)."""
+    return a @ w.t()
+
+
+class _ConvNeXtBlock(Function):
+    """One whole block (models/convnext.py:37-50) as a single autograd node on NHWC bf16:
+
+        t1 = dwconv7(x) ; t2 = LN(t1) ; z = t2 W1^T ; a = GELU(z + b1) ; z2 = a W2^T ; out = x + gamma (z2 + b2)
+
+    Owning the whole backward lets the input-gradient pass (all the attack ever asks for) keep only
+    {t1, LN stats, z}, fold the residual-gradient join into the depthwise input-gradient kernel, and skip
+    every weight gradient; the outer training step additionally saves {x, t2, a, z2} for the weight grads.
+    """
+
+    @staticmethod
+    def forward(ctx, x, dw_w, dw_b, ln_w, ln_b, w1, b1, w2, b2, gamma):
+        x = x.contiguous()
+        B, H, W, C = x.shape
+        M = B * H * W
+        pg = not _INPUT_GRAD_ONLY[0]
+        wt = _f32(dw_w).reshape(C, 49).t().contiguous()                 # tap-major [49][C]
+        lnw, lnb, b1f, b2f, gf = _f32(ln_w), _f32(ln_b), _f32(b1), _f32(b2), _f32(gamma)
+        w1b, w2b = w1.detach().to(BF16), w2.detach().to(BF16)
+        t1 = torch.empty_like(x)
+        _abi.dwconv7_fwd(x, wt, _f32(dw_b), t1)
+        t2 = torch.empty_like(x)
+        mean = torch.empty(M, device=x.device, dtype=torch.float32)
+        rstd = torch.empty_like(mean)
+        _abi.ln_fwd(t1, lnw, lnb, t2, mean, rstd, 1e-6, False)
+        z = _gemm_nt(t2.view(M, C), w1b)
+        a = torch.empty_like(z)
+        _abi.bias_gelu_fwd(z, b1f, a)
+        z2 = _gemm_nt(a, w2b)
+        out = torch.empty_like(x)
+        _abi.scale_residual_fwd(z2, b2f, gf, x.view(M, C), out.view(M, C))
+        ctx.param_grads = pg
+        if pg:
+            ctx.save_for_backward(t1, mean, rstd, z, wt, lnw, lnb, b1f, b2f, gf, w1b, w2b, x, t2, a, z2)
+        else:
+            ctx.save_for_backward(t1, mean, rstd, z, wt, lnw, lnb, b1f, b2f, gf, w1b, w2b)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        sv = ctx.saved_tensors
+        t1, mean, rstd, z, wt, lnw, lnb, b1f, b2f, gf, w1b, w2b = sv[:12]
+        dout = dout.contiguous()
+        B, H, W, C = dout.shape
+        M = B * H * W
+        pg = ctx.param_grads and any(ctx.needs_input_grad[1:])
+        d2 = dout.view(M, C)
+        dz2 = torch.empty_like(d2)
+        _abi.scale_bwd(d2, gf, dz2)
+        da = dz2 @ w2b                                                  # [M,4C]
+        dz = torch.empty_like(da)
+        _abi.bias_gelu_bwd(da, z, b1f, dz)
+        dt2 = (dz @ w1b).view(B, H, W, C)
+        dt1 = torch.empty_like(dt2)
+        dlnw = torch.zeros_like(lnw) if pg else None
+        dlnb = torch.zeros_like(lnb) if pg else None
+        _abi.ln_bwd(dt2, t1, lnw, lnb, mean, rstd, dt1, dlnw, dlnb, False)
+        dx = torch.empty_like(dout)
+        _abi.dwconv7_fwd(dt1, wt.flip(0).contiguous(), None, dx, add=dout)   # + residual gradient
+        if not pg:
+            return (dx,) + (None,) * 9
+        x, t2, a, z2 = sv[12:]
+        ddw = torch.zeros(49, C, device=dout.device, dtype=torch.float32)
+        ddb = torch.zeros(C, device=dout.device, dtype=torch.float32)
+        _abi.dwconv7_wgrad(x, dt1, ddw, ddb)
+        dw1 = (dz.t() @ t2.view(M, C)).float()
+        db1 = dz.sum(0, dtype=torch.float32)
+        dw2 = (dz2.t() @ a).float()
+        col = d2.sum(0, dtype=torch.float32)
+        db2 = col * gf
+        dgamma = (d2.float() * z2.float()).sum(0) + col * b2f
+        return dx, ddw.t().reshape(C, 1, 7, 7), ddb, dlnw, dlnb, dw1, db1, dw2, db2, dgamma
+
+
 def convnext_block(x, dw_w, dw_b, ln_w, ln_b, w1, b1, w2, b2, gamma):
     """x: [B,H,W,C] bf16 NHWC -> same.  models/convnext.py:37-50."""
-    B, H, W, C = x.shape
-    h = _DwConv7.apply(x, dw_w, dw_b)
-    h = layer_norm(h, ln_w, ln_b, 1e-6).view(-1, C)
-    z = h @ w1.to(BF16).t()                              # pwconv1 (cuBLAS)
-    a = _BiasGelu.apply(z, b1)
-    z2 = a @ w2.to(BF16).t()                             # pwconv2 (cuBLAS)
-    return _ScaleResidual.apply(z2, b2, gamma, x.view(-1, C)).view(B, H, W, C)
+    return _ConvNeXtBlock.apply(x, dw_w, dw_b, ln_w, ln_b, w1, b1, w2, b2, gamma)
 
 
 def stem_layer(x, cw, cb, lw, lb, stride, first, mean=None, std=None):

@@ -99,6 +99,42 @@ def test_bias_gelu_and_scale_residual(ops, cuda_dev):
     _close(got[3], rg[3], atol=1e-6)
 
 
+@pytest.mark.parametrize('shape', [(2, 28, 28, 96), (3, 7, 7, 192)])
+def test_block_function_fwd_bwd(ops, cuda_dev, shape):
+    """whole-block autograd node vs the fp32 reference block (all gradients), and the input-grad-only mode"""
+    B, H, W, C = shape
+    g = torch.Generator(device='cuda').manual_seed(C)
+    rnd = lambda *s, k=1.0: (torch.randn(*s, generator=g, device=cuda_dev) * k)
+    x = rnd(B, H, W, C).to(BF16)
+    P = dict(dw_w=rnd(C, 1, 7, 7, k=0.1), dw_b=rnd(C, k=0.1), ln_w=1 + rnd(C, k=0.1), ln_b=rnd(C, k=0.1),
+             w1=rnd(4 * C, C, k=0.05), b1=rnd(4 * C, k=0.1), w2=rnd(C, 4 * C, k=0.05), b2=rnd(C, k=0.1),
+             gamma=rnd(C, k=0.5))
+    P = {k: v.requires_grad_() for k, v in P.items()}
+    dout = rnd(B, H, W, C).to(BF16)
+
+    xr = x.float().requires_grad_()
+    h = F.conv2d(xr.permute(0, 3, 1, 2), P['dw_w'], P['dw_b'], padding=3, groups=C).permute(0, 2, 3, 1)
+    h = F.layer_norm(h, (C,), P['ln_w'], P['ln_b'], 1e-6)
+    h = F.linear(F.gelu(F.linear(h, P['w1'], P['b1'])), P['w2'], P['b2'])
+    ref = xr + P['gamma'] * h
+    names = list(P)
+    rg = torch.autograd.grad(ref, [xr] + [P[n] for n in names], dout.float())
+
+    xt = x.clone().requires_grad_()
+    out = ops.convnext_block(xt, *[P[n] for n in names])
+    _close(out, ref, atol=4e-2)
+    got = torch.autograd.grad(out, [xt] + [P[n] for n in names], dout)
+    _close(got[0], rg[0], atol=4e-2)
+    for n, a, r in zip(names, got[1:], rg[1:]):
+        cs = F.cosine_similarity(a.flatten().float(), r.flatten(), dim=0).item()
+        assert cs > 0.995, (n, cs)
+        assert abs(a.float().norm().item() / r.norm().item() - 1) < 0.03, n
+    with ops.input_grad_only():
+        out2 = ops.convnext_block(xt, *[P[n] for n in names])
+    (dx2,) = torch.autograd.grad(out2, [xt], dout)
+    assert torch.equal(dx2, got[0])
+
+
 def test_convnext_engine_matches_oracle(cuda_dev):
     """ConvNeXt-T-CvSt, same seed-0 weights: bf16 engine on the GPU vs fp32 oracle on the CPU.
     Tolerances: logits 5e-2 absolute (|logit| ~ 1, ~40 bf16 layers); input gradient cosine >= 0.98."""
