@@ -48,6 +48,25 @@ int b200at_dwconv7_fwd(const void* x, const float* wt, const float* bias, const 
 int b200at_dwconv7_wgrad(const void* x, const void* dy, float* dw, float* db, int64_t B, int64_t H, int64_t W,
                          int64_t C, void* stream);
 
+/* models/convnext.py:30,32 `pwconv1` / `pwconv2` (nn.Linear on the NHWC rows) and their input gradients:
+ *     C[M,N] = epilogue(A[M,K] . B[N,K]^T),  A, B, C bf16 row-major, fp32 accumulation in TMEM.
+ * Hand-written tcgen05.mma (cta_group::1, UMMA 128 x BLOCK_N x 16) fed by TMA (SWIZZLE_128B), persistent and
+ * warp specialised; the block's elementwise tail is fused into the epilogue:
+ *   NONE       C = acc
+ *   BIAS       C = acc + bias[n]
+ *   BIAS_GELU  C = GELU(acc + bias[n]);  if c2 != null also c2 = acc + bias[n]   (pre-activation for the backward)
+ *   RESIDUAL   C = aux + acc + bias[n]                                           (layer scale folded into B, bias)
+ *   GELU_GRAD  C = acc * GELU'(aux)                                              (aux = saved pre-activation)
+ * N % 16 == 0, K % 8 == 0, pointers 16-byte aligned.  The weight-gradient GEMMs (contraction over M) stay on
+ * cuBLAS. */
+#define B200AT_EPI_NONE 0
+#define B200AT_EPI_BIAS 1
+#define B200AT_EPI_BIAS_GELU 2
+#define B200AT_EPI_RESIDUAL 3
+#define B200AT_EPI_GELU_GRAD 4
+int b200at_gemm_bf16(const void* a, const void* b, void* c, void* c2, const void* aux, const float* bias,
+                     int64_t M, int64_t N, int64_t K, int epilogue, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -97,6 +97,7 @@ def _declare(L):
         'b200at_add_bf16': [P, P, P, I64, P],
         'b200at_dwconv7_fwd': [P, P, P, P, P, I64, I64, I64, I64, P],
         'b200at_dwconv7_wgrad': [P, P, P, P, I64, I64, I64, I64, P],
+        'b200at_gemm_bf16': [P, P, P, P, P, P, I64, I64, I64, I, P],
     })
     for name, args in sig.items():
         fn = getattr(L, name)
@@ -343,3 +344,22 @@ def gather_best(x_slots, x_best, x_best_adv, state):
         _check(lib().b200at_gather_best(_slot_ptrs(x_slots, x_best, 'x_slots'), len(x_slots), _img(x_best, name='x_best'),
                                         _img(x_best_adv, x_best, 'x_best_adv'), _p(state), B, n, _stream()),
                'gather_best')
+
+
+EPI_NONE, EPI_BIAS, EPI_BIAS_GELU, EPI_RESIDUAL, EPI_GELU_GRAD = range(5)
+
+
+def gemm_bf16(a, b, c, epilogue=EPI_NONE, bias=None, aux=None, c2=None):
+    """c[M,N] = epilogue(a[M,K] @ b[N,K]^T) on the tcgen05 kernel (include/b200at_model.h)."""
+    M, K = a.shape
+    N = b.shape[0]
+    if b.shape[1] != K or tuple(c.shape) != (M, N):
+        raise B200atError(f'gemm shapes: a {tuple(a.shape)} b {tuple(b.shape)} c {tuple(c.shape)}')
+    for t, nm in ((aux, 'aux'), (c2, 'c2')):
+        if t is not None and tuple(t.shape) != (M, N):
+            raise B200atError(f'gemm {nm} must be [M,N]')
+    with _Timed('gemm_bf16'):
+        _check(lib().b200at_gemm_bf16(_act(a, 'a'), _act(b, 'b'), _act(c, 'c'),
+                                      _act(c2, 'c2') if c2 is not None else c_void_p(0),
+                                      _act(aux, 'aux') if aux is not None else c_void_p(0),
+                                      _par(bias, 'bias', N), M, N, K, epilogue, _stream()), 'gemm_bf16')

@@ -1,0 +1,388 @@
+// K10: tcgen05 / TMEM / TMA GEMM for the dense pwconv (MLP) layers of the ConvNeXt block, with the
+// block's elementwise tail fused into the epilogue (include/b200at_model.h: b200at_gemm_bf16).
+//
+//   C[M,N] = epilogue( A[M,K] · B[N,K]^T )        A, B bf16 K-major (row-major, K contiguous), fp32 accumulate
+//
+// Persistent, warp-specialised, one CTA per SM (cta_group::1):
+//   warp 0   TMA producer   cp.async.bulk.tensor.2d (SWIZZLE_128B boxes of 64 bf16 along K) -> kStages-deep smem ring
+//   warp 1   MMA issuer     one elected lane issues tcgen05.mma.kind::f16 (UMMA 128 x BLOCK_N x 16), accumulators in
+//                           TMEM (2 x BLOCK_N fp32 columns, double buffered across output tiles)
+//   warp 2   TMEM allocator
+//   warps 4-7 epilogue      tcgen05.ld 32x32b -> registers -> bias / GELU / GELU' / residual -> bf16 -> global
+// Synchronisation is mbarrier only (full/empty per smem stage, full/empty per TMEM accumulator).
+// Out-of-range rows / K tails are zero-filled by TMA; the epilogue masks its loads/stores on M.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+#include "../../include/b200at_model.h"
+
+namespace {
+
+typedef __nv_bfloat16 bf16;
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;            // 64 bf16 = 128 B = one SWIZZLE_128B row
+constexpr int kUmmaK = 16;
+constexpr int kStages = 4;
+constexpr int kNumThreads = 256;       // warps 0..3: TMA / MMA / TMEM-alloc / idle, warps 4..7: epilogue
+constexpr int kEpilogueWarp0 = 4;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .b32 rx;\n"
+      ".reg .pred px;\n"
+      "elect.sync rx|px, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, px;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+//   [0,14) start address >> 4, [16,30) LBO >> 4 (unused for swizzled K-major: 1), [32,46) SBO >> 4 (1024 B between
+//   8-row groups), [46,48) version = 1 (Blackwell), [61,64) layout type = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_desc(const void* smem) {
+  const uint32_t addr = smem_u32(smem);
+  uint64_t d = (uint64_t)((addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// kind::f16 instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = BF16, both K-major
+__device__ __forceinline__ uint32_t make_idesc(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float gelu_f(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_grad_f(float v) {
+  const float cdf = 0.5f * (1.0f + erff(v * 0.70710678118654752f));
+  return cdf + v * 0.3989422804014327f * __expf(-0.5f * v * v);
+}
+__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+    f[2 * i] = t.x; f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat162 t = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    w[i] = *reinterpret_cast<uint32_t*>(&t);
+  }
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+struct GemmParams {
+  bf16* c;            // [M][N] output
+  bf16* c2;           // optional second output (EPI_BIAS_GELU: the pre-activation z = acc), or null
+  const bf16* aux;    // EPI_RESIDUAL: residual [M][N];  EPI_GELU_GRAD: saved pre-activation z [M][N]
+  const float* bias;  // [N] or null
+  int M, N, K;
+  int block_n, tiles_m, tiles_n;
+};
+
+template <int EPI>
+__global__ void __launch_bounds__(kNumThreads, 1) gemm_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                              const __grid_constant__ CUtensorMap map_b,
+                                                              const GemmParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: [stages][A 16 KB][B block_n*128 B] then barriers
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t a_bytes = kBlockM * kBlockK * 2;
+  const uint32_t b_bytes = (uint32_t)p.block_n * kBlockK * 2;
+  const uint32_t stage_bytes = a_bytes + b_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * stage_bytes);
+  uint64_t* full = bars;                   // [kStages]
+  uint64_t* empty = bars + kStages;        // [kStages]
+  uint64_t* tfull = bars + 2 * kStages;    // [2]
+  uint64_t* tempty = bars + 2 * kStages + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_k = (p.K + kBlockK - 1) / kBlockK;
+  const int num_tiles = p.tiles_m * p.tiles_n;
+  const uint32_t tmem_cols = p.block_n * 2 <= 32 ? 32 : (p.block_n * 2 <= 64 ? 64 : (p.block_n * 2 <= 128 ? 128 : (p.block_n * 2 <= 256 ? 256 : 512)));
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int tm = tile / p.tiles_n, tn = tile % p.tiles_n;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * stage_bytes;
+          mbar_expect_tx(&full[stage], stage_bytes);
+          tma_load_2d(&map_a, &full[stage], sa, kb * kBlockK, tm * kBlockM);
+          tma_load_2d(&map_b, &full[stage], sa + a_bytes, kb * kBlockK, tn * p.block_n);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    const uint32_t idesc = make_idesc(kBlockM, p.block_n);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tempty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.block_n);
+      for (int kb = 0; kb < num_k; ++kb) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint8_t* sa = smem + stage * stage_bytes;
+          const uint64_t da = make_desc(sa), db = make_desc(sa + a_bytes);
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            // advance 32 B along K inside the 128 B swizzle atom: +2 in the (addr >> 4) field
+            umma(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty[stage]);                 // frees the smem stage when these MMAs retire
+          if (kb == num_k - 1) umma_commit(&tfull[acc]);
+        }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp >= kEpilogueWarp0) {
+    // ------------------------------------------------------------------ epilogue (TMEM -> regs -> global)
+    const int q = warp & 3;                            // TMEM lane quarter this warp may access
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int tm = tile / p.tiles_n, tn = tile % p.tiles_n;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const int row = tm * kBlockM + q * 32 + lane;
+      const bool row_ok = row < p.M;
+      const int64_t row_off = (int64_t)row * p.N;
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.block_n);
+      for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(t_row + (uint32_t)c0, v);
+        tmem_ld_wait();
+        const int col = tn * p.block_n + c0;
+        if (row_ok && col < p.N) {
+          float f[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+          if (EPI == B200AT_EPI_BIAS || EPI == B200AT_EPI_BIAS_GELU || EPI == B200AT_EPI_RESIDUAL) {
+            if (p.bias) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) f[i] += __ldg(p.bias + col + i);
+            }
+          }
+          if (EPI == B200AT_EPI_BIAS_GELU) {
+            if (p.c2) {   // pre-activation (with bias) kept for the backward
+              *reinterpret_cast<uint4*>(p.c2 + row_off + col) = pack8(f);
+              *reinterpret_cast<uint4*>(p.c2 + row_off + col + 8) = pack8(f + 8);
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] = gelu_f(f[i]);
+          }
+          if (EPI == B200AT_EPI_RESIDUAL) {
+            float r[16];
+            unpack8(__ldg(reinterpret_cast<const uint4*>(p.aux + row_off + col)), r);
+            unpack8(__ldg(reinterpret_cast<const uint4*>(p.aux + row_off + col + 8)), r + 8);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] += r[i];
+          }
+          if (EPI == B200AT_EPI_GELU_GRAD) {
+            float z[16];
+            unpack8(__ldg(reinterpret_cast<const uint4*>(p.aux + row_off + col)), z);
+            unpack8(__ldg(reinterpret_cast<const uint4*>(p.aux + row_off + col + 8)), z + 8);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] *= gelu_grad_f(z[i]);
+          }
+          *reinterpret_cast<uint4*>(p.c + row_off + col) = pack8(f);
+          *reinterpret_cast<uint4*>(p.c + row_off + col + 8) = pack8(f + 8);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// [rows][K] bf16 row-major tensor, boxes of (64 along K) x box_rows, 128 B swizzle, zero fill outside
+bool make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t K, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+int pick_block_n(int64_t N) {
+  // largest multiple of 16 that divides N and is <= 256 (UMMA N limit at M = 128); else 128 with a masked tail
+  for (int bn = 256; bn >= 16; bn -= 16)
+    if (N % bn == 0) return bn;
+  return 128;
+}
+
+template <int EPI>
+int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, size_t smem, int grid, cudaStream_t s) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  gemm_kernel<EPI><<<grid, kNumThreads, smem, s>>>(ma, mb, p);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace
+
+extern "C" int b200at_gemm_bf16(const void* a, const void* b, void* c, void* c2, const void* aux, const float* bias,
+                                int64_t M, int64_t N, int64_t K, int epilogue, void* stream) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  if (N % 16 || K % 8) return (int)cudaErrorInvalidValue;
+  if ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c)) & 15)
+    return (int)cudaErrorInvalidValue;
+  GemmParams p;
+  p.c = (bf16*)c; p.c2 = (bf16*)c2; p.aux = (const bf16*)aux; p.bias = bias;
+  p.M = (int)M; p.N = (int)N; p.K = (int)K;
+  p.block_n = pick_block_n(N);
+  p.tiles_m = (int)((M + kBlockM - 1) / kBlockM);
+  p.tiles_n = (int)((N + p.block_n - 1) / p.block_n);
+  CUtensorMap ma, mb;
+  if (!make_map(&ma, a, M, K, kBlockM) || !make_map(&mb, b, N, K, p.block_n)) return (int)cudaErrorUnknown;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int tiles = p.tiles_m * p.tiles_n;
+  const int grid = tiles < sms ? tiles : sms;
+  const size_t smem = 1024 + (size_t)kStages * (kBlockM * kBlockK * 2 + (size_t)p.block_n * kBlockK * 2) + 256;
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (epilogue) {
+    case B200AT_EPI_NONE: return launch<B200AT_EPI_NONE>(ma, mb, p, smem, grid, s);
+    case B200AT_EPI_BIAS: return launch<B200AT_EPI_BIAS>(ma, mb, p, smem, grid, s);
+    case B200AT_EPI_BIAS_GELU: return launch<B200AT_EPI_BIAS_GELU>(ma, mb, p, smem, grid, s);
+    case B200AT_EPI_RESIDUAL: return launch<B200AT_EPI_RESIDUAL>(ma, mb, p, smem, grid, s);
+    case B200AT_EPI_GELU_GRAD: return launch<B200AT_EPI_GELU_GRAD>(ma, mb, p, smem, grid, s);
+    default: return (int)cudaErrorInvalidValue;
+  }
+}

@@ -66,9 +66,15 @@ enum { B200AT_NORM_LINF = 0, B200AT_NORM_L2 = 1, B200AT_NORM_L1 = 2 };
 B200AT_HD int32_t b200at_f2i(float f) { int32_t i; memcpy(&i, &f, 4); return i; }
 B200AT_HD float b200at_i2f(int32_t i) { float f; memcpy(&f, &i, 4); return f; }
 
-// torch.max / torch.min / clamp semantics: NaN propagates
+// torch.max / torch.min / clamp semantics: NaN propagates.  On the device this is the single
+// FMNMX.NAN instruction (PTX max.NaN / min.NaN); the update kernels are close to issue-bound otherwise.
+#if defined(__CUDA_ARCH__)
+B200AT_HD float b200at_max(float a, float b) { float r; asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
+B200AT_HD float b200at_min(float a, float b) { float r; asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
+#else
 B200AT_HD float b200at_max(float a, float b) { return (a != a || b != b) ? (a + b) : (a < b ? b : a); }
 B200AT_HD float b200at_min(float a, float b) { return (a != a || b != b) ? (a + b) : (b < a ? b : a); }
+#endif
 B200AT_HD float b200at_clamp01(float v) { return b200at_min(b200at_max(v, 0.0f), 1.0f); }
 // torch.sign: 0 for +-0 and NaN
 B200AT_HD float b200at_sign(float g) { return (float)((g > 0.0f) - (g < 0.0f)); }
