@@ -8,7 +8,9 @@
 //   warp 1   MMA issuer     one elected lane issues tcgen05.mma.kind::f16 (UMMA 128 x BLOCK_N x 16), accumulators in
 //                           TMEM (2 x BLOCK_N fp32 columns, double buffered across output tiles)
 //   warp 2   TMEM allocator
-//   warps 4-7 epilogue      tcgen05.ld 32x32b -> registers -> bias / GELU / GELU' / residual -> bf16 -> global
+//   warps 4-11 epilogue     tcgen05.ld 32x32b -> registers -> bias / GELU / GELU' / residual -> bf16 -> XOR-swizzled
+//                           per-warp staging tile in shared memory -> 128-byte-line coalesced global stores
+//                           (two warps per TMEM lane quarter, alternating 64-column strips)
 // Synchronisation is mbarrier only (full/empty per smem stage, full/empty per TMEM accumulator).
 // Out-of-range rows / K tails are zero-filled by TMA; the epilogue masks its loads/stores on M.
 #include <cuda.h>
@@ -26,8 +28,11 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;            // 64 bf16 = 128 B = one SWIZZLE_128B row
 constexpr int kUmmaK = 16;
 constexpr int kStages = 4;
-constexpr int kNumThreads = 256;       // warps 0..3: TMA / MMA / TMEM-alloc / idle, warps 4..7: epilogue
-constexpr int kEpilogueWarp0 = 4;
+constexpr int kEpilogueWarp0 = 4;      // warps 0..3: TMA / MMA / TMEM-alloc / idle
+constexpr int kEpilogueWarps = 8;      // warps 4..11
+constexpr int kNumThreads = 32 * (kEpilogueWarp0 + kEpilogueWarps);
+constexpr int kStripCols = 64;         // columns per epilogue strip (128 B of bf16 per row)
+constexpr int kStageTileBytes = 32 * kStripCols * 2;   // per-warp staging tile: 32 rows x 128 B
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -114,6 +119,11 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
         "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
       : "r"(taddr));
 }
+// 32 rows x 128 B staging tile, 16-byte pieces XOR-swizzled by (row & 7): conflict-free both for the
+// row-per-lane writes and for the line-per-8-lanes reads
+__device__ __forceinline__ uint4* stage_piece(uint8_t* tile, int row, int piece) {
+  return reinterpret_cast<uint4*>(tile + row * (kStripCols * 2) + ((piece ^ (row & 7)) << 4));
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ float gelu_f(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f)); }
@@ -164,6 +174,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_kernel(const __grid_const
   uint64_t* tfull = bars + 2 * kStages;    // [2]
   uint64_t* tempty = bars + 2 * kStages + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+  uint8_t* staging = smem + kStages * stage_bytes + 256;   // [kEpilogueWarps][kStageTileBytes]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_k = (p.K + kBlockK - 1) / kBlockK;
@@ -176,7 +187,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_kernel(const __grid_const
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], kEpilogueWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -238,58 +249,85 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_kernel(const __grid_const
       }
     }
   } else if (warp >= kEpilogueWarp0) {
-    // ------------------------------------------------------------------ epilogue (TMEM -> regs -> global)
+    // ------------------------------------------------------------------ epilogue (TMEM -> regs -> smem -> global)
     const int q = warp & 3;                            // TMEM lane quarter this warp may access
+    const int half = (warp - kEpilogueWarp0) >> 2;     // which of the two warps of that quarter
+    uint8_t* tile = staging + (warp - kEpilogueWarp0) * kStageTileBytes;
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int tm = tile / p.tiles_n, tn = tile % p.tiles_n;
+    for (int tile_id = blockIdx.x; tile_id < num_tiles; tile_id += gridDim.x, ++it) {
+      const int tm = tile_id / p.tiles_n, tn = tile_id % p.tiles_n;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
-      const int row = tm * kBlockM + q * 32 + lane;
+      const int row0 = tm * kBlockM + q * 32;           // first row of this warp's quarter
+      const int row = row0 + lane;
       const bool row_ok = row < p.M;
       const int64_t row_off = (int64_t)row * p.N;
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.block_n);
-      for (int c0 = 0; c0 < p.block_n; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld16(t_row + (uint32_t)c0, v);
+      for (int s0 = half * kStripCols; s0 < p.block_n; s0 += 2 * kStripCols) {
+        const int width = (p.block_n - s0) < kStripCols ? (p.block_n - s0) : kStripCols;   // multiple of 16
+        const int col0 = tn * p.block_n + s0;
+        float f[kStripCols];
+#pragma unroll
+        for (int c = 0; c < kStripCols; c += 16) {
+          if (c < width) {
+            uint32_t v[16];
+            tmem_ld16(t_row + (uint32_t)(s0 + c), v);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[c + i] = __uint_as_float(v[i]);
+          }
+        }
         tmem_ld_wait();
-        const int col = tn * p.block_n + c0;
-        if (row_ok && col < p.N) {
-          float f[16];
+        const bool live = row_ok;
 #pragma unroll
-          for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
-          if (EPI == B200AT_EPI_BIAS || EPI == B200AT_EPI_BIAS_GELU || EPI == B200AT_EPI_RESIDUAL) {
-            if (p.bias) {
+        for (int c = 0; c < kStripCols; c += 16) {
+          if (c < width && col0 + c < p.N) {
+            float* g = f + c;
+            if (EPI == B200AT_EPI_BIAS || EPI == B200AT_EPI_BIAS_GELU || EPI == B200AT_EPI_RESIDUAL) {
+              if (p.bias) {
 #pragma unroll
-              for (int i = 0; i < 16; ++i) f[i] += __ldg(p.bias + col + i);
+                for (int i = 0; i < 16; ++i) g[i] += __ldg(p.bias + col0 + c + i);
+              }
+            }
+            if (EPI == B200AT_EPI_RESIDUAL && live) {
+              float r[16];
+              unpack8(__ldg(reinterpret_cast<const uint4*>(p.aux + row_off + col0 + c)), r);
+              unpack8(__ldg(reinterpret_cast<const uint4*>(p.aux + row_off + col0 + c + 8)), r + 8);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) g[i] += r[i];
+            }
+            if (EPI == B200AT_EPI_GELU_GRAD && live) {
+              float z[16];
+              unpack8(__ldg(reinterpret_cast<const uint4*>(p.aux + row_off + col0 + c)), z);
+              unpack8(__ldg(reinterpret_cast<const uint4*>(p.aux + row_off + col0 + c + 8)), z + 8);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) g[i] *= gelu_grad_f(z[i]);
             }
           }
-          if (EPI == B200AT_EPI_BIAS_GELU) {
-            if (p.c2) {   // pre-activation (with bias) kept for the backward
-              *reinterpret_cast<uint4*>(p.c2 + row_off + col) = pack8(f);
-              *reinterpret_cast<uint4*>(p.c2 + row_off + col + 8) = pack8(f + 8);
-            }
+        }
+        // one or two outputs leave through the staging tile: rows per lane in, 128-byte lines out
+        const int n_out = (EPI == B200AT_EPI_BIAS_GELU && p.c2 != nullptr) ? 2 : 1;
+        for (int o = 0; o < n_out; ++o) {
+          bf16* dst = (n_out == 2 && o == 0) ? p.c2 : p.c;
+          if (EPI == B200AT_EPI_BIAS_GELU && o == n_out - 1) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) f[i] = gelu_f(f[i]);
+            for (int i = 0; i < kStripCols; ++i) f[i] = gelu_f(f[i]);
           }
-          if (EPI == B200AT_EPI_RESIDUAL) {
-            float r[16];
-            unpack8(__ldg(reinterpret_cast<const uint4*>(p.aux + row_off + col)), r);
-            unpack8(__ldg(reinterpret_cast<const uint4*>(p.aux + row_off + col + 8)), r + 8);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) f[i] += r[i];
+          for (int c = 0; c < kStripCols; c += 8) {
+            if (c < width) *stage_piece(tile, lane, c >> 3) = pack8(f + c);
           }
-          if (EPI == B200AT_EPI_GELU_GRAD) {
-            float z[16];
-            unpack8(__ldg(reinterpret_cast<const uint4*>(p.aux + row_off + col)), z);
-            unpack8(__ldg(reinterpret_cast<const uint4*>(p.aux + row_off + col + 8)), z + 8);
+          __syncwarp();
+          const int piece = lane & 7;                   // 16-byte piece of the 128-byte row segment
 #pragma unroll
-            for (int i = 0; i < 16; ++i) f[i] *= gelu_grad_f(z[i]);
+          for (int j = 0; j < 8; ++j) {
+            const int r = (lane >> 3) + 4 * j;          // 4 rows per store instruction
+            const int col = col0 + piece * 8;
+            if (piece * 8 < width && row0 + r < p.M && col < p.N)
+              *reinterpret_cast<uint4*>(dst + (int64_t)(row0 + r) * p.N + col) = *stage_piece(tile, r, piece);
           }
-          *reinterpret_cast<uint4*>(p.c + row_off + col) = pack8(f);
-          *reinterpret_cast<uint4*>(p.c + row_off + col + 8) = pack8(f + 8);
+          __syncwarp();
         }
       }
       tc_fence_before();
@@ -375,7 +413,8 @@ extern "C" int b200at_gemm_bf16(const void* a, const void* b, void* c, void* c2,
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int tiles = p.tiles_m * p.tiles_n;
   const int grid = tiles < sms ? tiles : sms;
-  const size_t smem = 1024 + (size_t)kStages * (kBlockM * kBlockK * 2 + (size_t)p.block_n * kBlockK * 2) + 256;
+  const size_t smem = 1024 + (size_t)kStages * (kBlockM * kBlockK * 2 + (size_t)p.block_n * kBlockK * 2) + 256 +
+                      (size_t)kEpilogueWarps * kStageTileBytes;
   cudaStream_t s = (cudaStream_t)stream;
   switch (epilogue) {
     case B200AT_EPI_NONE: return launch<B200AT_EPI_NONE>(ma, mb, p, smem, grid, s);

@@ -10,6 +10,8 @@ downsample convolutions are library calls (cuBLAS / cuDNN through torch) in this
 round-1 baseline (profiles/r01_launches_summary_torch_model.txt) shows them at ~8 % of the step against
 ~85 % for the memory-bound ops, which is why those were written first.
 """
+import os
+
 import torch
 import torch.nn.functional as F
 from torch.autograd import Function
@@ -156,19 +158,52 @@ def _f32(t):
     return t.detach().float().contiguous()
 
 
-def _gemm_nt(a, w):
-    """a [M,K] bf16 @ w[N,K]^T -> [M,N] bf16 (pwconv GEMM; cuBLAS in this round)."""
-    return a @ w.t()
+# which pwconv GEMMs run on the hand-written tcgen05 kernel (the rest: cuBLAS + the elementwise kernels).
+#   'residual'  pwconv2 forward with layer-scale + bias + residual fused in the epilogue
+#   'dgrad1'    d(t2) = dz W1                     (no epilogue; same speed as cuBLAS, one library call less)
+#   'gelu'      pwconv1 forward with bias + GELU fused (+ pre-activation saved)
+#   'gelu_grad' dz = (dout W2g) * GELU'(z)        fused
+TCGEN05 = set(filter(None, os.environ.get('B200AT_TCGEN05', 'residual,dgrad1').split(',')))
+
+_WCACHE = {}
+
+
+def _prepared(w1, w2, b2, gamma):
+    """bf16 / transposed / layer-scale-folded copies of the block's MLP weights, rebuilt only when a
+    parameter changes (once per optimiser step; shared by the 4 forwards + 3 backwards of a step)."""
+    key = (w1.data_ptr(), w2.data_ptr(), b2.data_ptr(), gamma.data_ptr())
+    ver = (w1._version, w2._version, b2._version, gamma._version)
+    hit = _WCACHE.get(key)
+    if hit is not None and hit[0] == ver:
+        return hit[1]
+    with torch.no_grad():
+        gf = gamma.detach().float()
+        w1b = w1.detach().to(BF16).contiguous()                         # [4C, C]   pwconv1: t2 @ w1b^T
+        w1t = w1b.t().contiguous()                                      # [C, 4C]   dt2 = dz @ w1b  == dz @ w1t^T
+        w2g = (gf[:, None] * w2.detach().float()).to(BF16).contiguous()  # [C, 4C]   gamma folded: a @ w2g^T
+        w2gt = w2g.t().contiguous()                                     # [4C, C]   da = dout @ w2g == dout @ w2gt^T
+        b2g = (gf * b2.detach().float()).contiguous()
+        prep = dict(w1b=w1b, w1t=w1t, w2g=w2g, w2gt=w2gt, b2g=b2g, gf=gf.contiguous())
+    _WCACHE[key] = (ver, prep)
+    return prep
+
+
+def _gemm(a, w, epi=_abi.EPI_NONE, bias=None, aux=None, c2=None):
+    c = torch.empty(a.shape[0], w.shape[0], device=a.device, dtype=BF16)
+    _abi.gemm_bf16(a, w, c, epi, bias=bias, aux=aux, c2=c2)
+    return c
 
 
 class _ConvNeXtBlock(Function):
     """One whole block (models/convnext.py:37-50) as a single autograd node on NHWC bf16:
 
-        t1 = dwconv7(x) ; t2 = LN(t1) ; z = t2 W1^T ; a = GELU(z + b1) ; z2 = a W2^T ; out = x + gamma (z2 + b2)
+        t1 = dwconv7(x) ; t2 = LN(t1) ; z = t2 W1^T + b1 ; a = GELU(z) ; out = x + a (gamma W2)^T + gamma b2
 
     Owning the whole backward lets the input-gradient pass (all the attack ever asks for) keep only
     {t1, LN stats, z}, fold the residual-gradient join into the depthwise input-gradient kernel, and skip
-    every weight gradient; the outer training step additionally saves {x, t2, a, z2} for the weight grads.
+    every weight gradient; the outer training step additionally saves {x, t2, a} for the weight grads.
+    Layer scale is folded into the second weight matrix (gamma W2, gamma b2), so `out` is one GEMM with a
+    residual epilogue and the backward needs no separate scale pass.
     """
 
     @staticmethod
@@ -177,43 +212,58 @@ class _ConvNeXtBlock(Function):
         B, H, W, C = x.shape
         M = B * H * W
         pg = not _INPUT_GRAD_ONLY[0]
+        P = _prepared(w1, w2, b2, gamma)
         wt = _f32(dw_w).reshape(C, 49).t().contiguous()                 # tap-major [49][C]
-        lnw, lnb, b1f, b2f, gf = _f32(ln_w), _f32(ln_b), _f32(b1), _f32(b2), _f32(gamma)
-        w1b, w2b = w1.detach().to(BF16), w2.detach().to(BF16)
+        lnw, lnb, b1f = _f32(ln_w), _f32(ln_b), _f32(b1)
         t1 = torch.empty_like(x)
         _abi.dwconv7_fwd(x, wt, _f32(dw_b), t1)
         t2 = torch.empty_like(x)
         mean = torch.empty(M, device=x.device, dtype=torch.float32)
         rstd = torch.empty_like(mean)
         _abi.ln_fwd(t1, lnw, lnb, t2, mean, rstd, 1e-6, False)
-        z = _gemm_nt(t2.view(M, C), w1b)
-        a = torch.empty_like(z)
-        _abi.bias_gelu_fwd(z, b1f, a)
-        z2 = _gemm_nt(a, w2b)
-        out = torch.empty_like(x)
-        _abi.scale_residual_fwd(z2, b2f, gf, x.view(M, C), out.view(M, C))
-        ctx.param_grads = pg
-        if pg:
-            ctx.save_for_backward(t1, mean, rstd, z, wt, lnw, lnb, b1f, b2f, gf, w1b, w2b, x, t2, a, z2)
+        if 'gelu' in TCGEN05:
+            z = torch.empty(M, 4 * C, device=x.device, dtype=BF16)      # pre-activation INCLUDING the bias
+            a = _gemm(t2.view(M, C), P['w1b'], _abi.EPI_BIAS_GELU, bias=b1f, c2=z)
+            zb = None
         else:
-            ctx.save_for_backward(t1, mean, rstd, z, wt, lnw, lnb, b1f, b2f, gf, w1b, w2b)
+            z = t2.view(M, C) @ P['w1b'].t()                            # cuBLAS; bias added inside the kernels
+            a = torch.empty_like(z)
+            _abi.bias_gelu_fwd(z, b1f, a)
+            zb = b1f
+        if 'residual' in TCGEN05:
+            out = _gemm(a, P['w2g'], _abi.EPI_RESIDUAL, bias=P['b2g'], aux=x.view(M, C)).view(B, H, W, C)
+        else:
+            z2 = a @ P['w2g'].t()
+            out = torch.empty_like(x)
+            _abi.scale_residual_fwd(z2, P['b2g'], torch.ones_like(P['gf']), x.view(M, C), out.view(M, C))
+        ctx.param_grads = pg
+        ctx.zb = zb
+        ctx.prep = P
+        keep = (t1, mean, rstd, z, wt, lnw, lnb)
+        ctx.save_for_backward(*(keep + ((x, t2, a, w2.detach(), _f32(b2)) if pg else ())))
         return out
 
     @staticmethod
     def backward(ctx, dout):
         sv = ctx.saved_tensors
-        t1, mean, rstd, z, wt, lnw, lnb, b1f, b2f, gf, w1b, w2b = sv[:12]
+        t1, mean, rstd, z, wt, lnw, lnb = sv[:7]
+        P = ctx.prep
         dout = dout.contiguous()
         B, H, W, C = dout.shape
         M = B * H * W
         pg = ctx.param_grads and any(ctx.needs_input_grad[1:])
         d2 = dout.view(M, C)
-        dz2 = torch.empty_like(d2)
-        _abi.scale_bwd(d2, gf, dz2)
-        da = dz2 @ w2b                                                  # [M,4C]
-        dz = torch.empty_like(da)
-        _abi.bias_gelu_bwd(da, z, b1f, dz)
-        dt2 = (dz @ w1b).view(B, H, W, C)
+        if 'gelu_grad' in TCGEN05 and ctx.zb is None:
+            dz = _gemm(d2, P['w2gt'], _abi.EPI_GELU_GRAD, aux=z)
+        else:
+            da = d2 @ P['w2g']                                          # [M,4C]  (layer scale already folded)
+            dz = torch.empty_like(da)
+            zero = ctx.zb if ctx.zb is not None else torch.zeros(4 * C, device=dout.device, dtype=torch.float32)
+            _abi.bias_gelu_bwd(da, z, zero, dz)
+        if 'dgrad1' in TCGEN05:
+            dt2 = _gemm(dz, P['w1t']).view(B, H, W, C)
+        else:
+            dt2 = (dz @ P['w1b']).view(B, H, W, C)
         dt1 = torch.empty_like(dt2)
         dlnw = torch.zeros_like(lnw) if pg else None
         dlnb = torch.zeros_like(lnb) if pg else None
@@ -222,16 +272,18 @@ class _ConvNeXtBlock(Function):
         _abi.dwconv7_fwd(dt1, wt.flip(0).contiguous(), None, dx, add=dout)   # + residual gradient
         if not pg:
             return (dx,) + (None,) * 9
-        x, t2, a, z2 = sv[12:]
+        x, t2, a, w2, b2f = sv[7:]
+        gf = P['gf']
         ddw = torch.zeros(49, C, device=dout.device, dtype=torch.float32)
         ddb = torch.zeros(C, device=dout.device, dtype=torch.float32)
         _abi.dwconv7_wgrad(x, dt1, ddw, ddb)
         dw1 = (dz.t() @ t2.view(M, C)).float()
         db1 = dz.sum(0, dtype=torch.float32)
-        dw2 = (dz2.t() @ a).float()
+        dw2g = (d2.t() @ a).float()                                     # gradient w.r.t. gamma-folded W2
         col = d2.sum(0, dtype=torch.float32)
+        dw2 = gf[:, None] * dw2g
         db2 = col * gf
-        dgamma = (d2.float() * z2.float()).sum(0) + col * b2f
+        dgamma = (dw2g * w2.float()).sum(1) + col * b2f
         return dx, ddw.t().reshape(C, 1, 7, 7), ddb, dlnw, dlnb, dw1, db1, dw2, db2, dgamma
 
 

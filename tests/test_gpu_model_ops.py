@@ -99,9 +99,12 @@ def test_bias_gelu_and_scale_residual(ops, cuda_dev):
     _close(got[3], rg[3], atol=1e-6)
 
 
+@pytest.mark.parametrize('tc', ['', 'residual,dgrad1', 'residual,dgrad1,gelu,gelu_grad'])
 @pytest.mark.parametrize('shape', [(2, 28, 28, 96), (3, 7, 7, 192)])
-def test_block_function_fwd_bwd(ops, cuda_dev, shape):
-    """whole-block autograd node vs the fp32 reference block (all gradients), and the input-grad-only mode"""
+def test_block_function_fwd_bwd(ops, cuda_dev, shape, tc, monkeypatch):
+    """whole-block autograd node vs the fp32 reference block (all gradients), and the input-grad-only mode;
+    `tc` = which pwconv GEMMs run on the tcgen05 kernel (the others: cuBLAS + elementwise kernels)"""
+    monkeypatch.setattr(ops, 'TCGEN05', set(filter(None, tc.split(','))))
     B, H, W, C = shape
     g = torch.Generator(device='cuda').manual_seed(C)
     rnd = lambda *s, k=1.0: (torch.randn(*s, generator=g, device=cuda_dev) * k)
