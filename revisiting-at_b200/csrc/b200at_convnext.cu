@@ -12,6 +12,7 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 
+#include "b200at_gelu.cuh"
 #include "../../include/b200at_model.h"
 
 namespace {
@@ -19,16 +20,14 @@ namespace {
 typedef __nv_bfloat16 bf16;
 typedef __nv_bfloat162 bf162;
 
-__device__ __forceinline__ float gelu_f(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f)); }
-__device__ __forceinline__ float gelu_grad_f(float v) {
-  const float cdf = 0.5f * (1.0f + erff(v * 0.70710678118654752f));
-  const float pdf = 0.3989422804014327f * __expf(-0.5f * v * v);
-  return cdf + v * pdf;
-}
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
+__device__ __forceinline__ float gelu_f(float v) { return b200at_gelu(v); }
+__device__ __forceinline__ float gelu_grad_f(float v) { return b200at_gelu_grad(v); }
+// packed fp32x2 FMA (sm_100 FFMA2): one issue slot for the two channels a thread carries
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b),
+                     rc = *reinterpret_cast<unsigned long long*>(&c), rd;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  return *reinterpret_cast<float2*>(&rd);
 }
 __device__ __forceinline__ void unpack4(const uint2& u, float* f) {
   const float2 a = __bfloat1622float2(*reinterpret_cast<const bf162*>(&u.x));
@@ -313,7 +312,7 @@ __global__ void __launch_bounds__(256) dwconv7_kernel(const bf16* __restrict__ x
                                                       const float* __restrict__ bias, const bf16* __restrict__ add,
                                                       bf16* __restrict__ y, int H, int W, int C, int tiles_w,
                                                       int tiles_h) {
-  __shared__ bf162 tile[kDwIn][kDwIn][kDwCh / 2];
+  __shared__ __align__(16) bf162 tile[kDwIn][kDwIn][kDwCh / 2];
   __shared__ float2 wsm[49][kDwCh / 2];
   const int cp = threadIdx.x & 15, t = threadIdx.x >> 4;
   const int cgroups = C / kDwCh;
@@ -324,14 +323,15 @@ __global__ void __launch_bounds__(256) dwconv7_kernel(const bf16* __restrict__ x
   const int n = bid;
   const int h0 = th * kDwTile, w0 = tw * kDwTile, c0 = cg * kDwCh;
   const bf16* xin = x + (int64_t)n * H * W * C;
-  // stage the (20 x 20) halo tile: 16 consecutive lanes fetch the 64 contiguous bytes of one pixel
-  for (int p = t; p < kDwIn * kDwIn; p += 16) {
-    const int r = p / kDwIn, c = p % kDwIn;
+  // stage the (20 x 20) halo tile: 4 consecutive lanes fetch the 64 contiguous bytes of one pixel (16 B each)
+  for (int q = threadIdx.x; q < kDwIn * kDwIn * 4; q += 256) {
+    const int pix = q >> 2, piece = q & 3;
+    const int r = pix / kDwIn, c = pix % kDwIn;
     const int hh = h0 + r - 3, ww = w0 + c - 3;
-    bf162 v = __floats2bfloat162_rn(0.f, 0.f);
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
     if (hh >= 0 && hh < H && ww >= 0 && ww < W)
-      v = *reinterpret_cast<const bf162*>(xin + ((int64_t)hh * W + ww) * C + c0 + cp * 2);
-    tile[r][c][cp] = v;
+      v = __ldg(reinterpret_cast<const uint4*>(xin + ((int64_t)hh * W + ww) * C + c0 + piece * 8));
+    *reinterpret_cast<uint4*>(&tile[r][c][piece * 4]) = v;
   }
   for (int k = t; k < 49; k += 16) wsm[k][cp] = make_float2(wt[k * C + c0 + cp * 2], wt[k * C + c0 + cp * 2 + 1]);
   __syncthreads();
@@ -351,10 +351,7 @@ __global__ void __launch_bounds__(256) dwconv7_kernel(const bf16* __restrict__ x
 #pragma unroll
       for (int i = 0; i < 7; ++i) {
         const int o = r - i;  // output row fed by input row r through tap row i
-        if (o >= 0 && o < kDwTile) {
-          acc[o].x = fmaf(v.x, wj[i].x, acc[o].x);
-          acc[o].y = fmaf(v.y, wj[i].y, acc[o].y);
-        }
+        if (o >= 0 && o < kDwTile) acc[o] = ffma2(v, wj[i], acc[o]);
       }
     }
   }
@@ -377,7 +374,7 @@ __global__ void __launch_bounds__(256) dwconv7_kernel(const bf16* __restrict__ x
 __global__ void __launch_bounds__(256) dwconv7_wgrad_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy,
                                                             float* __restrict__ dw, float* __restrict__ db, int H,
                                                             int W, int C, int tiles_w, int tiles_h) {
-  __shared__ bf162 tile[kDwIn][kDwIn][kDwCh / 2];
+  __shared__ __align__(16) bf162 tile[kDwIn][kDwIn][kDwCh / 2];
   __shared__ float2 red[16][kDwCh / 2];
   const int cp = threadIdx.x & 15, t = threadIdx.x >> 4;
   const int cgroups = C / kDwCh;
@@ -389,13 +386,15 @@ __global__ void __launch_bounds__(256) dwconv7_wgrad_kernel(const bf16* __restri
   const int h0 = th * kDwTile, w0 = tw * kDwTile, c0 = cg * kDwCh;
   const bf16* xin = x + (int64_t)n * H * W * C;
   const bf16* gin = dy + (int64_t)n * H * W * C;
-  for (int p = t; p < kDwIn * kDwIn; p += 16) {
-    const int r = p / kDwIn, c = p % kDwIn;
+  // stage the (20 x 20) halo tile: 4 consecutive lanes fetch the 64 contiguous bytes of one pixel (16 B each)
+  for (int q = threadIdx.x; q < kDwIn * kDwIn * 4; q += 256) {
+    const int pix = q >> 2, piece = q & 3;
+    const int r = pix / kDwIn, c = pix % kDwIn;
     const int hh = h0 + r - 3, ww = w0 + c - 3;
-    bf162 v = __floats2bfloat162_rn(0.f, 0.f);
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
     if (hh >= 0 && hh < H && ww >= 0 && ww < W)
-      v = *reinterpret_cast<const bf162*>(xin + ((int64_t)hh * W + ww) * C + c0 + cp * 2);
-    tile[r][c][cp] = v;
+      v = __ldg(reinterpret_cast<const uint4*>(xin + ((int64_t)hh * W + ww) * C + c0 + piece * 8));
+    *reinterpret_cast<uint4*>(&tile[r][c][piece * 4]) = v;
   }
   __syncthreads();
   // this thread's dy column (zero outside the image)
@@ -421,10 +420,7 @@ __global__ void __launch_bounds__(256) dwconv7_wgrad_kernel(const bf16* __restri
 #pragma unroll
         for (int i = 0; i < 7; ++i) {
           const int o = r - i;
-          if (o >= 0 && o < kDwTile) {
-            a[i].x = fmaf(v.x, g[o].x, a[i].x);
-            a[i].y = fmaf(v.y, g[o].y, a[i].y);
-          }
+          if (o >= 0 && o < kDwTile) a[i] = ffma2(v, g[o], a[i]);
         }
       }
     }

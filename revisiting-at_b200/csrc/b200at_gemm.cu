@@ -18,6 +18,7 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 
+#include "b200at_gelu.cuh"
 #include "../../include/b200at_model.h"
 
 namespace {
@@ -126,11 +127,8 @@ __device__ __forceinline__ uint4* stage_piece(uint8_t* tile, int row, int piece)
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-__device__ __forceinline__ float gelu_f(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f)); }
-__device__ __forceinline__ float gelu_grad_f(float v) {
-  const float cdf = 0.5f * (1.0f + erff(v * 0.70710678118654752f));
-  return cdf + v * 0.3989422804014327f * __expf(-0.5f * v * v);
-}
+__device__ __forceinline__ float gelu_f(float v) { return b200at_gelu(v); }
+__device__ __forceinline__ float gelu_grad_f(float v) { return b200at_gelu_grad(v); }
 __device__ __forceinline__ void unpack8(const uint4& u, float* f) {
   const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
