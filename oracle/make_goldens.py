@@ -22,7 +22,6 @@ from oracle.scripted_model import ScriptedModel           # noqa: E402
 from oracle.small_cnn import SmallCNN                     # noqa: E402
 
 OUT = os.path.join(ROOT, 'tests', 'golden')
-torch.set_num_threads(4)
 
 
 def scripted_inputs(seed, B, shape, C, n_calls, soft, in_box=False):
@@ -57,23 +56,28 @@ def scripted_inputs(seed, B, shape, C, n_calls, soft, in_box=False):
     return x, y, logits, grads
 
 
-def run_scripted(ref, name, norm, eps, n_iter, seed, soft=False, loss='ce', B=8, shape=(3, 12, 12), C=10,
-                 is_train=True):
+def compute_scripted(ref, norm, eps, n_iter, seed, soft=False, loss='ce', B=8, shape=(3, 12, 12), C=10,
+                     is_train=True):
+    """One scripted-model run of the reference; returns the fixture dict (also used live by the tests)."""
     x, y, logits, grads = scripted_inputs(seed, B, shape, C, n_iter + 1, soft, in_box=(norm == 'L1'))
     model = ScriptedModel(logits, grads)
     out = ref.apgd_train(model, x, y, norm=norm, eps=eps, n_iter=n_iter, loss=loss,
                          mixup=(object() if soft else None), is_train=is_train)
     x_best, acc, loss_best, x_best_adv = out
-    np.savez_compressed(
-        os.path.join(OUT, f'scripted_{name}.npz'),
+    return dict(
         norm=norm, eps=np.float64(eps), n_iter=n_iter, soft=soft, loss=loss, is_train=is_train,
         x=x.numpy(), y=y.numpy(), logits=logits.numpy(), grads=grads.numpy(),
         x_calls=torch.stack(model.seen).numpy(),
         x_best=x_best.numpy(), acc=acc.numpy(), loss_best=loss_best.numpy(), x_best_adv=x_best_adv.numpy())
-    print(f'scripted_{name}: acc={acc.float().mean():.2f} loss_best={loss_best.mean():.4f}')
 
 
-def run_cnn(ref, name, norm, eps, n_iter, seed):
+def run_scripted(ref, name, norm, eps, n_iter, seed, **kw):
+    d = compute_scripted(ref, norm, eps, n_iter, seed, **kw)
+    np.savez_compressed(os.path.join(OUT, f'scripted_{name}.npz'), **d)
+    print(f'scripted_{name}: acc={d["acc"].mean():.2f} loss_best={d["loss_best"].mean():.4f}')
+
+
+def compute_cnn(ref, norm, eps, n_iter, seed):
     torch.manual_seed(seed)
     model = SmallCNN().eval()
     g = torch.Generator().manual_seed(seed + 1)
@@ -81,10 +85,15 @@ def run_cnn(ref, name, norm, eps, n_iter, seed):
     y = torch.randint(0, 10, (8,), generator=g)
     x_best, acc, loss_best, x_best_adv = ref.apgd_train(model, x, y, norm=norm, eps=eps, n_iter=n_iter)
     sd = {'w_' + k.replace('.', '_'): v.numpy() for k, v in model.state_dict().items()}
-    np.savez_compressed(os.path.join(OUT, f'cnn_{name}.npz'), norm=norm, eps=np.float64(eps), n_iter=n_iter,
-                        x=x.numpy(), y=y.numpy(), x_best=x_best.numpy(), acc=acc.numpy(),
-                        loss_best=loss_best.numpy(), x_best_adv=x_best_adv.numpy(), **sd)
-    print(f'cnn_{name}: acc={acc.float().mean():.2f} loss_best={loss_best.mean():.4f}')
+    return dict(norm=norm, eps=np.float64(eps), n_iter=n_iter,
+                x=x.numpy(), y=y.numpy(), x_best=x_best.numpy(), acc=acc.numpy(),
+                loss_best=loss_best.numpy(), x_best_adv=x_best_adv.numpy(), **sd)
+
+
+def run_cnn(ref, name, norm, eps, n_iter, seed):
+    d = compute_cnn(ref, norm, eps, n_iter, seed)
+    np.savez_compressed(os.path.join(OUT, f'cnn_{name}.npz'), **d)
+    print(f'cnn_{name}: acc={d["acc"].mean():.2f} loss_best={d["loss_best"].mean():.4f}')
 
 
 def run_convnext(ref):
@@ -133,23 +142,33 @@ def run_fgsm():
     print('fgsm_cnn done')
 
 
+# name -> ((norm, eps, n_iter), kwargs of compute_scripted); the tests replay the same table live
+SCRIPTED_CASES = {}
+for _n in (1, 2, 10):
+    SCRIPTED_CASES[f'linf_n{_n}'] = (('Linf', 4 / 255., _n), dict(seed=10 + _n))
+    SCRIPTED_CASES[f'l2_n{_n}'] = (('L2', 0.5, _n), dict(seed=20 + _n))
+    SCRIPTED_CASES[f'l1_n{_n}'] = (('L1', 12., _n), dict(seed=30 + _n))
+SCRIPTED_CASES.update({
+    'linf_n25': (('Linf', 8 / 255., 25), dict(seed=41, B=5)),
+    'l1_n25': (('L1', 12., 25), dict(seed=42, B=5)),
+    'l1_n10_eval': (('L1', 12., 10), dict(seed=43, is_train=False)),
+    'linf_n2_soft': (('Linf', 4 / 255., 2), dict(seed=51, soft=True)),
+    'linf_n10_soft': (('Linf', 4 / 255., 10), dict(seed=52, soft=True)),
+    'linf_n10_dlr': (('Linf', 4 / 255., 10), dict(seed=53, loss='dlr')),
+    'linf_n2_b1': (('Linf', 4 / 255., 2), dict(seed=54, B=1)),
+})
+CNN_CASES = {f'{_norm.lower()}_n5': (_norm, _eps, 5, 7) for _norm, _eps in (('Linf', 4 / 255.), ('L2', 0.5), ('L1', 12.))}
+
+
 def main():
     assert ref_loader.available(), 'reference not mounted'
+    torch.set_num_threads(4)
     os.makedirs(OUT, exist_ok=True)
     ref = ref_loader.attack_module()
-    for n_iter in (1, 2, 10):
-        run_scripted(ref, f'linf_n{n_iter}', 'Linf', 4 / 255., n_iter, seed=10 + n_iter)
-        run_scripted(ref, f'l2_n{n_iter}', 'L2', 0.5, n_iter, seed=20 + n_iter)
-        run_scripted(ref, f'l1_n{n_iter}', 'L1', 12., n_iter, seed=30 + n_iter)
-    run_scripted(ref, 'linf_n25', 'Linf', 8 / 255., 25, seed=41, B=5)
-    run_scripted(ref, 'l1_n25', 'L1', 12., 25, seed=42, B=5)
-    run_scripted(ref, 'l1_n10_eval', 'L1', 12., 10, seed=43, is_train=False)
-    run_scripted(ref, 'linf_n2_soft', 'Linf', 4 / 255., 2, seed=51, soft=True)
-    run_scripted(ref, 'linf_n10_soft', 'Linf', 4 / 255., 10, seed=52, soft=True)
-    run_scripted(ref, 'linf_n10_dlr', 'Linf', 4 / 255., 10, seed=53, loss='dlr')
-    run_scripted(ref, 'linf_n2_b1', 'Linf', 4 / 255., 2, seed=54, B=1)
-    for norm, eps in (('Linf', 4 / 255.), ('L2', 0.5), ('L1', 12.)):
-        run_cnn(ref, f'{norm.lower()}_n5', norm, eps, 5, seed=7)
+    for name, (args, kw) in SCRIPTED_CASES.items():
+        run_scripted(ref, name, *args, **kw)
+    for name, args in CNN_CASES.items():
+        run_cnn(ref, name, *args)
     run_convnext(ref)
     run_fgsm()
 
