@@ -27,8 +27,13 @@ int b200at_ln_bwd(const void* dy, const void* x, const float* w, const float* b,
 
 /* models/convnext.py:30-31: h = GELU(z + bias) on the 4C hidden (z = x @ W1^T from the GEMM), N % 8 == 0 */
 int b200at_bias_gelu_fwd(const void* z, const float* bias, void* h, int64_t M, int64_t N, void* stream);
-/* dz = dh * GELU'(z + bias) */
-int b200at_bias_gelu_bwd(const void* dh, const void* z, const float* bias, void* dz, int64_t M, int64_t N, void* stream);
+/* dz = dh * GELU'(z + bias); if dbias is non-null also ACCUMULATES the pwconv1 bias gradient
+ * dbias[n] += sum_m dz[m][n] (fp32 [N], caller zeroes) in the same pass.  N <= 8192. */
+int b200at_bias_gelu_bwd(const void* dh, const void* z, const float* bias, void* dz, float* dbias, int64_t M, int64_t N,
+                         void* stream);
+/* out[n] += sum_m a[m][n] (a bf16 [M][N], out fp32 [N], caller zeroes): bias gradients of `pwconv2` /
+ * column sums of an upstream gradient (models/convnext.py:32,45).  N % 8 == 0, N <= 8192. */
+int b200at_colsum_bf16(const void* a, float* out, int64_t M, int64_t N, void* stream);
 
 /* models/convnext.py:45-49: out = res + gamma * (z + bias)  (layer scale + residual), N % 8 == 0 */
 int b200at_scale_residual_fwd(const void* z, const float* bias, const float* gamma, const void* res, void* out,
@@ -47,6 +52,23 @@ int b200at_dwconv7_fwd(const void* x, const float* wt, const float* bias, const 
 /* weight / bias gradients, ACCUMULATED into dw [49][C] and db [C] (fp32, caller zeroes) */
 int b200at_dwconv7_wgrad(const void* x, const void* dy, float* dw, float* db, int64_t B, int64_t H, int64_t W,
                          int64_t C, void* stream);
+
+/* First stage of the CvSt stems as one kernel (utils_architecture.py:198-217 ConvBlock1, :174-195 ConvBlock3:
+ * `nn.Conv2d(3, C0, 3, stride=2, padding=1)` -> channels-first LayerNorm (:57-81) -> GELU), with the
+ * ImageNormalizer (:86-98) folded in:  y = GELU(LN(conv((x - mean) / std) + bias)).
+ * x: fp32 NCHW [B][3][H][W] (the attack's iterate, read as is); y: NHWC bf16 [B][Ho][Wo][C0], Ho = (H-1)/2+1.
+ * wk: fp32 [27][C0], wk[c*9+kh*3+kw][co] = weight[co][c][kh][kw].  mean3 / std3: HOST pointers to 3 floats, or
+ * null for no normalisation.  C0 in {48, 64, 96}.  Used for the attack's evaluations (no weight gradients);
+ * the training forward keeps the library convolution, whose weight gradient it needs. */
+int b200at_stem0_fwd(const float* x, const float* mean3, const float* std3, const float* wk, const float* bias,
+                     const float* ln_w, const float* ln_b, void* y, int64_t B, int64_t H, int64_t W, int64_t C0,
+                     float eps, void* stream);
+/* dL/dx (fp32 NCHW, every element written) of the above given dy = dL/dy (NHWC bf16): the attack's
+ * `torch.autograd.grad(loss, [x_adv])` (autopgd_train_clean.py:185,283) through the first layer.  Recomputes the
+ * pre-LayerNorm activation from x; nothing is saved by the forward. */
+int b200at_stem0_bwd_input(const void* dy, const float* x, const float* mean3, const float* std3, const float* wk,
+                           const float* bias, const float* ln_w, const float* ln_b, float* dx, int64_t B, int64_t H,
+                           int64_t W, int64_t C0, float eps, void* stream);
 
 /* models/convnext.py:30,32 `pwconv1` / `pwconv2` (nn.Linear on the NHWC rows) and their input gradients:
  *     C[M,N] = epilogue(A[M,K] . B[N,K]^T),  A, B, C bf16 row-major, fp32 accumulation in TMEM.

@@ -91,13 +91,16 @@ def _declare(L):
         'b200at_ln_fwd': [P, P, P, P, P, P, I64, I64, F, I, P],
         'b200at_ln_bwd': [P, P, P, P, P, P, P, P, P, I64, I64, I, P],
         'b200at_bias_gelu_fwd': [P, P, P, I64, I64, P],
-        'b200at_bias_gelu_bwd': [P, P, P, P, I64, I64, P],
+        'b200at_bias_gelu_bwd': [P, P, P, P, P, I64, I64, P],
+        'b200at_colsum_bf16': [P, P, I64, I64, P],
         'b200at_scale_residual_fwd': [P, P, P, P, P, I64, I64, P],
         'b200at_scale_bwd': [P, P, P, I64, I64, P],
         'b200at_add_bf16': [P, P, P, I64, P],
         'b200at_dwconv7_fwd': [P, P, P, P, P, I64, I64, I64, I64, P],
         'b200at_dwconv7_wgrad': [P, P, P, P, I64, I64, I64, I64, P],
         'b200at_gemm_bf16': [P, P, P, P, P, P, I64, I64, I64, I, P],
+        'b200at_stem0_fwd': [P, P, P, P, P, P, P, P, I64, I64, I64, I64, F, P],
+        'b200at_stem0_bwd_input': [P, P, P, P, P, P, P, P, P, I64, I64, I64, I64, I64, F, P],
     })
     for name, args in sig.items():
         fn = getattr(L, name)
@@ -283,11 +286,19 @@ def bias_gelu_fwd(z, bias, h):
         _check(lib().b200at_bias_gelu_fwd(_act(z, 'z'), _par(bias, 'bias', N), _act(h, 'h'), M, N, _stream()), 'bias_gelu_fwd')
 
 
-def bias_gelu_bwd(dh, z, bias, dz):
+def bias_gelu_bwd(dh, z, bias, dz, dbias=None):
+    """dz = dh * GELU'(z + bias); dbias (fp32 [N], zeroed by the caller) also receives the column sums of dz."""
     M, N = z.shape
     with _Timed('bias_gelu_bwd'):
-        _check(lib().b200at_bias_gelu_bwd(_act(dh, 'dh'), _act(z, 'z'), _par(bias, 'bias', N), _act(dz, 'dz'), M, N,
-                                          _stream()), 'bias_gelu_bwd')
+        _check(lib().b200at_bias_gelu_bwd(_act(dh, 'dh'), _act(z, 'z'), _par(bias, 'bias', N), _act(dz, 'dz'),
+                                          _par(dbias, 'dbias', N), M, N, _stream()), 'bias_gelu_bwd')
+
+
+def colsum_bf16(a, out):
+    """out[n] += sum_m a[m][n]"""
+    M, N = a.shape
+    with _Timed('colsum_bf16'):
+        _check(lib().b200at_colsum_bf16(_act(a, 'a'), _par(out, 'out', N), M, N, _stream()), 'colsum_bf16')
 
 
 def scale_residual_fwd(z, bias, gamma, res, out):
@@ -322,6 +333,42 @@ def dwconv7_wgrad(x, dy, dw, db):
     with _Timed('dwconv7_wgrad'):
         _check(lib().b200at_dwconv7_wgrad(_act(x, 'x'), _act(dy, 'dy'), _par(dw, 'dw', 49 * C), _par(db, 'db', C),
                                           B, H, W, C, _stream()), 'dwconv7_wgrad')
+
+
+def _host3(v):
+    return (c_float * 3)(*[float(t) for t in v]) if v is not None else None
+
+
+def _x_nchw(x):
+    if not x.is_cuda or x.dtype != torch.float32 or x.dim() != 4 or x.shape[1] != 3 or not x.is_contiguous():
+        raise B200atError(f'stem0: x must be a contiguous CUDA fp32 NCHW image batch with 3 channels, got {x.dtype} '
+                          f'{tuple(x.shape)} strides {x.stride()} on {x.device}')
+    return c_void_p(x.data_ptr())
+
+
+def stem0_fwd(x, mean3, std3, wk, bias, ln_w, ln_b, y, eps=1e-6):
+    """y[B,Ho,Wo,C0] bf16 NHWC = GELU(LN(conv3x3s2((x - mean) / std) + bias)); mean3 / std3: 3 python floats or None."""
+    B, _, H, W = x.shape
+    C0 = bias.numel()
+    if tuple(y.shape) != (B, (H - 1) // 2 + 1, (W - 1) // 2 + 1, C0):
+        raise B200atError(f'stem0_fwd: y shape {tuple(y.shape)}')
+    m, sd = _host3(mean3), _host3(std3)
+    with _Timed('stem0_fwd'):
+        _check(lib().b200at_stem0_fwd(_x_nchw(x), m, sd, _par(wk, 'wk', 27 * C0), _par(bias, 'bias', C0),
+                                      _par(ln_w, 'ln_w', C0), _par(ln_b, 'ln_b', C0), _act(y, 'y'), B, H, W, C0, eps,
+                                      _stream()), 'stem0_fwd')
+
+
+def stem0_bwd_input(dy, x, mean3, std3, wk, bias, ln_w, ln_b, dx, eps=1e-6):
+    B, _, H, W = x.shape
+    C0 = bias.numel()
+    if tuple(dy.shape) != (B, (H - 1) // 2 + 1, (W - 1) // 2 + 1, C0) or dx.shape != x.shape:
+        raise B200atError(f'stem0_bwd_input: dy {tuple(dy.shape)} dx {tuple(dx.shape)}')
+    m, sd = _host3(mean3), _host3(std3)
+    with _Timed('stem0_bwd_input'):
+        _check(lib().b200at_stem0_bwd_input(_act(dy, 'dy'), _x_nchw(x), m, sd, _par(wk, 'wk', 27 * C0),
+                                            _par(bias, 'bias', C0), _par(ln_w, 'ln_w', C0), _par(ln_b, 'ln_b', C0),
+                                            _x_nchw(dx), B, H, W, C0, eps, _stream()), 'stem0_bwd_input')
 
 
 def _slot_ptrs(ts, like, name):

@@ -229,24 +229,72 @@ __global__ void __launch_bounds__(256) bias_gelu_fwd_kernel(const bf16* __restri
   }
 }
 
-// dz = dh * gelu'(z + bias)
+// dz = dh * gelu'(z + bias);  DBIAS: also dbias[c] += sum_rows dz[.,c] (the pwconv1 bias gradient).  The launcher
+// makes the total thread count a multiple of n8, so a thread keeps its 8 columns for the whole grid-stride loop
+// and carries their partial sums in registers; one shared-memory + one global atomic pass at the end.
+template <bool DBIAS>
 __global__ void __launch_bounds__(256) bias_gelu_bwd_kernel(const bf16* __restrict__ dh, const bf16* __restrict__ z,
                                                             const float* __restrict__ bias, bf16* __restrict__ dz,
-                                                            int64_t total8, int n8) {
-  for (int64_t q = (int64_t)blockIdx.x * 256 + threadIdx.x; q < total8; q += (int64_t)gridDim.x * 256) {
-    const int c0 = (int)(q % n8) * 8;
+                                                            float* __restrict__ dbias, int64_t total8, int n8) {
+  extern __shared__ float colred[];   // DBIAS: [8 * n8]
+  const int64_t q0 = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  const int c0 = (int)(q0 % n8) * 8;
+  const float4 b0 = *reinterpret_cast<const float4*>(bias + c0), b1 = *reinterpret_cast<const float4*>(bias + c0 + 4);
+  const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+  float acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+  if (DBIAS) {
+    for (int c = threadIdx.x; c < 8 * n8; c += 256) colred[c] = 0.f;
+    __syncthreads();
+  }
+  for (int64_t q = q0; q < total8; q += (int64_t)gridDim.x * 256) {
     const uint4 u = __ldcs(reinterpret_cast<const uint4*>(z) + q);
     const uint4 d = __ldcs(reinterpret_cast<const uint4*>(dh) + q);
     float f[8], g[8];
     unpack4(make_uint2(u.x, u.y), f); unpack4(make_uint2(u.z, u.w), f + 4);
     unpack4(make_uint2(d.x, d.y), g); unpack4(make_uint2(d.z, d.w), g + 4);
-    const float4 b0 = *reinterpret_cast<const float4*>(bias + c0), b1 = *reinterpret_cast<const float4*>(bias + c0 + 4);
-    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
     for (int k = 0; k < 8; ++k) g[k] *= gelu_grad_f(f[k] + bb[k]);
     const uint2 lo = pack4(g), hi = pack4(g + 4);
     reinterpret_cast<uint4*>(dz)[q] = make_uint4(lo.x, lo.y, hi.x, hi.y);
+    if (DBIAS) {   // sum what the weight-gradient GEMM will see: the bf16-rounded dz
+      float r[8];
+      unpack4(lo, r); unpack4(hi, r + 4);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] += r[k];
+    }
   }
+  if (DBIAS) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) atomicAdd(&colred[c0 + k], acc[k]);
+    __syncthreads();
+    for (int c = threadIdx.x; c < 8 * n8; c += 256) atomicAdd(dbias + c, colred[c]);
+  }
+}
+
+// colsum[c] += sum_rows a[.,c]  on [M][N] bf16 (bias gradients of the second pwconv: column sums of dout)
+__global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ a, float* __restrict__ out, int64_t total8,
+                                                     int n8) {
+  extern __shared__ float colred[];
+  const int64_t q0 = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  const int c0 = (int)(q0 % n8) * 8;
+  float acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+  for (int c = threadIdx.x; c < 8 * n8; c += 256) colred[c] = 0.f;
+  __syncthreads();
+  for (int64_t q = q0; q < total8; q += (int64_t)gridDim.x * 256) {
+    const uint4 u = __ldcs(reinterpret_cast<const uint4*>(a) + q);
+    float f[8];
+    unpack4(make_uint2(u.x, u.y), f); unpack4(make_uint2(u.z, u.w), f + 4);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] += f[k];
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) atomicAdd(&colred[c0 + k], acc[k]);
+  __syncthreads();
+  for (int c = threadIdx.x; c < 8 * n8; c += 256) atomicAdd(out + c, colred[c]);
 }
 
 // out = res + gamma * (z + bias)   (layer scale + residual; models/convnext.py:45-49)
@@ -456,6 +504,18 @@ inline int flat_grid(int64_t total8) {
   return (int)(g < cap ? (g < 1 ? 1 : g) : cap);
 }
 
+// grid whose thread count (256 per CTA) is a multiple of n8, so a grid-stride thread keeps its column group
+inline int column_grid(int64_t total8, int n8, int ctas_per_sm) {
+  int a = n8, b = 256;
+  while (b) { const int t = a % b; a = b; b = t; }     // a = gcd(n8, 256)
+  const int unit = n8 / a;                             // grid must be a multiple of this
+  int64_t want = (total8 + 255) / 256;
+  const int64_t cap = 148 * (int64_t)ctas_per_sm;
+  if (want > cap) want = cap;
+  int64_t g = (want + unit - 1) / unit * unit;
+  return (int)(g < unit ? unit : g);
+}
+
 // (G, VPL) with the best lane utilisation for nv = C/4 vectors per row; ties go to the wider group
 inline void ln_shape(int nv, int& G, int& VPL) {
   double best = -1.0;
@@ -538,11 +598,26 @@ int b200at_bias_gelu_fwd(const void* z, const float* bias, void* h, int64_t M, i
   return (int)cudaGetLastError();
 }
 
-int b200at_bias_gelu_bwd(const void* dh, const void* z, const float* bias, void* dz, int64_t M, int64_t N, void* stream) {
+int b200at_bias_gelu_bwd(const void* dh, const void* z, const float* bias, void* dz, float* dbias, int64_t M, int64_t N,
+                         void* stream) {
   if (M <= 0) return 0;
-  if (N % 8) return (int)cudaErrorInvalidValue;
+  if (N % 8 || N > 8192) return (int)cudaErrorInvalidValue;
   const int64_t total8 = M * N / 8;
-  bias_gelu_bwd_kernel<<<flat_grid(total8), 256, 0, (cudaStream_t)stream>>>((const bf16*)dh, (const bf16*)z, bias, (bf16*)dz, total8, (int)(N / 8));
+  const int n8 = (int)(N / 8);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dbias)
+    bias_gelu_bwd_kernel<true><<<column_grid(total8, n8, 8), 256, sizeof(float) * N, s>>>((const bf16*)dh, (const bf16*)z, bias, (bf16*)dz, dbias, total8, n8);
+  else
+    bias_gelu_bwd_kernel<false><<<column_grid(total8, n8, 16), 256, 0, s>>>((const bf16*)dh, (const bf16*)z, bias, (bf16*)dz, nullptr, total8, n8);
+  return (int)cudaGetLastError();
+}
+
+int b200at_colsum_bf16(const void* a, float* out, int64_t M, int64_t N, void* stream) {
+  if (M <= 0) return 0;
+  if (N % 8 || N > 8192) return (int)cudaErrorInvalidValue;
+  const int64_t total8 = M * N / 8;
+  const int n8 = (int)(N / 8);
+  colsum_kernel<<<column_grid(total8, n8, 4), 256, sizeof(float) * N, (cudaStream_t)stream>>>((const bf16*)a, out, total8, n8);
   return (int)cudaGetLastError();
 }
 

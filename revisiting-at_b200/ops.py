@@ -11,6 +11,7 @@ round-1 baseline (profiles/r01_launches_summary_torch_model.txt) shows them at ~
 ~85 % for the memory-bound ops, which is why those were written first.
 """
 import os
+import weakref
 
 import torch
 import torch.nn.functional as F
@@ -83,21 +84,21 @@ class _DwConv7(Function):
     def forward(ctx, x, w, b):
         x = x.contiguous()
         C = x.shape[-1]
-        wt = w.detach().float().reshape(C, 49).t().contiguous()          # tap-major [49][C]
+        wt = _taps(w)
         y = torch.empty_like(x)
         _abi.dwconv7_fwd(x, wt, b.detach().float().contiguous(), y)
-        ctx.save_for_backward(x, wt)
+        ctx.save_for_backward(x, _taps_flipped(w))
         ctx.param_grads = not _INPUT_GRAD_ONLY[0]
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, wt = ctx.saved_tensors
+        x, wtf = ctx.saved_tensors
         dy = dy.contiguous()
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
-            _abi.dwconv7_fwd(dy, wt.flip(0).contiguous(), None, dx)        # correlation with the flipped taps
+            _abi.dwconv7_fwd(dy, wtf, None, dx)                            # correlation with the flipped taps
         if _wants(ctx, 1, 2):
             C = x.shape[-1]
             dwt = torch.zeros(49, C, device=x.device, dtype=torch.float32)
@@ -122,8 +123,8 @@ class _BiasGelu(Function):
     def backward(ctx, dh):
         z, bf = ctx.saved_tensors
         dz = torch.empty_like(z)
-        _abi.bias_gelu_bwd(dh.contiguous(), z, bf, dz)
-        db = dz.sum(0, dtype=torch.float32) if _wants(ctx, 1) else None
+        db = torch.zeros_like(bf) if _wants(ctx, 1) else None
+        _abi.bias_gelu_bwd(dh.contiguous(), z, bf, dz, db)
         return dz, db
 
 
@@ -166,15 +167,46 @@ def _f32(t):
 TCGEN05 = set(filter(None, os.environ.get('B200AT_TCGEN05', 'residual,dgrad1').split(',')))
 
 _WCACHE = {}
+_PCACHE = {}
+
+
+def _derived(param, tag, fn):
+    """Kernel-side copy of a parameter (cast / transposed / flipped), rebuilt only when the parameter changes
+    (its version counter moves once per optimiser step); shared by the 4 forwards + 3 backwards of a step."""
+    key = (id(param), tag)
+    hit = _PCACHE.get(key)
+    if hit is not None and hit[2]() is param and hit[0] == (param._version, param.data_ptr()):
+        return hit[1]
+    with torch.no_grad():
+        val = fn(param.detach())
+    if len(_PCACHE) > 4096:                                  # models that came and went (tests)
+        for k in [k for k, v in _PCACHE.items() if v[2]() is None]:
+            del _PCACHE[k]
+    _PCACHE[key] = ((param._version, param.data_ptr()), val, weakref.ref(param))
+    return val
+
+
+def _taps(dw_w):
+    """depthwise weight [C,1,7,7] -> tap-major fp32 [49][C]"""
+    return _derived(dw_w, 'taps', lambda w: w.float().reshape(w.shape[0], 49).t().contiguous())
+
+
+def _taps_flipped(dw_w):
+    """taps of the input-gradient correlation (180-degree rotated kernel)"""
+    return _derived(dw_w, 'taps_flip', lambda w: w.float().reshape(w.shape[0], 49).t().flip(0).contiguous())
+
+
+def _bf16(p):
+    return _derived(p, 'bf16', lambda w: w.to(BF16).contiguous())
 
 
 def _prepared(w1, w2, b2, gamma):
     """bf16 / transposed / layer-scale-folded copies of the block's MLP weights, rebuilt only when a
     parameter changes (once per optimiser step; shared by the 4 forwards + 3 backwards of a step)."""
-    key = (w1.data_ptr(), w2.data_ptr(), b2.data_ptr(), gamma.data_ptr())
-    ver = (w1._version, w2._version, b2._version, gamma._version)
+    key = (id(w1), id(w2), id(b2), id(gamma))
+    ver = (w1._version, w2._version, b2._version, gamma._version, w1.data_ptr(), w2.data_ptr())
     hit = _WCACHE.get(key)
-    if hit is not None and hit[0] == ver:
+    if hit is not None and hit[0] == ver and hit[2]() is w1 and hit[3]() is w2:
         return hit[1]
     with torch.no_grad():
         gf = gamma.detach().float()
@@ -184,7 +216,10 @@ def _prepared(w1, w2, b2, gamma):
         w2gt = w2g.t().contiguous()                                     # [4C, C]   da = dout @ w2g == dout @ w2gt^T
         b2g = (gf * b2.detach().float()).contiguous()
         prep = dict(w1b=w1b, w1t=w1t, w2g=w2g, w2gt=w2gt, b2g=b2g, gf=gf.contiguous())
-    _WCACHE[key] = (ver, prep)
+    if len(_WCACHE) > 1024:
+        for k in [k for k, v in _WCACHE.items() if v[2]() is None]:
+            del _WCACHE[k]
+    _WCACHE[key] = (ver, prep, weakref.ref(w1), weakref.ref(w2))
     return prep
 
 
@@ -213,7 +248,7 @@ class _ConvNeXtBlock(Function):
         M = B * H * W
         pg = not _INPUT_GRAD_ONLY[0]
         P = _prepared(w1, w2, b2, gamma)
-        wt = _f32(dw_w).reshape(C, 49).t().contiguous()                 # tap-major [49][C]
+        wt, wtf = _taps(dw_w), _taps_flipped(dw_w)                      # tap-major [49][C]
         lnw, lnb, b1f = _f32(ln_w), _f32(ln_b), _f32(b1)
         t1 = torch.empty_like(x)
         _abi.dwconv7_fwd(x, wt, _f32(dw_b), t1)
@@ -239,27 +274,30 @@ class _ConvNeXtBlock(Function):
         ctx.param_grads = pg
         ctx.zb = zb
         ctx.prep = P
-        keep = (t1, mean, rstd, z, wt, lnw, lnb)
+        keep = (t1, mean, rstd, z, wtf, lnw, lnb)
         ctx.save_for_backward(*(keep + ((x, t2, a, w2.detach(), _f32(b2)) if pg else ())))
         return out
 
     @staticmethod
     def backward(ctx, dout):
         sv = ctx.saved_tensors
-        t1, mean, rstd, z, wt, lnw, lnb = sv[:7]
+        t1, mean, rstd, z, wtf, lnw, lnb = sv[:7]
         P = ctx.prep
         dout = dout.contiguous()
         B, H, W, C = dout.shape
         M = B * H * W
         pg = ctx.param_grads and any(ctx.needs_input_grad[1:])
         d2 = dout.view(M, C)
+        db1 = torch.zeros(4 * C, device=dout.device, dtype=torch.float32) if pg else None
         if 'gelu_grad' in TCGEN05 and ctx.zb is None:
             dz = _gemm(d2, P['w2gt'], _abi.EPI_GELU_GRAD, aux=z)
+            if pg:
+                _abi.colsum_bf16(dz, db1)
         else:
             da = d2 @ P['w2g']                                          # [M,4C]  (layer scale already folded)
             dz = torch.empty_like(da)
             zero = ctx.zb if ctx.zb is not None else torch.zeros(4 * C, device=dout.device, dtype=torch.float32)
-            _abi.bias_gelu_bwd(da, z, zero, dz)
+            _abi.bias_gelu_bwd(da, z, zero, dz, db1)                    # pwconv1 bias gradient rides along
         if 'dgrad1' in TCGEN05:
             dt2 = _gemm(dz, P['w1t']).view(B, H, W, C)
         else:
@@ -269,7 +307,7 @@ class _ConvNeXtBlock(Function):
         dlnb = torch.zeros_like(lnb) if pg else None
         _abi.ln_bwd(dt2, t1, lnw, lnb, mean, rstd, dt1, dlnw, dlnb, False)
         dx = torch.empty_like(dout)
-        _abi.dwconv7_fwd(dt1, wt.flip(0).contiguous(), None, dx, add=dout)   # + residual gradient
+        _abi.dwconv7_fwd(dt1, wtf, None, dx, add=dout)                  # + residual gradient
         if not pg:
             return (dx,) + (None,) * 9
         x, t2, a, w2, b2f = sv[7:]
@@ -278,9 +316,9 @@ class _ConvNeXtBlock(Function):
         ddb = torch.zeros(C, device=dout.device, dtype=torch.float32)
         _abi.dwconv7_wgrad(x, dt1, ddw, ddb)
         dw1 = (dz.t() @ t2.view(M, C)).float()
-        db1 = dz.sum(0, dtype=torch.float32)
         dw2g = (d2.t() @ a).float()                                     # gradient w.r.t. gamma-folded W2
-        col = d2.sum(0, dtype=torch.float32)
+        col = torch.zeros(C, device=dout.device, dtype=torch.float32)
+        _abi.colsum_bf16(d2, col)
         dw2 = gf[:, None] * dw2g
         db2 = col * gf
         dgamma = (dw2g * w2.float()).sum(1) + col * b2f
@@ -292,17 +330,68 @@ def convnext_block(x, dw_w, dw_b, ln_w, ln_b, w1, b1, w2, b2, gamma):
     return _ConvNeXtBlock.apply(x, dw_w, dw_b, ln_w, ln_b, w1, b1, w2, b2, gamma)
 
 
+def _cast(p):
+    """bf16 copy of a parameter for a library call.  When the parameter needs a gradient (outer training step)
+    the cast stays in the autograd graph; for the attack's input-grad-only evaluations it is cached."""
+    if _INPUT_GRAD_ONLY[0] or not torch.is_grad_enabled() or not p.requires_grad:
+        return _bf16(p)
+    return p.to(BF16)
+
+
+class _Stem0(Function):
+    """First stem stage in one kernel per direction (csrc/b200at_stem.cu): normalise -> conv3x3 s2 -> LN -> GELU.
+    Input-gradient only (the attack's evaluations); the forward saves nothing but its input."""
+
+    @staticmethod
+    def forward(ctx, x, wk, cb, lw, lb, mean3, std3):
+        B, _, H, W = x.shape
+        y = torch.empty(B, (H - 1) // 2 + 1, (W - 1) // 2 + 1, cb.numel(), device=x.device, dtype=BF16)
+        _abi.stem0_fwd(x, mean3, std3, wk, cb, lw, lb, y)
+        ctx.save_for_backward(x, wk, cb, lw, lb)
+        ctx.norm = (mean3, std3)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, wk, cb, lw, lb = ctx.saved_tensors
+        dx = torch.empty_like(x)
+        _abi.stem0_bwd_input(dy.contiguous(), x, ctx.norm[0], ctx.norm[1], wk, cb, lw, lb, dx)
+        return dx, None, None, None, None, None, None
+
+
+_HOST3 = {}
+
+
+def _host3(t):
+    """3 python floats of the normaliser's mean / std buffer (one D2H copy per buffer, then cached)."""
+    if t is None:
+        return None
+    key = (t.data_ptr(), t._version)
+    if key not in _HOST3:
+        _HOST3[key] = tuple(float(v) for v in t.detach().flatten().cpu())
+    return _HOST3[key]
+
+
+STEM0_KERNEL = os.environ.get('B200AT_STEM0', '1') == '1'
+
+
 def stem_layer(x, cw, cb, lw, lb, stride, first, mean=None, std=None):
-    """conv3x3 (cuDNN) -> LN over C + GELU (fused kernel).  First layer: x is fp32 NCHW in [0,1]
-    (normalised here when mean/std are given); later layers: x is NHWC bf16.  Returns NHWC bf16."""
+    """conv3x3 -> LN over C + GELU.  First layer: x is fp32 NCHW in [0,1] (normalised here when mean/std are
+    given); later layers: x is NHWC bf16.  Returns NHWC bf16.  The first layer of an attack evaluation (input
+    gradient only / no gradient) is the fused direct kernel; everything else is the library convolution
+    followed by the fused LN+GELU kernel."""
     _need_cuda(x)
+    if (first and STEM0_KERNEL and stride == 2 and cw.shape[0] in (48, 64, 96) and x.dtype == torch.float32
+            and (_INPUT_GRAD_ONLY[0] or not torch.is_grad_enabled())):
+        wk = _derived(cw, 'stem0_wk', lambda w: w.float().reshape(w.shape[0], 27).t().contiguous())   # [27][C0]
+        return _Stem0.apply(x.contiguous(), wk, _f32(cb), _f32(lw), _f32(lb), _host3(mean), _host3(std))
     if first:
         if mean is not None:
             x = (x - mean) / std
         x = x.to(BF16).contiguous(memory_format=torch.channels_last)
     else:
         x = x.permute(0, 3, 1, 2)                        # NHWC storage viewed as NCHW channels_last
-    y = F.conv2d(x, cw.to(BF16), cb.to(BF16), stride=stride, padding=1)
+    y = F.conv2d(x, _cast(cw), _cast(cb), stride=stride, padding=1)
     y = y.permute(0, 2, 3, 1)                            # -> NHWC view of the channels_last result
     return layer_norm(y, lw, lb, 1e-6, gelu=True)
 
@@ -310,7 +399,7 @@ def stem_layer(x, cw, cb, lw, lb, stride, first, mean=None, std=None):
 def downsample(x, ln_w, ln_b, cw, cb):
     """LN over C (kernel) -> conv2x2 s2 (cuDNN).  NHWC bf16 in/out."""
     y = layer_norm(x, ln_w, ln_b, 1e-6).permute(0, 3, 1, 2)
-    y = F.conv2d(y, cw.to(BF16), cb.to(BF16), stride=2)
+    y = F.conv2d(y, _cast(cw), _cast(cb), stride=2)
     return y.permute(0, 2, 3, 1)
 
 
@@ -318,4 +407,4 @@ def head(x, ln_w, ln_b, fw, fb):
     """global mean-pool -> LN -> Linear (tiny; library ops).  x NHWC bf16 -> logits bf16."""
     p = x.float().mean((1, 2))
     p = F.layer_norm(p, (p.shape[-1],), ln_w.float(), ln_b.float(), 1e-6)
-    return F.linear(p.to(BF16), fw.to(BF16), fb.to(BF16))
+    return F.linear(p.to(BF16), _cast(fw), _cast(fb))

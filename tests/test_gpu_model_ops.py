@@ -99,6 +99,46 @@ def test_bias_gelu_and_scale_residual(ops, cuda_dev):
     _close(got[3], rg[3], atol=1e-6)
 
 
+def test_colsum(cuda_dev):
+    from revisiting_at_b200 import _abi
+    g = torch.Generator(device='cuda').manual_seed(5)
+    for M, N in ((1000, 96), (4097, 384), (33, 3072), (1, 8)):
+        a = torch.randn(M, N, generator=g, device=cuda_dev).to(BF16)
+        out = torch.zeros(N, device=cuda_dev)
+        _abi.colsum_bf16(a, out)
+        _close(out, a.float().sum(0), atol=1e-3 * M ** 0.5, rtol=1e-5)
+
+
+@pytest.mark.parametrize('C0', [48, 64, 96])
+@pytest.mark.parametrize('shape,norm', [((2, 3, 64, 64), True), ((3, 3, 37, 45), False), ((1, 3, 224, 224), True)])
+def test_stem0_direct_kernels(ops, cuda_dev, C0, shape, norm):
+    """fused first stem stage (normalise -> conv3x3 s2 p1 -> LN -> GELU) and its input gradient vs fp32 torch"""
+    g = torch.Generator(device='cuda').manual_seed(C0 + shape[2])
+    x = torch.rand(*shape, generator=g, device=cuda_dev)
+    cw = (torch.randn(C0, 3, 3, 3, generator=g, device=cuda_dev) * 0.3)
+    cb = torch.randn(C0, generator=g, device=cuda_dev) * 0.1
+    lw = 1 + 0.2 * torch.randn(C0, generator=g, device=cuda_dev)
+    lb = 0.2 * torch.randn(C0, generator=g, device=cuda_dev)
+    mean = torch.tensor([0.485, 0.456, 0.406], device=cuda_dev).view(1, 3, 1, 1) if norm else None
+    std = torch.tensor([0.229, 0.224, 0.225], device=cuda_dev).view(1, 3, 1, 1) if norm else None
+    xr = x.clone().requires_grad_()
+    h = F.conv2d((xr - mean) / std if norm else xr, cw, cb, stride=2, padding=1).permute(0, 2, 3, 1)
+    ref = F.gelu(F.layer_norm(h, (C0,), lw, lb, 1e-6))
+    dy = torch.randn(ref.shape, generator=g, device=cuda_dev).to(BF16)
+    (rdx,) = torch.autograd.grad(ref, [xr], dy.float())
+    xt = x.clone().requires_grad_()
+    with ops.input_grad_only():
+        out = ops.stem_layer(xt, cw, cb, lw, lb, 2, True, mean, std)
+    assert out.dtype == BF16 and out.shape == ref.shape
+    assert out.grad_fn is not None and type(out.grad_fn).__name__.startswith('_Stem0')
+    _close(out, ref, atol=1e-2)                     # fp32 math, one bf16 rounding of the result
+    (dx,) = torch.autograd.grad(out, [xt], dy)
+    assert dx.dtype == torch.float32 and dx.shape == x.shape
+    _close(dx, rdx, atol=2e-3 * rdx.abs().max().item(), rtol=1e-3)   # fp32 math on the same bf16 dy
+    with torch.no_grad():
+        assert torch.equal(ops.stem_layer(x, cw, cb, lw, lb, 2, True, mean, std), out)
+
+
 @pytest.mark.parametrize('tc', ['', 'residual,dgrad1', 'residual,dgrad1,gelu,gelu_grad'])
 @pytest.mark.parametrize('shape', [(2, 28, 28, 96), (3, 7, 7, 192)])
 def test_block_function_fwd_bwd(ops, cuda_dev, shape, tc, monkeypatch):
@@ -159,6 +199,15 @@ def test_convnext_engine_matches_oracle(cuda_dev):
     assert (lm.float().cpu() - lo).abs().max() <= 5e-2, (lm.float().cpu() - lo).abs().max()
     cos = F.cosine_similarity(gm.cpu().flatten(1), go.flatten(1)).min().item()
     assert cos >= 0.98, cos
+    assert all(p.grad is None for p in m.parameters())
+    # the attack's evaluation mode (input-grad only: fused first stem stage, no weight gradients)
+    from revisiting_at_b200 import ops as O
+    xa = x.to(cuda_dev).requires_grad_()
+    with O.input_grad_only():
+        la = m(xa)
+    (ga,) = torch.autograd.grad(F.cross_entropy(la.float(), y.to(cuda_dev), reduction='sum'), xa)
+    assert (la.float().cpu() - lo).abs().max() <= 5e-2
+    assert F.cosine_similarity(ga.cpu().flatten(1), go.flatten(1)).min().item() >= 0.98
     assert all(p.grad is None for p in m.parameters())
     # full backward (outer training step): every parameter receives a finite gradient
     m.train()
