@@ -9,6 +9,7 @@ fp32 FMA rate, the GEMMs TFLOP/s.  CUDA events on the launching stream; buffers 
 """
 import argparse
 import os
+import re
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -32,7 +33,7 @@ def main():
     rows = []
 
     def timeit(name, fn, bytes_alg=0., flops=0., fma=0.):
-        if a.only and a.only not in name:
+        if a.only and not re.search(a.only, name):
             return
         if a.once:
             fn()

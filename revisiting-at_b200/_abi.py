@@ -100,7 +100,7 @@ def _declare(L):
         'b200at_dwconv7_wgrad': [P, P, P, P, I64, I64, I64, I64, P],
         'b200at_gemm_bf16': [P, P, P, P, P, P, I64, I64, I64, I, P],
         'b200at_stem0_fwd': [P, P, P, P, P, P, P, P, I64, I64, I64, I64, F, P],
-        'b200at_stem0_bwd_input': [P, P, P, P, P, P, P, P, P, I64, I64, I64, I64, I64, F, P],
+        'b200at_stem0_bwd_input': [P, P, P, P, P, P, P, P, P, I64, I64, I64, I64, F, P],
     })
     for name, args in sig.items():
         fn = getattr(L, name)

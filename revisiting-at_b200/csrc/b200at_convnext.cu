@@ -13,6 +13,7 @@
 #include <stdint.h>
 
 #include "b200at_gelu.cuh"
+#include "b200at_tma.cuh"
 #include "../../include/b200at_model.h"
 
 namespace {
@@ -212,20 +213,32 @@ __global__ void __launch_bounds__(kLnThreads) ln_bwd_kernel(const bf16* __restri
 }
 
 // ------------------------------------------------------------------------------------------------ K9
-// h = gelu(z + bias) on [M][N] bf16, 16 bytes per thread per iteration
+// h = gelu(z + bias) on [M][N] bf16, 16 bytes per thread per load, two loads in flight.  The launcher makes the
+// thread count a multiple of n8 = N/8, so a thread keeps its 8 columns (and their bias) for the whole loop.
 __global__ void __launch_bounds__(256) bias_gelu_fwd_kernel(const bf16* __restrict__ z, const float* __restrict__ bias,
                                                             bf16* __restrict__ h, int64_t total8, int n8) {
-  for (int64_t q = (int64_t)blockIdx.x * 256 + threadIdx.x; q < total8; q += (int64_t)gridDim.x * 256) {
-    const int c0 = (int)(q % n8) * 8;
-    const uint4 u = __ldcs(reinterpret_cast<const uint4*>(z) + q);
+  const int64_t q0 = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * 256;
+  const int c0 = (int)(q0 % n8) * 8;
+  const float4 b0 = *reinterpret_cast<const float4*>(bias + c0), b1 = *reinterpret_cast<const float4*>(bias + c0 + 4);
+  const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+  for (int64_t q = q0; q < total8; q += 2 * stride) {
+    const bool two = q + stride < total8;
+    const uint4 u0 = __ldcs(reinterpret_cast<const uint4*>(z) + q);
+    const uint4 u1 = two ? __ldcs(reinterpret_cast<const uint4*>(z) + q + stride) : u0;
     float f[8];
-    unpack4(make_uint2(u.x, u.y), f); unpack4(make_uint2(u.z, u.w), f + 4);
-    const float4 b0 = *reinterpret_cast<const float4*>(bias + c0), b1 = *reinterpret_cast<const float4*>(bias + c0 + 4);
-    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    unpack4(make_uint2(u0.x, u0.y), f); unpack4(make_uint2(u0.z, u0.w), f + 4);
 #pragma unroll
     for (int k = 0; k < 8; ++k) f[k] = gelu_f(f[k] + bb[k]);
-    const uint2 lo = pack4(f), hi = pack4(f + 4);
+    uint2 lo = pack4(f), hi = pack4(f + 4);
     reinterpret_cast<uint4*>(h)[q] = make_uint4(lo.x, lo.y, hi.x, hi.y);
+    if (two) {
+      unpack4(make_uint2(u1.x, u1.y), f); unpack4(make_uint2(u1.z, u1.w), f + 4);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) f[k] = gelu_f(f[k] + bb[k]);
+      lo = pack4(f); hi = pack4(f + 4);
+      reinterpret_cast<uint4*>(h)[q + stride] = make_uint4(lo.x, lo.y, hi.x, hi.y);
+    }
   }
 }
 
@@ -248,21 +261,30 @@ __global__ void __launch_bounds__(256) bias_gelu_bwd_kernel(const bf16* __restri
     for (int c = threadIdx.x; c < 8 * n8; c += 256) colred[c] = 0.f;
     __syncthreads();
   }
-  for (int64_t q = q0; q < total8; q += (int64_t)gridDim.x * 256) {
-    const uint4 u = __ldcs(reinterpret_cast<const uint4*>(z) + q);
-    const uint4 d = __ldcs(reinterpret_cast<const uint4*>(dh) + q);
-    float f[8], g[8];
-    unpack4(make_uint2(u.x, u.y), f); unpack4(make_uint2(u.z, u.w), f + 4);
-    unpack4(make_uint2(d.x, d.y), g); unpack4(make_uint2(d.z, d.w), g + 4);
+  const int64_t stride = (int64_t)gridDim.x * 256;
+  for (int64_t q = q0; q < total8; q += 2 * stride) {
+    const bool two = q + stride < total8;
+    uint4 u[2], d[2];
+    u[0] = __ldcs(reinterpret_cast<const uint4*>(z) + q);
+    d[0] = __ldcs(reinterpret_cast<const uint4*>(dh) + q);
+    u[1] = two ? __ldcs(reinterpret_cast<const uint4*>(z) + q + stride) : u[0];
+    d[1] = two ? __ldcs(reinterpret_cast<const uint4*>(dh) + q + stride) : d[0];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) g[k] *= gelu_grad_f(f[k] + bb[k]);
-    const uint2 lo = pack4(g), hi = pack4(g + 4);
-    reinterpret_cast<uint4*>(dz)[q] = make_uint4(lo.x, lo.y, hi.x, hi.y);
-    if (DBIAS) {   // sum what the weight-gradient GEMM will see: the bf16-rounded dz
-      float r[8];
-      unpack4(lo, r); unpack4(hi, r + 4);
+    for (int w = 0; w < 2; ++w) {
+      if (w == 1 && !two) break;
+      float f[8], g[8];
+      unpack4(make_uint2(u[w].x, u[w].y), f); unpack4(make_uint2(u[w].z, u[w].w), f + 4);
+      unpack4(make_uint2(d[w].x, d[w].y), g); unpack4(make_uint2(d[w].z, d[w].w), g + 4);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) acc[k] += r[k];
+      for (int k = 0; k < 8; ++k) g[k] *= gelu_grad_f(f[k] + bb[k]);
+      const uint2 lo = pack4(g), hi = pack4(g + 4);
+      reinterpret_cast<uint4*>(dz)[q + w * stride] = make_uint4(lo.x, lo.y, hi.x, hi.y);
+      if (DBIAS) {   // sum what the weight-gradient GEMM will see: the bf16-rounded dz
+        float r[8];
+        unpack4(lo, r); unpack4(hi, r + 4);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] += r[k];
+      }
     }
   }
   if (DBIAS) {
@@ -348,75 +370,157 @@ __global__ void __launch_bounds__(256) add_kernel(const bf16* __restrict__ a, co
 }
 
 // ------------------------------------------------------------------------------------------------ K7
-// Depthwise 7x7, stride 1, pad 3, NHWC bf16.  CTA = (TILE x TILE output pixels) x 32 channels of one image.
-// Thread (cp, t): channel pair cp (16 per CTA), output column t (TILE <= 16 columns).  The thread slides its
-// output column through the 7 input columns; each shared-memory load (one bf16x2) feeds up to 7 x 2 FMAs.
+// Depthwise 7x7, stride 1, pad 3, NHWC bf16 -- persistent, TMA-fed, double buffered, register tiled.
+// A CTA works through a contiguous run of tiles; a tile is (NB images) x (TH x TW output pixels) x 32 channels.
+// Its (TH+6) x (TW+6) halo box is ONE cp.async.bulk.tensor.4d request by one thread: the tensor map's zero fill
+// supplies the padding (negative / past-the-edge coordinates), so there is no staging code, no address math and
+// no load latency in the compute warps -- the box of tile i+1 lands in the other buffer while tile i is computed
+// (the st.shared staging loop this replaces held 47 % of the warp-stall samples: profiles/r01_dwconv_ncu_v5.txt).
+// Thread (cp, t): channel pair cp (16 per CTA) and TWO adjacent output columns.  The thread slides through the 8
+// input columns its two outputs touch, keeping the previous column in registers, so every shared-memory load
+// (one bf16x2 -> fp32x2) feeds up to 14 packed fp32x2 FMAs: the kernel is bound by the FMA pipe
+// (2 cycles per FFMA2), not by instruction issue (the one-column form issued 3 instructions per FFMA2).
+constexpr int kDwCh = 32;            // channels per tile (16 bf16x2 lanes)
+
+template <int TH, int TW, int NB>
+struct DwTile {
+  static constexpr int IH = TH + 6, IW = TW + 6;
+  static constexpr int kPairs = (TW / 2) * NB;                           // column pairs = threads / 16
+  static constexpr int kThreads = kPairs * 16;
+  static constexpr int kTileWords = NB * IH * IW * (kDwCh / 2);          // bf16x2 words per input buffer
+  static constexpr int kTileBytes = kTileWords * 4;
+  static constexpr int kTilePad = (kTileBytes + 127) / 128 * 128;        // TMA destination: 128-byte aligned
+  static constexpr int kWBytes = 49 * (kDwCh / 2) * 8;                   // fp32x2 taps of the channel group
+  static constexpr int kSmem = 2 * kTilePad + kWBytes + 64 + 128;        // + barriers + alignment slack
+};
+
+struct DwParams {
+  const float* wt;      // [49][C] taps
+  const float* bias;    // [C] or null
+  const bf16* add;      // [B][H][W][C] or null
+  bf16* y;
+  int B, H, W, C;
+  int tiles_w, tiles_h, groups_b;   // spatial tiles per image, image groups
+  int total_tiles;
+};
+
+template <int TH, int TW, int NB, bool BIAS, bool ADD>
+__global__ void __launch_bounds__(DwTile<TH, TW, NB>::kThreads, 2)
+    dwconv7_kernel(const __grid_constant__ CUtensorMap map_x, const DwParams p) {
+  typedef DwTile<TH, TW, NB> T;
+  extern __shared__ __align__(128) uint8_t dw_smem_raw[];
+  // 128-byte aligned TMA destinations; offset arithmetic on the __shared__ array keeps the loads LDS (not generic LD)
+  uint8_t* smem = dw_smem_raw + ((128u - (b200at::smem_u32(dw_smem_raw) & 127u)) & 127u);
+  float2* wk = reinterpret_cast<float2*>(smem + 2 * T::kTilePad);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * T::kTilePad + T::kWBytes);
+
+  const int tid = threadIdx.x;
+  const int cp = tid & 15, t = tid >> 4;
+  const int img = t / (TW / 2), col = 2 * (t % (TW / 2));
+  // this CTA's contiguous run of tiles (channel group slowest, so the taps are reloaded at most a few times)
+  const int q = p.total_tiles / (int)gridDim.x, rem = p.total_tiles % (int)gridDim.x;
+  const int b = (int)blockIdx.x;
+  const int first = b * q + (b < rem ? b : rem);
+  const int count = q + (b < rem ? 1 : 0);
+  const int spatial = p.tiles_w * p.tiles_h * p.groups_b;
+
+  auto decode = [&](int tile, int& cg, int& n0, int& h0, int& w0) {
+    cg = tile / spatial;
+    int s = tile - cg * spatial;
+    const int tw = s % p.tiles_w; s /= p.tiles_w;
+    const int th = s % p.tiles_h; s /= p.tiles_h;
+    n0 = s * NB; h0 = th * TH; w0 = tw * TW;
+  };
+  if (tid == 0) {
+    b200at::tma_prefetch_desc(&map_x);
+    b200at::mbar_init(&bars[0], 1);
+    b200at::mbar_init(&bars[1], 1);
+    b200at::mbar_fence_init();
+    if (count > 0) {
+      int cg, n0, h0, w0;
+      decode(first, cg, n0, h0, w0);
+      b200at::mbar_expect_tx(&bars[0], T::kTileBytes);
+      b200at::tma_load_4d(&map_x, &bars[0], smem, cg * kDwCh, w0 - 3, h0 - 3, n0);
+    }
+  }
+  __syncthreads();
+
+  int cur_cg = -1;
+  for (int it = 0; it < count; ++it) {
+    const int cur = it & 1;
+    int cg, n0, h0, w0;
+    decode(first + it, cg, n0, h0, w0);
+    const int c0 = cg * kDwCh;
+    if (cg != cur_cg) {   // new channel group (CTA-uniform, rare): reload the taps once the previous tile is done
+      cur_cg = cg;
+      __syncthreads();
+      for (int k = tid; k < 49 * (kDwCh / 2); k += T::kThreads) {
+        const int tap = k >> 4, c2 = k & 15;
+        wk[k] = *reinterpret_cast<const float2*>(p.wt + (int64_t)tap * p.C + c0 + c2 * 2);
+      }
+    }
+    b200at::mbar_wait(&bars[cur], (uint32_t)((it >> 1) & 1));   // this tile's box has landed
+    __syncthreads();   // taps visible; everybody is done with the previous tile => the other buffer is free
+    if (tid == 0 && it + 1 < count) {
+      int cg1, n1, h1, w1;
+      decode(first + it + 1, cg1, n1, h1, w1);
+      b200at::mbar_expect_tx(&bars[cur ^ 1], T::kTileBytes);
+      b200at::tma_load_4d(&map_x, &bars[cur ^ 1], smem + (cur ^ 1) * T::kTilePad, cg1 * kDwCh, w1 - 3, h1 - 3, n1);
+    }
+    const bf162* tile = reinterpret_cast<const bf162*>(smem + cur * T::kTilePad) +
+                        (img * (T::IH * T::IW) + col) * (kDwCh / 2) + cp;
+    float2 acc0[TH], acc1[TH], vp[T::IH];
+    const float2 b2 = BIAS ? make_float2(p.bias[c0 + cp * 2], p.bias[c0 + cp * 2 + 1]) : make_float2(0.f, 0.f);
+#pragma unroll
+    for (int r = 0; r < TH; ++r) { acc0[r] = b2; acc1[r] = b2; }
+#pragma unroll
+    for (int r = 0; r < T::IH; ++r) vp[r] = __bfloat1622float2(tile[(r * T::IW) * (kDwCh / 2)]);
+#pragma unroll
+    for (int j = 0; j < 7; ++j) {
+      float2 wj[7];
+#pragma unroll
+      for (int i = 0; i < 7; ++i) wj[i] = wk[(i * 7 + j) * (kDwCh / 2) + cp];
+#pragma unroll
+      for (int r = 0; r < T::IH; ++r) {
+        // input column (col + j) feeds output column col, input column (col + j + 1) output column col + 1
+        const float2 vn = __bfloat1622float2(tile[(r * T::IW + j + 1) * (kDwCh / 2)]);
+#pragma unroll
+        for (int i = 0; i < 7; ++i) {
+          const int o = r - i;  // output row fed by input row r through tap row i
+          if (o >= 0 && o < TH) {
+            acc0[o] = ffma2(vp[r], wj[i], acc0[o]);
+            acc1[o] = ffma2(vn, wj[i], acc1[o]);
+          }
+        }
+        vp[r] = vn;
+      }
+    }
+    const int n = n0 + img, w = w0 + col;
+    if (n < p.B && w < p.W) {
+      const bool second = w + 1 < p.W;
+#pragma unroll
+      for (int r = 0; r < TH; ++r) {
+        if (h0 + r < p.H) {
+          const int64_t off = (((int64_t)n * p.H + h0 + r) * p.W + w) * p.C + c0 + cp * 2;
+          if (ADD) {  // residual-gradient join fused into the input-gradient pass
+            const float2 a = __bfloat1622float2(*reinterpret_cast<const bf162*>(p.add + off));
+            acc0[r].x += a.x; acc0[r].y += a.y;
+            if (second) {
+              const float2 a1 = __bfloat1622float2(*reinterpret_cast<const bf162*>(p.add + off + p.C));
+              acc1[r].x += a1.x; acc1[r].y += a1.y;
+            }
+          }
+          *reinterpret_cast<bf162*>(p.y + off) = __floats2bfloat162_rn(acc0[r].x, acc0[r].y);
+          if (second) *reinterpret_cast<bf162*>(p.y + off + p.C) = __floats2bfloat162_rn(acc1[r].x, acc1[r].y);
+        }
+      }
+    }
+  }
+}
+
+// tile staging of the weight-gradient kernel below (plain loads; that kernel is not TMA-fed yet)
 constexpr int kDwTile = 14;
 constexpr int kDwIn = kDwTile + 6;   // 20
-constexpr int kDwCh = 32;            // channels per CTA (16 bf16x2 lanes)
-
-template <bool BIAS, bool ADD>
-__global__ void __launch_bounds__(256) dwconv7_kernel(const bf16* __restrict__ x, const float* __restrict__ wt,
-                                                      const float* __restrict__ bias, const bf16* __restrict__ add,
-                                                      bf16* __restrict__ y, int H, int W, int C, int tiles_w,
-                                                      int tiles_h) {
-  __shared__ __align__(16) bf162 tile[kDwIn][kDwIn][kDwCh / 2];
-  __shared__ float2 wsm[49][kDwCh / 2];
-  const int cp = threadIdx.x & 15, t = threadIdx.x >> 4;
-  const int cgroups = C / kDwCh;
-  int bid = blockIdx.x;
-  const int cg = bid % cgroups; bid /= cgroups;
-  const int tw = bid % tiles_w; bid /= tiles_w;
-  const int th = bid % tiles_h; bid /= tiles_h;
-  const int n = bid;
-  const int h0 = th * kDwTile, w0 = tw * kDwTile, c0 = cg * kDwCh;
-  const bf16* xin = x + (int64_t)n * H * W * C;
-  // stage the (20 x 20) halo tile: 4 consecutive lanes fetch the 64 contiguous bytes of one pixel (16 B each)
-  for (int q = threadIdx.x; q < kDwIn * kDwIn * 4; q += 256) {
-    const int pix = q >> 2, piece = q & 3;
-    const int r = pix / kDwIn, c = pix % kDwIn;
-    const int hh = h0 + r - 3, ww = w0 + c - 3;
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (hh >= 0 && hh < H && ww >= 0 && ww < W)
-      v = __ldg(reinterpret_cast<const uint4*>(xin + ((int64_t)hh * W + ww) * C + c0 + piece * 8));
-    *reinterpret_cast<uint4*>(&tile[r][c][piece * 4]) = v;
-  }
-  for (int k = t; k < 49; k += 16) wsm[k][cp] = make_float2(wt[k * C + c0 + cp * 2], wt[k * C + c0 + cp * 2 + 1]);
-  __syncthreads();
-  if (t >= kDwTile || w0 + t >= W) return;
-  float2 acc[kDwTile];
-  const float2 b2 = BIAS ? make_float2(bias[c0 + cp * 2], bias[c0 + cp * 2 + 1]) : make_float2(0.f, 0.f);
-#pragma unroll
-  for (int r = 0; r < kDwTile; ++r) acc[r] = b2;
-#pragma unroll
-  for (int j = 0; j < 7; ++j) {
-    float2 wj[7];
-#pragma unroll
-    for (int i = 0; i < 7; ++i) wj[i] = wsm[i * 7 + j][cp];
-#pragma unroll
-    for (int r = 0; r < kDwIn; ++r) {
-      const float2 v = __bfloat1622float2(tile[r][t + j][cp]);
-#pragma unroll
-      for (int i = 0; i < 7; ++i) {
-        const int o = r - i;  // output row fed by input row r through tap row i
-        if (o >= 0 && o < kDwTile) acc[o] = ffma2(v, wj[i], acc[o]);
-      }
-    }
-  }
-  bf16* yout = y + (int64_t)n * H * W * C;
-#pragma unroll
-  for (int r = 0; r < kDwTile; ++r) {
-    if (h0 + r < H) {
-      const int64_t off = (int64_t)n * H * W * C + ((int64_t)(h0 + r) * W + w0 + t) * C + c0 + cp * 2;
-      if (ADD) {  // residual-gradient join fused into the input-gradient pass
-        const float2 a = __bfloat1622float2(*reinterpret_cast<const bf162*>(add + off));
-        acc[r].x += a.x; acc[r].y += a.y;
-      }
-      *reinterpret_cast<bf162*>(y + off) = __floats2bfloat162_rn(acc[r].x, acc[r].y);
-    }
-  }
-  (void)yout;
-}
 
 // weight gradient: dw[tap][c] += sum_{pixels} dy[p][c] * x[p + tap][c];  db[c] += sum dy
 __global__ void __launch_bounds__(256) dwconv7_wgrad_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy,
@@ -564,6 +668,43 @@ int launch_ln_bwd(const bf16* dy, const bf16* x, const float* w, const float* b,
   return (int)cudaErrorInvalidValue;
 }
 
+template <int TH, int TW, int NB>
+int launch_dwconv(const void* x, const float* wt, const float* bias, const void* add, void* y, int64_t B, int64_t H,
+                  int64_t W, int64_t C, cudaStream_t s) {
+  typedef DwTile<TH, TW, NB> T;
+  DwParams p;
+  p.wt = wt; p.bias = bias; p.add = (const bf16*)add; p.y = (bf16*)y;
+  p.B = (int)B; p.H = (int)H; p.W = (int)W; p.C = (int)C;
+  p.tiles_w = (int)((W + TW - 1) / TW); p.tiles_h = (int)((H + TH - 1) / TH); p.groups_b = (int)((B + NB - 1) / NB);
+  const int64_t total = (int64_t)p.tiles_w * p.tiles_h * p.groups_b * (C / kDwCh);
+  if (total > 0x7fffffff) return (int)cudaErrorInvalidValue;
+  p.total_tiles = (int)total;
+  CUtensorMap map;
+  if (!b200at::make_map_nhwc_bf16(&map, x, B, H, W, C, kDwCh, T::IW, T::IH, NB)) return (int)cudaErrorUnknown;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int per_sm = (228 * 1024) / (T::kSmem + 1024);      // resident CTAs per SM by shared memory (launch bounds: 2)
+  per_sm = per_sm < 1 ? 1 : (per_sm > 2 ? 2 : per_sm);
+  const int64_t cap = (int64_t)sms * per_sm;
+  const int grid = (int)(total < cap ? total : cap);
+#define B200AT_DW(BI, AD)                                                                                     \
+  do {                                                                                                        \
+    static bool configured = false;                                                                           \
+    if (!configured) {                                                                                        \
+      cudaError_t e = cudaFuncSetAttribute(dwconv7_kernel<TH, TW, NB, BI, AD>,                                \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, T::kSmem);           \
+      if (e != cudaSuccess) return (int)e;                                                                    \
+      configured = true;                                                                                      \
+    }                                                                                                         \
+    dwconv7_kernel<TH, TW, NB, BI, AD><<<grid, T::kThreads, T::kSmem, s>>>(map, p);                            \
+  } while (0)
+  if (bias) { if (add) B200AT_DW(true, true); else B200AT_DW(true, false); }
+  else { if (add) B200AT_DW(false, true); else B200AT_DW(false, false); }
+#undef B200AT_DW
+  return (int)cudaGetLastError();
+}
+
 }  // namespace
 
 extern "C" {
@@ -594,7 +735,7 @@ int b200at_bias_gelu_fwd(const void* z, const float* bias, void* h, int64_t M, i
   if (M <= 0) return 0;
   if (N % 8) return (int)cudaErrorInvalidValue;
   const int64_t total8 = M * N / 8;
-  bias_gelu_fwd_kernel<<<flat_grid(total8), 256, 0, (cudaStream_t)stream>>>((const bf16*)z, bias, (bf16*)h, total8, (int)(N / 8));
+  bias_gelu_fwd_kernel<<<column_grid(total8, (int)(N / 8), 16), 256, 0, (cudaStream_t)stream>>>((const bf16*)z, bias, (bf16*)h, total8, (int)(N / 8));
   return (int)cudaGetLastError();
 }
 
@@ -606,7 +747,7 @@ int b200at_bias_gelu_bwd(const void* dh, const void* z, const float* bias, void*
   const int n8 = (int)(N / 8);
   cudaStream_t s = (cudaStream_t)stream;
   if (dbias)
-    bias_gelu_bwd_kernel<true><<<column_grid(total8, n8, 8), 256, sizeof(float) * N, s>>>((const bf16*)dh, (const bf16*)z, bias, (bf16*)dz, dbias, total8, n8);
+    bias_gelu_bwd_kernel<true><<<column_grid(total8, n8, 16), 256, sizeof(float) * N, s>>>((const bf16*)dh, (const bf16*)z, bias, (bf16*)dz, dbias, total8, n8);
   else
     bias_gelu_bwd_kernel<false><<<column_grid(total8, n8, 16), 256, 0, s>>>((const bf16*)dh, (const bf16*)z, bias, (bf16*)dz, nullptr, total8, n8);
   return (int)cudaGetLastError();
@@ -648,16 +789,13 @@ int b200at_add_bf16(const void* a, const void* b, void* c, int64_t total, void* 
 int b200at_dwconv7_fwd(const void* x, const float* wt, const float* bias, const void* add, void* y, int64_t B,
                        int64_t H, int64_t W, int64_t C, void* stream) {
   if (B <= 0) return 0;
-  if (C % kDwCh) return (int)cudaErrorInvalidValue;
-  const int tw = (int)((W + kDwTile - 1) / kDwTile), th = (int)((H + kDwTile - 1) / kDwTile);
-  const int64_t grid = B * th * tw * (C / kDwCh);
-  if (grid > 0x7fffffff) return (int)cudaErrorInvalidValue;
+  if (C % kDwCh || (reinterpret_cast<uintptr_t>(x) & 15)) return (int)cudaErrorInvalidValue;
   cudaStream_t s = (cudaStream_t)stream;
-#define B200AT_DW(BI, AD) dwconv7_kernel<BI, AD><<<(unsigned)grid, 256, 0, s>>>((const bf16*)x, wt, bias, (const bf16*)add, (bf16*)y, (int)H, (int)W, (int)C, tw, th)
-  if (bias) { if (add) B200AT_DW(true, true); else B200AT_DW(true, false); }
-  else { if (add) B200AT_DW(false, true); else B200AT_DW(false, false); }
-#undef B200AT_DW
-  return (int)cudaGetLastError();
+  // tile shapes: wide maps 14 x 28; 14-wide maps two images side by side; the 7 x 7 maps of the last stage three
+  // images of 7 x 8 (one masked column)
+  if (W > 14) return launch_dwconv<14, 28, 1>(x, wt, bias, add, y, B, H, W, C, s);
+  if (W > 8 || H > 7) return launch_dwconv<14, 14, 2>(x, wt, bias, add, y, B, H, W, C, s);
+  return launch_dwconv<7, 8, 3>(x, wt, bias, add, y, B, H, W, C, s);
 }
 
 int b200at_dwconv7_wgrad(const void* x, const void* dy, float* dw, float* db, int64_t B, int64_t H, int64_t W,

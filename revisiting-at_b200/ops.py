@@ -176,7 +176,7 @@ def _derived(param, tag, fn):
     key = (id(param), tag)
     hit = _PCACHE.get(key)
     if hit is not None and hit[2]() is param and hit[0] == (param._version, param.data_ptr()):
-        return hit[1]
+        return hit[1]                                        # same live tensor object, same storage, not written since
     with torch.no_grad():
         val = fn(param.detach())
     if len(_PCACHE) > 4096:                                  # models that came and went (tests)
@@ -359,17 +359,11 @@ class _Stem0(Function):
         return dx, None, None, None, None, None, None
 
 
-_HOST3 = {}
-
-
 def _host3(t):
-    """3 python floats of the normaliser's mean / std buffer (one D2H copy per buffer, then cached)."""
+    """3 python floats of the normaliser's mean / std buffer (one D2H copy per buffer object and version)."""
     if t is None:
         return None
-    key = (t.data_ptr(), t._version)
-    if key not in _HOST3:
-        _HOST3[key] = tuple(float(v) for v in t.detach().flatten().cpu())
-    return _HOST3[key]
+    return _derived(t, 'host3', lambda v: tuple(float(a) for a in v.flatten().cpu()))
 
 
 STEM0_KERNEL = os.environ.get('B200AT_STEM0', '1') == '1'
