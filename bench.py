@@ -51,16 +51,43 @@ def parse():
     ap.add_argument('--steps', type=int, default=8)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--batch', type=int, default=BATCH_PER_GPU)
+    ap.add_argument('--arch', default=ARCH, choices=sorted(WORKLOADS),
+                    help='convnext_tiny = BASELINE configs[1] (the metric line); the others are secondary workloads')
+    ap.add_argument('--batch', type=int, default=None, help='images per GPU (default: the BASELINE config of --arch)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--cpu-seconds', type=float, default=20.0, help='budget of the cpu_baseline sample')
     return ap.parse_args()
 
 
-def workload_config(n_gpus, batch):
-    return {'workload': f'ConvNeXt-T-CvSt APGD l-inf 4/255 n_iter={N_ITER} adversarial train step, bf16 autocast, '
-                        f'batch {batch}/GPU, 3x{RES}x{RES} (BASELINE.json configs[1])',
-            'arch': ARCH, 'batch_per_gpu': batch, 'global_batch': batch * n_gpus, 'resolution': RES,
+# arch -> (display name, default batch per GPU, which BASELINE.json config it is)
+WORKLOADS = {
+    'convnext_tiny': ('ConvNeXt-T-CvSt', 128, 'BASELINE.json configs[1]'),
+    'vit_small': ('ViT-S-CvSt', 256, 'BASELINE.json configs[2], single-GPU share'),
+    'convnext_base': ('ConvNeXt-B-CvSt', 64, 'BASELINE.json configs[3] model, single-GPU share'),
+}
+
+
+def build_engine(arch):
+    if arch == 'vit_small':
+        from revisiting_at_b200 import vit
+        return vit.build(normalize=True, seed=0)
+    from revisiting_at_b200 import convnext
+    return convnext.build(arch, normalize=True, seed=0)
+
+
+def build_oracle(arch):
+    if arch == 'vit_small':
+        from oracle import vit_oracle
+        return vit_oracle.build(normalize=True, seed=0)
+    from oracle import convnext_oracle
+    return convnext_oracle.build(arch, normalize=True, seed=0)
+
+
+def workload_config(n_gpus, batch, arch=ARCH):
+    name, _, which = WORKLOADS[arch]
+    return {'workload': f'{name} APGD l-inf 4/255 n_iter={N_ITER} adversarial train step, bf16 autocast, '
+                        f'batch {batch}/GPU, 3x{RES}x{RES} ({which})',
+            'arch': arch, 'batch_per_gpu': batch, 'global_batch': batch * n_gpus, 'resolution': RES,
             'norm': 'Linf', 'eps': '4/255', 'n_iter': N_ITER, 'parallelism': f'dp{n_gpus}',
             'l2_policy': 'inputs_exceed_l2 (per-step working set >> 126 MB; image-sized passes stream 385 MB)'}
 
@@ -70,6 +97,16 @@ def synth_batch(batch, seed):
     x = torch.rand(batch, 3, RES, RES, generator=g)
     y = torch.randint(0, 1000, (batch,), generator=g)
     return x, y
+
+
+ENGINE_NOTE = {
+    False: 'hand-written NHWC bf16 kernels: fused first stem stage, dwconv7 fwd/dgrad/wgrad, LayerNorm, bias+GELU, '
+           'tcgen05 GEMM (pwconv2+scale+residual, pwconv1 dgrad); cuBLAS for pwconv1 fwd / weight-gradient GEMMs, '
+           'cuDNN for the strided stem/downsample convs',
+    True: 'hand-written kernels: fused first stem stage, LayerNorm(+GELU), bias+GELU, mma.sync attention fwd/bwd, '
+          'tcgen05 GEMM (qkv+bias, proj/fc2+bias+residual, fc1, all input-gradient GEMMs); cuBLAS for weight-gradient '
+          'GEMMs, cuDNN for stem convs 2-4',
+}
 
 
 # ---------------------------------------------------------------------------------------------- clocks
@@ -119,18 +156,16 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------- CPU arm
-def cpu_step_factory():
-    from oracle import convnext_oracle
+def cpu_step_factory(arch=ARCH):
     from oracle.train_step_oracle import OracleTrainStep
     torch.set_num_threads(os.cpu_count())
-    model = convnext_oracle.build(ARCH, normalize=True, seed=0)
-    return OracleTrainStep(model, 'Linf', EPS, N_ITER)
+    return OracleTrainStep(build_oracle(arch), 'Linf', EPS, N_ITER)
 
 
-def cpu_baseline(seconds):
+def cpu_baseline(seconds, arch=ARCH):
     """Oracle port of the step on the host cores, bounded sample: one warm-up step at batch 4, then as many
     images as fit in ~`seconds` (batch 8..32), timed with the wall clock."""
-    step = cpu_step_factory()
+    step = cpu_step_factory(arch)
     x, y = synth_batch(4, 7)
     t0 = time.time(); step(x, y); t_warm = time.time() - t0
     ips_guess = 4 / max(t_warm, 1e-3)
@@ -153,7 +188,7 @@ def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    step = cpu_step_factory()
+    step = cpu_step_factory(args.arch)
     total = args.steps + args.warmup
     x, y = synth_batch(2, 7)
     t0 = time.time(); step(x, y); t2 = time.time() - t0
@@ -168,10 +203,10 @@ def run_reference(args):
     dt = time.time() - t0
     v = batch * args.steps / dt
     cores = torch.get_num_threads()
-    sample = f'{args.steps} steps of {batch} images (bounded sample of the {BATCH_PER_GPU}/GPU step), fp32, {cores} threads'
+    sample = f'{args.steps} steps of {batch} images (bounded sample of the {args.batch}/GPU step), fp32, {cores} threads'
     line = {'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps, 'higher_is_better': True, 'scaling': 'weak',
-            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(args.gpus, args.batch),
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(args.gpus, args.batch, args.arch),
             'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
             'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
@@ -191,13 +226,13 @@ def run_b200(args):
     if distributed:
         dist.init_process_group('nccl', device_id=dev)
     import revisiting_at_b200  # noqa: F401
-    from revisiting_at_b200 import _abi, convnext
+    from revisiting_at_b200 import _abi
     from revisiting_at_b200.train_step import AdvTrainStep
     _abi.lib()                                              # fail loudly if the CUDA library is missing
     torch.backends.cudnn.benchmark = True                   # main.py:25
 
     batch = args.batch
-    model = convnext.build(ARCH, normalize=True, seed=0)
+    model = build_engine(args.arch)
     step = AdvTrainStep(model, 'apgd', 'Linf', EPS, N_ITER, distributed=distributed, device=dev)
 
     pool = 2
@@ -243,6 +278,10 @@ def run_b200(args):
     if rank == 0:
         sampler.start()
     launches0 = _abi.LAUNCHES['count']
+    # algorithmic bytes per element of each timed K1 launch (SURVEY.md 8d: 20 B = read x, x_adv, x_adv_old, grad +
+    # write x_adv; the first move of a call has x_adv_old == x_adv, one stream fewer => credited 16 B)
+    credit = {'linf_step': 20.0, 'linf_step_log': 20.0, 'linf_step_log_first': 16.0}
+    _abi.TIMING['names'] = set(credit)                      # events only around the K1 launches (2 per attack call)
     _abi.TIMING['enabled'] = True
     _abi.TIMING['events'].clear()
     profile_range = os.environ.get('B200AT_PROFILE_RANGE') == '1'      # ncu --profile-from-start off
@@ -253,9 +292,6 @@ def run_b200(args):
         torch.cuda.profiler.stop()
     _abi.TIMING['enabled'] = False
     launches = _abi.LAUNCHES['count'] - launches0
-    # algorithmic bytes per element of each timed K1 launch (SURVEY.md 8d: 20 B = read x, x_adv, x_adv_old, grad +
-    # write x_adv; the first move of a call has x_adv_old == x_adv, one stream fewer => credited 16 B)
-    credit = {'linf_step': 20.0, 'linf_step_log': 20.0, 'linf_step_log_first': 16.0}
     k1 = [(a.elapsed_time(b), credit[name]) for name, a, b in _abi.TIMING['events'] if name in credit]
     _abi.TIMING['events'].clear()
     for i in range(2):
@@ -283,7 +319,7 @@ def run_b200(args):
     line = {
         'metric': METRIC, 'value': imgs / (ms * 1e-3), 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
         'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
-        'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic', 'config': workload_config(world, batch),
+        'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic', 'config': workload_config(world, batch, args.arch),
         'e2e': {'value': imgs / (ms_e2e * 1e-3), 'unit': UNIT,
                 'h2d_bytes_per_step': batch * N_FTS * 4 + batch * 8, 'd2h_bytes_per_step': 4,
                 'ms_per_step': ms_e2e / args.steps},
@@ -294,12 +330,11 @@ def run_b200(args):
                      'algorithmic_bytes_per_launch': alg_bytes, 'launch_ms_mean': k1_ms, 'launches_timed': len(k1),
                      'peak_source': peak_src, 'frac_of_nominal_8TBps': achieved / 8000.0},
         'clocks': clocks,
-        'model_engine': 'hand-written NHWC bf16 kernels for dwconv7/LayerNorm/GELU/layer-scale; cuBLAS GEMMs and '
-                        'cuDNN strided convs (stem, downsample) through torch',
+        'model_engine': ENGINE_NOTE[args.arch == 'vit_small'],
     }
     if world == 1 and not args.no_cpu_baseline:
         torch.cuda.empty_cache()
-        line['cpu_baseline'] = cpu_baseline(args.cpu_seconds)
+        line['cpu_baseline'] = cpu_baseline(args.cpu_seconds, args.arch)
     print(json.dumps(line), flush=True)
     if distributed:
         dist.destroy_process_group()
@@ -307,6 +342,8 @@ def run_b200(args):
 
 def main():
     args = parse()
+    if args.batch is None:
+        args.batch = WORKLOADS[args.arch][1]
     if args.impl == 'reference':
         run_reference(args)
     else:

@@ -89,6 +89,17 @@ int b200at_stem0_bwd_input(const void* dy, const float* x, const float* mean3, c
 int b200at_gemm_bf16(const void* a, const void* b, void* c, void* c2, const void* aux, const float* bias,
                      int64_t M, int64_t N, int64_t K, int epilogue, void* stream);
 
+/* Multi-head self-attention of the ViT-S-CvSt blocks (timm 0.8 vision_transformer.Attention.forward, un-vendored;
+ * call sites utils_architecture.py:271-301):  q,k,v = qkv.reshape(B,N,3,H,64).permute(2,0,3,1,4);
+ * o = softmax(q k^T * scale) v, written as [B][N][H*64].  qkv: bf16 [B][N][3][H][64]; lse: fp32 [B][H][N], the
+ * per-row log2-sum-exp of the scaled scores (saved for the backward).  Head dimension 64, N <= 208 (the whole
+ * sequence of one (image, head) lives in one CTA's shared memory). */
+int b200at_attn_fwd(const void* qkv, void* o, float* lse, int64_t B, int64_t N, int64_t H, float scale, void* stream);
+/* dqkv (same layout as qkv, every element written) given d_o = dL/do; recomputes the probabilities from qkv and
+ * lse.  Deterministic (no atomics). */
+int b200at_attn_bwd(const void* qkv, const void* o, const void* d_o, const float* lse, void* dqkv, int64_t B, int64_t N,
+                    int64_t H, float scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

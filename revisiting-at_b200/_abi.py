@@ -31,7 +31,7 @@ LAUNCHES = {'count': 0}   # kernels launched through this ABI (bench.py reports 
 
 # optional per-launch device timing (bench.py): CUDA events recorded on the launching stream around
 # each kernel; nothing is synchronised here, the reader calls elapsed_time after its own sync
-TIMING = {'enabled': False, 'events': []}
+TIMING = {'enabled': False, 'events': [], 'names': None}    # names: only these kernels are timed (None = all)
 
 
 class B200atError(RuntimeError):
@@ -43,14 +43,15 @@ class _Timed:
         self.name = name
 
     def __enter__(self):
-        if TIMING['enabled']:
+        self.on = TIMING['enabled'] and (TIMING['names'] is None or self.name in TIMING['names'])
+        if self.on:
             self.a = torch.cuda.Event(enable_timing=True)
             self.b = torch.cuda.Event(enable_timing=True)
             self.a.record()
         return self
 
     def __exit__(self, *exc):
-        if TIMING['enabled']:
+        if self.on:
             self.b.record()
             TIMING['events'].append((self.name, self.a, self.b))
         LAUNCHES['count'] += 1
@@ -101,6 +102,8 @@ def _declare(L):
         'b200at_gemm_bf16': [P, P, P, P, P, P, I64, I64, I64, I, P],
         'b200at_stem0_fwd': [P, P, P, P, P, P, P, P, I64, I64, I64, I64, F, P],
         'b200at_stem0_bwd_input': [P, P, P, P, P, P, P, P, P, I64, I64, I64, I64, F, P],
+        'b200at_attn_fwd': [P, P, P, I64, I64, I64, F, P],
+        'b200at_attn_bwd': [P, P, P, P, P, I64, I64, I64, F, P],
     })
     for name, args in sig.items():
         fn = getattr(L, name)
@@ -410,3 +413,22 @@ def gemm_bf16(a, b, c, epilogue=EPI_NONE, bias=None, aux=None, c2=None):
                                       _act(c2, 'c2') if c2 is not None else c_void_p(0),
                                       _act(aux, 'aux') if aux is not None else c_void_p(0),
                                       _par(bias, 'bias', N), M, N, K, epilogue, _stream()), 'gemm_bf16')
+
+
+def attn_fwd(qkv, o, lse, heads, scale):
+    """o = softmax(q k^T scale) v per head; qkv [B,N,3*heads*64] bf16, o [B,N,heads*64], lse fp32 [B,heads,N]."""
+    B, N, C3 = qkv.shape
+    if C3 != 3 * heads * 64 or tuple(o.shape) != (B, N, heads * 64):
+        raise B200atError(f'attention shapes: qkv {tuple(qkv.shape)} o {tuple(o.shape)} heads {heads} (head dim 64)')
+    with _Timed('attn_fwd'):
+        _check(lib().b200at_attn_fwd(_act(qkv, 'qkv'), _act(o, 'o'), _par(lse, 'lse', B * heads * N), B, N, heads,
+                                     scale, _stream()), 'attn_fwd')
+
+
+def attn_bwd(qkv, o, d_o, lse, dqkv, heads, scale):
+    B, N, C3 = qkv.shape
+    if C3 != 3 * heads * 64 or o.shape != d_o.shape or dqkv.shape != qkv.shape:
+        raise B200atError('attention backward shapes')
+    with _Timed('attn_bwd'):
+        _check(lib().b200at_attn_bwd(_act(qkv, 'qkv'), _act(o, 'o'), _act(d_o, 'd_o'), _par(lse, 'lse', B * heads * N),
+                                     _act(dqkv, 'dqkv'), B, N, heads, scale, _stream()), 'attn_bwd')

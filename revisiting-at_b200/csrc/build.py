@@ -19,6 +19,7 @@ UNITS = [
     ('b200at_convnext.cu', []),
     ('b200at_gemm.cu', []),
     ('b200at_stem.cu', []),
+    ('b200at_attention.cu', []),
 ]
 
 

@@ -402,3 +402,175 @@ def head(x, ln_w, ln_b, fw, fb):
     p = x.float().mean((1, 2))
     p = F.layer_norm(p, (p.shape[-1],), ln_w.float(), ln_b.float(), 1e-6)
     return F.linear(p.to(BF16), _cast(fw), _cast(fb))
+
+
+# ------------------------------------------------------------------------------------------------ ViT-S-CvSt
+# timm 0.8 `vision_transformer.Block` (un-vendored; call sites utils_architecture.py:271-301):
+#     x = x + proj(attention(qkv(norm1(x)))) ;  x = x + fc2(GELU(fc1(norm2(x))))
+# on token rows [B*N, D] bf16.  LayerNorm / bias+GELU: the kernels above; qkv (+bias), proj (+bias+residual),
+# fc2 (+bias+residual) and every input-gradient GEMM: the tcgen05 kernel; attention: csrc/b200at_attention.cu.
+ATTENTION_KERNEL = os.environ.get('B200AT_ATTN', 'kernel')     # 'sdpa' = library attention (A/B measurements only)
+
+
+def _vit_prepared(wqkv, wproj, w1, w2):
+    key = (id(wqkv), id(wproj), id(w1), id(w2))
+    ver = tuple(w._version for w in (wqkv, wproj, w1, w2)) + (wqkv.data_ptr(), w2.data_ptr())
+    hit = _WCACHE.get(key)
+    if hit is not None and hit[0] == ver and hit[2]() is wqkv and hit[3]() is w2:
+        return hit[1]
+    with torch.no_grad():
+        prep = {}
+        for name, w in (('qkv', wqkv), ('proj', wproj), ('w1', w1), ('w2', w2)):
+            wb = w.detach().to(BF16).contiguous()
+            prep[name] = wb                                   # [out, in]: y = x @ wb^T
+            prep[name + '_t'] = wb.t().contiguous()           # [in, out]: dx = dy @ wb == dy @ (wb^T)^T
+    _WCACHE[key] = (ver, prep, weakref.ref(wqkv), weakref.ref(w2))
+    return prep
+
+
+class _Attention(Function):
+    """softmax(q k^T scale) v per head on the packed qkv rows (csrc/b200at_attention.cu)."""
+    @staticmethod
+    def forward(ctx, qkv, heads, scale):
+        B, N, _ = qkv.shape
+        qkv = qkv.contiguous()
+        o = torch.empty(B, N, heads * 64, device=qkv.device, dtype=BF16)
+        lse = torch.empty(B * heads * N, device=qkv.device, dtype=torch.float32)
+        _abi.attn_fwd(qkv, o, lse, heads, scale)
+        ctx.save_for_backward(qkv, o, lse)
+        ctx.heads, ctx.scale = heads, scale
+        return o
+
+    @staticmethod
+    def backward(ctx, d_o):
+        qkv, o, lse = ctx.saved_tensors
+        dqkv = torch.empty_like(qkv)
+        _abi.attn_bwd(qkv, o, d_o.contiguous(), lse, dqkv, ctx.heads, ctx.scale)
+        return dqkv, None, None
+
+
+def attention(qkv, heads, scale=None):
+    """qkv: [B,N,3*heads*64] bf16 -> [B,N,heads*64]."""
+    _need_cuda(qkv)
+    return _Attention.apply(qkv, heads, 64 ** -0.5 if scale is None else scale)
+
+
+class _ViTBlock(Function):
+    @staticmethod
+    def forward(ctx, x, n1w, n1b, wqkv, bqkv, wproj, bproj, n2w, n2b, w1, b1, w2, b2, heads):
+        x = x.contiguous()
+        B, N, D = x.shape
+        M = B * N
+        pg = not _INPUT_GRAD_ONLY[0]
+        P = _vit_prepared(wqkv, wproj, w1, w2)
+        scale = (D // heads) ** -0.5
+        n1wf, n1bf, n2wf, n2bf = _f32(n1w), _f32(n1b), _f32(n2w), _f32(n2b)
+        x2 = x.view(M, D)
+        t = torch.empty_like(x2)
+        mean1 = torch.empty(M, device=x.device, dtype=torch.float32)
+        rstd1 = torch.empty_like(mean1)
+        _abi.ln_fwd(x2, n1wf, n1bf, t, mean1, rstd1, 1e-6, False)
+        qkv = _gemm(t, P['qkv'], _abi.EPI_BIAS, bias=_f32(bqkv))
+        o = torch.empty(B, N, D, device=x.device, dtype=BF16)
+        lse = torch.empty(B * heads * N, device=x.device, dtype=torch.float32)
+        _abi.attn_fwd(qkv.view(B, N, 3 * D), o, lse, heads, scale)
+        x1 = _gemm(o.view(M, D), P['proj'], _abi.EPI_RESIDUAL, bias=_f32(bproj), aux=x2)
+        t2 = torch.empty_like(x1)
+        mean2 = torch.empty_like(mean1)
+        rstd2 = torch.empty_like(mean1)
+        _abi.ln_fwd(x1, n2wf, n2bf, t2, mean2, rstd2, 1e-6, False)
+        b1f = _f32(b1)
+        z = _gemm(t2, P['w1'])                                          # bias added inside the GELU kernels
+        a = torch.empty_like(z)
+        _abi.bias_gelu_fwd(z, b1f, a)
+        out = _gemm(a, P['w2'], _abi.EPI_RESIDUAL, bias=_f32(b2), aux=x1)
+        ctx.param_grads, ctx.prep, ctx.heads, ctx.scale = pg, P, heads, scale
+        keep = (x2, mean1, rstd1, qkv, o, lse, x1, mean2, rstd2, z, n1wf, n1bf, n2wf, n2bf, b1f)
+        ctx.save_for_backward(*(keep + ((t, t2, a) if pg else ())))
+        return out.view(B, N, D)
+
+    @staticmethod
+    def backward(ctx, dout):
+        sv = ctx.saved_tensors
+        x2, mean1, rstd1, qkv, o, lse, x1, mean2, rstd2, z, n1wf, n1bf, n2wf, n2bf, b1f = sv[:15]
+        P, heads = ctx.prep, ctx.heads
+        B, N, D = dout.shape
+        M = B * N
+        dev = dout.device
+        pg = ctx.param_grads and any(ctx.needs_input_grad[1:13])
+        d2 = dout.contiguous().view(M, D)
+        # ---- MLP branch
+        da = _gemm(d2, P['w2_t'])                                       # [M,4D]
+        dz = torch.empty_like(da)
+        db1 = torch.zeros(4 * D, device=dev, dtype=torch.float32) if pg else None
+        _abi.bias_gelu_bwd(da, z, b1f, dz, db1)
+        dt2 = _gemm(dz, P['w1_t'])                                      # [M,D]
+        dn2w = torch.zeros(D, device=dev, dtype=torch.float32) if pg else None
+        dn2b = torch.zeros(D, device=dev, dtype=torch.float32) if pg else None
+        dx1 = torch.empty_like(dt2)
+        _abi.ln_bwd(dt2, x1, n2wf, n2bf, mean2, rstd2, dx1, dn2w, dn2b, False)
+        _abi.add_bf16(dx1, d2, dx1)                                     # + residual gradient
+        # ---- attention branch
+        do = _gemm(dx1, P['proj_t'])                                    # [M,D]
+        dqkv = torch.empty_like(qkv)
+        _abi.attn_bwd(qkv.view(B, N, 3 * D), o, do.view(B, N, D), lse, dqkv.view(B, N, 3 * D), heads, ctx.scale)
+        dt = _gemm(dqkv, P['qkv_t'])                                    # [M,D]
+        dn1w = torch.zeros(D, device=dev, dtype=torch.float32) if pg else None
+        dn1b = torch.zeros(D, device=dev, dtype=torch.float32) if pg else None
+        dx = torch.empty_like(dt)
+        _abi.ln_bwd(dt, x2, n1wf, n1bf, mean1, rstd1, dx, dn1w, dn1b, False)
+        _abi.add_bf16(dx, dx1, dx)
+        dx = dx.view(B, N, D)
+        if not pg:
+            return (dx,) + (None,) * 13
+        t, t2, a = sv[15:]
+
+        def colsum(m):
+            out = torch.zeros(m.shape[1], device=dev, dtype=torch.float32)
+            _abi.colsum_bf16(m, out)
+            return out
+        dwqkv = (dqkv.t() @ t).float()
+        dwproj = (dx1.t() @ o.view(M, D)).float()
+        dw1 = (dz.t() @ t2).float()
+        dw2 = (d2.t() @ a).float()
+        return (dx, dn1w, dn1b, dwqkv, colsum(dqkv), dwproj, colsum(dx1), dn2w, dn2b, dw1, db1, dw2, colsum(d2), None)
+
+
+def vit_block(x, n1w, n1b, wqkv, bqkv, wproj, bproj, n2w, n2b, w1, b1, w2, b2, heads):
+    """x: [B,N,D] bf16 tokens -> same (timm vision_transformer.Block, no layer scale, no drop path in eval)."""
+    _need_cuda(x)
+    return _ViTBlock.apply(x, n1w, n1b, wqkv, bqkv, wproj, bproj, n2w, n2b, w1, b1, w2, b2, heads)
+
+
+class _Linear1x1(Function):
+    """1x1 convolution / Linear on NHWC rows through the tcgen05 GEMM (last layer of the ViT conv stem,
+    utils_architecture.py:139: `nn.Conv2d(planes*8, fin_dim, kernel_size=1)`)."""
+    @staticmethod
+    def forward(ctx, x, w, b):
+        x = x.contiguous()
+        M = x.numel() // x.shape[-1]
+        wb = _derived(w, 'bf16_2d', lambda v: v.to(BF16).reshape(v.shape[0], -1).contiguous())
+        y = _gemm(x.view(M, -1), wb, _abi.EPI_BIAS, bias=_f32(b))
+        ctx.param_grads = not _INPUT_GRAD_ONLY[0]
+        ctx.save_for_backward(x if ctx.param_grads else None, w)
+        ctx.wshape = w.shape
+        return y.view(*x.shape[:-1], w.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dy2 = dy.contiguous().view(-1, dy.shape[-1])
+        wt = _derived(w, 'bf16_2d_t', lambda v: v.to(BF16).reshape(v.shape[0], -1).t().contiguous())
+        dx = _gemm(dy2, wt).view(*dy.shape[:-1], wt.shape[0])
+        if not _wants(ctx, 1, 2):
+            return dx, None, None
+        dw = (dy2.t() @ x.view(dy2.shape[0], -1)).float().view(ctx.wshape)
+        db = torch.zeros(dy2.shape[1], device=dy.device, dtype=torch.float32)
+        _abi.colsum_bf16(dy2, db)
+        return dx, dw, db
+
+
+def linear_rows(x, w, b):
+    """y = x W^T + b over the last dimension of a bf16 row tensor (W may be a [out,in,1,1] conv weight)."""
+    _need_cuda(x)
+    return _Linear1x1.apply(x, w, b)
