@@ -50,24 +50,45 @@ __device__ __forceinline__ void load_a_frags(const bf16* tile, int r0, int g, in
     a[kk][3] = lds32(tile + (r0 + g + 8) * kRS + kk * 16 + 8 + 2 * t);
   }
 }
+// four 8x8 b16 matrices, one 16-byte row address per lane (lanes 8j..8j+7 address the rows of matrix j); thread
+// (g, t) receives elements (row g, columns 2t, 2t+1) of each: exactly the B-fragment words of mma.m16n8k16 when the
+// matrix rows are the n index and its columns the (contiguous) k index.
+__device__ __forceinline__ void ldmatrix_x4(uint32_t* r, const bf16* p) {
+  const uint32_t addr = (uint32_t)__cvta_generic_to_shared(p);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
 // acc[2][4] (16 x 16) += A(16 x 64, fragments) . T[c0 .. c0+15][0..63]^T      (T row-major, contraction over its columns)
-__device__ __forceinline__ void mma_rowmajor_b(float (*acc)[4], const uint32_t (*a)[4], const bf16* tile, int c0, int g,
-                                               int t) {
+__device__ __forceinline__ void mma_rowmajor_b(float (*acc)[4], const uint32_t (*a)[4], const bf16* tile, int c0,
+                                               int lane) {
 #pragma unroll
   for (int nt = 0; nt < 2; ++nt) {
-    const bf16* row = tile + (c0 + nt * 8 + g) * kRS + 2 * t;
+    // matrix j of the x4 load = T[c0+nt*8 .. +7][half*32 + 8j .. +7]: (b0, b1) of k-steps 2*half and 2*half+1
+    const bf16* row = tile + (c0 + nt * 8 + (lane & 7)) * kRS + (lane >> 3) * 8;
+    uint32_t b[8];
+    ldmatrix_x4(b, row);
+    ldmatrix_x4(b + 4, row + 32);
 #pragma unroll
-    for (int kk = 0; kk < 4; ++kk) mma16816(acc[nt], a[kk], lds32(row + kk * 16), lds32(row + kk * 16 + 8));
+    for (int kk = 0; kk < 4; ++kk) mma16816(acc[nt], a[kk], b[2 * kk], b[2 * kk + 1]);
   }
 }
 // acc[8][4] (16 x 64) += A(16 x 16, one fragment) . Tt[0..63][c0 .. c0+15]^T   (Tt = transposed tile [64][ts])
-__device__ __forceinline__ void mma_transposed_b(float (*acc)[4], const uint32_t* a, const bf16* tt, int ts, int c0, int g,
-                                                 int t) {
+__device__ __forceinline__ void mma_transposed_b(float (*acc)[4], const uint32_t* a, const bf16* tt, int ts, int c0,
+                                                 int lane) {
 #pragma unroll
-  for (int dt = 0; dt < 8; ++dt) {
-    const bf16* row = tt + (dt * 8 + g) * ts + c0 + 2 * t;
-    mma16816(acc[dt], a, lds32(row), lds32(row + 8));
+  for (int dp = 0; dp < 4; ++dp) {
+    // matrices: (rows dp*16 .. +7, cols c0 / c0+8), (rows dp*16+8 .. +15, cols c0 / c0+8): (b0, b1) of dt = 2dp, 2dp+1
+    const bf16* row = tt + (dp * 16 + ((lane >> 4) << 3) + (lane & 7)) * ts + c0 + ((lane >> 3) & 1) * 8;
+    uint32_t b[4];
+    ldmatrix_x4(b, row);
+    mma16816(acc[2 * dp], a, b[0], b[1]);
+    mma16816(acc[2 * dp + 1], a, b[2], b[3]);
   }
+}
+__device__ __forceinline__ float ex2(float x) {       // 2^x, MUFU.EX2; ex2(-inf) = +0
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 
 // 16-byte chunk `ch` (8 bf16) of token row `tok` of one head: zero beyond the sequence
@@ -98,7 +119,7 @@ __device__ __forceinline__ void store_tile(bf16* out, int64_t row_stride, int r0
 }
 
 // ------------------------------------------------------------------------------------------ forward
-__global__ void __launch_bounds__(32 * kMaxBlocks)
+__global__ void __launch_bounds__(32 * kMaxBlocks, 2)
 attn_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ o, float* __restrict__ lse, int N, int H, float c) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nkb = (N + 15) >> 4, npad = nkb << 4, ts = npad + 8;
@@ -109,8 +130,10 @@ attn_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ o, float* __res
   const bf16* qb = qkv + (int64_t)b * N * rs + h * kD;
   const bf16* kb = qb + H * kD;
   const bf16* vb = kb + H * kD;
+  // consecutive lanes take consecutive tokens of one 16-byte chunk: the 2-byte transposed stores of a warp fall
+  // into 16 consecutive words of one row and the 16-byte row-major stores into distinct bank groups
   for (int idx = threadIdx.x; idx < npad * 8; idx += blockDim.x) {
-    const int tok = idx >> 3, ch = idx & 7;
+    const int tok = idx % npad, ch = idx / npad;
     store_rowmajor(Ks, tok, ch, load_chunk(kb, rs, tok, ch, N));
     store_transposed(Vt, ts, tok, ch, load_chunk(vb, rs, tok, ch, N));
   }
@@ -134,7 +157,7 @@ attn_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ o, float* __res
   for (int dt = 0; dt < 8; ++dt) acc[dt][0] = acc[dt][1] = acc[dt][2] = acc[dt][3] = 0.f;
   for (int jb = 0; jb < nkb; ++jb) {
     float s[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-    mma_rowmajor_b(s, qa, Ks, jb * 16, g, t);
+    mma_rowmajor_b(s, qa, Ks, jb * 16, lane);
 #pragma unroll
     for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
@@ -149,20 +172,22 @@ attn_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ o, float* __res
     x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, 1));
     x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, 2));
     const float n0 = fmaxf(m0, x0), n1 = fmaxf(m1, x1);          // finite from block 0 on (column 0 is always live)
-    const float a0 = exp2f(m0 - n0), a1 = exp2f(m1 - n1);
+    const float a0 = ex2(m0 - n0), a1 = ex2(m1 - n1);
     m0 = n0; m1 = n1;
     float p[2][4];
 #pragma unroll
     for (int nt = 0; nt < 2; ++nt) {
-      p[nt][0] = exp2f(s[nt][0] - n0); p[nt][1] = exp2f(s[nt][1] - n0);
-      p[nt][2] = exp2f(s[nt][2] - n1); p[nt][3] = exp2f(s[nt][3] - n1);
+      p[nt][0] = ex2(s[nt][0] - n0); p[nt][1] = ex2(s[nt][1] - n0);
+      p[nt][2] = ex2(s[nt][2] - n1); p[nt][3] = ex2(s[nt][3] - n1);
     }
     l0 = l0 * a0 + (p[0][0] + p[0][1] + p[1][0] + p[1][1]);
     l1 = l1 * a1 + (p[0][2] + p[0][3] + p[1][2] + p[1][3]);
+    if (__any_sync(0xffffffffu, a0 != 1.f || a1 != 1.f)) {        // usually false after the first blocks
 #pragma unroll
-    for (int dt = 0; dt < 8; ++dt) { acc[dt][0] *= a0; acc[dt][1] *= a0; acc[dt][2] *= a1; acc[dt][3] *= a1; }
+      for (int dt = 0; dt < 8; ++dt) { acc[dt][0] *= a0; acc[dt][1] *= a0; acc[dt][2] *= a1; acc[dt][3] *= a1; }
+    }
     const uint32_t pa[4] = {pack2(p[0][0], p[0][1]), pack2(p[0][2], p[0][3]), pack2(p[1][0], p[1][1]), pack2(p[1][2], p[1][3])};
-    mma_transposed_b(acc, pa, Vt, ts, jb * 16, g, t);
+    mma_transposed_b(acc, pa, Vt, ts, jb * 16, lane);
   }
   l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
   l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
@@ -198,24 +223,28 @@ attn_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o, const 
   const bf16* gb = d_o + (int64_t)b * N * os + h * kD;
   const bf16* ob = o + (int64_t)b * N * os + h * kD;
   for (int idx = threadIdx.x; idx < npad * 8; idx += blockDim.x) {
-    const int tok = idx >> 3, ch = idx & 7;
+    const int tok = idx % npad, ch = idx / npad;
     const uint4 q = load_chunk(qb, rs, tok, ch, N), k = load_chunk(kb, rs, tok, ch, N);
     const uint4 v = load_chunk(vb, rs, tok, ch, N), gg = load_chunk(gb, os, tok, ch, N);
-    const uint4 oo = load_chunk(ob, os, tok, ch, N);
     store_rowmajor(Qs, tok, ch, q); store_transposed(Qt, ts, tok, ch, q);
     store_rowmajor(Ks, tok, ch, k); store_transposed(Kt, ts, tok, ch, k);
     store_rowmajor(Vs, tok, ch, v);
     store_rowmajor(Gs, tok, ch, gg); store_transposed(Gt, ts, tok, ch, gg);
-    // D[tok] = sum_d dO * O : 8 lanes (the 8 chunks of a row) are consecutive lanes of one warp
-    const bf16* ge = reinterpret_cast<const bf16*>(&gg);
-    const bf16* oe = reinterpret_cast<const bf16*>(&oo);
+  }
+  // D[tok] = sum_d dO[tok][d] * O[tok][d]: two lanes per token, 32 channels each, fixed order
+  for (int idx = threadIdx.x; idx < npad * 2; idx += blockDim.x) {
+    const int tok = idx >> 1, half = idx & 1;
     float d = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) d = fmaf(__bfloat162float(ge[i]), __bfloat162float(oe[i]), d);
+    for (int ch = 0; ch < 4; ++ch) {
+      const uint4 gg = load_chunk(gb, os, tok, half * 4 + ch, N), oo = load_chunk(ob, os, tok, half * 4 + ch, N);
+      const bf16* ge = reinterpret_cast<const bf16*>(&gg);
+      const bf16* oe = reinterpret_cast<const bf16*>(&oo);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) d = fmaf(__bfloat162float(ge[i]), __bfloat162float(oe[i]), d);
+    }
     d += __shfl_xor_sync(0xffffffffu, d, 1);
-    d += __shfl_xor_sync(0xffffffffu, d, 2);
-    d += __shfl_xor_sync(0xffffffffu, d, 4);
-    if (ch == 0) {
+    if (half == 0) {
       Ds[tok] = d;
       Ls[tok] = tok < N ? lse[((int64_t)b * H + h) * N + tok] : 0.f;
     }
@@ -238,8 +267,8 @@ attn_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o, const 
     for (int jb = 0; jb < nkb; ++jb) {
       float s[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
       float dp[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-      mma_rowmajor_b(s, qa, Ks, jb * 16, g, t);
-      mma_rowmajor_b(dp, ga, Vs, jb * 16, g, t);
+      mma_rowmajor_b(s, qa, Ks, jb * 16, lane);
+      mma_rowmajor_b(dp, ga, Vs, jb * 16, lane);
       float ds[2][4];
 #pragma unroll
       for (int nt = 0; nt < 2; ++nt)
@@ -247,12 +276,12 @@ attn_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o, const 
         for (int e = 0; e < 4; ++e) {
           const int col = jb * 16 + nt * 8 + 2 * t + (e & 1);
           const float L = (e < 2) ? L0 : L1, D = (e < 2) ? D0 : D1;
-          const float p = col < N ? exp2f(s[nt][e] * c - L) : 0.f;
+          const float p = col < N ? ex2(s[nt][e] * c - L) : 0.f;
           ds[nt][e] = p * (dp[nt][e] - D) * scale;
         }
       const uint32_t da[4] = {pack2(ds[0][0], ds[0][1]), pack2(ds[0][2], ds[0][3]), pack2(ds[1][0], ds[1][1]),
                               pack2(ds[1][2], ds[1][3])};
-      mma_transposed_b(dq, da, Kt, ts, jb * 16, g, t);
+      mma_transposed_b(dq, da, Kt, ts, jb * 16, lane);
     }
     store_tile(dq_out, rs, r0, g, t, N, dq, 1.f, 1.f);
   }
@@ -269,15 +298,15 @@ attn_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o, const 
     for (int ib = 0; ib < nkb; ++ib) {
       float st[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
       float dpt[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-      mma_rowmajor_b(st, ka, Qs, ib * 16, g, t);
-      mma_rowmajor_b(dpt, va, Gs, ib * 16, g, t);
+      mma_rowmajor_b(st, ka, Qs, ib * 16, lane);
+      mma_rowmajor_b(dpt, va, Gs, ib * 16, lane);
       float pt[2][4], dst[2][4];
 #pragma unroll
       for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int qi = ib * 16 + nt * 8 + 2 * t + (e & 1);
-          const float p = qi < N ? exp2f(st[nt][e] * c - Ls[qi]) : 0.f;
+          const float p = qi < N ? ex2(st[nt][e] * c - Ls[qi]) : 0.f;
           pt[nt][e] = p;
           dst[nt][e] = p * (dpt[nt][e] - Ds[qi]) * scale;
         }
@@ -285,8 +314,8 @@ attn_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o, const 
                               pack2(pt[1][2], pt[1][3])};
       const uint32_t da[4] = {pack2(dst[0][0], dst[0][1]), pack2(dst[0][2], dst[0][3]), pack2(dst[1][0], dst[1][1]),
                               pack2(dst[1][2], dst[1][3])};
-      mma_transposed_b(dv, pa, Gt, ts, ib * 16, g, t);
-      mma_transposed_b(dk, da, Qt, ts, ib * 16, g, t);
+      mma_transposed_b(dv, pa, Gt, ts, ib * 16, lane);
+      mma_transposed_b(dk, da, Qt, ts, ib * 16, lane);
     }
     store_tile(dk_out, rs, r0, g, t, N, dk, 1.f, 1.f);
     store_tile(dv_out, rs, r0, g, t, N, dv, 1.f, 1.f);

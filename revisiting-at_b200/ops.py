@@ -186,6 +186,15 @@ def _derived(param, tag, fn):
     return val
 
 
+def invalidate_derived(keep_tags=('host3',)):
+    """Forget every cached kernel-side parameter copy (except host-side constants): the next use rebuilds
+    it.  Called right before a CUDA-graph capture so that the cast / transpose / fold kernels are recorded
+    INSIDE the graph and every replay re-derives them from the (in-place updated) fp32 master parameters."""
+    for k in [k for k in _PCACHE if k[1] not in keep_tags]:
+        del _PCACHE[k]
+    _WCACHE.clear()
+
+
 def _taps(dw_w):
     """depthwise weight [C,1,7,7] -> tap-major fp32 [49][C]"""
     return _derived(dw_w, 'taps', lambda w: w.float().reshape(w.shape[0], 49).t().contiguous())

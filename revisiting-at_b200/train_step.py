@@ -17,6 +17,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import _abi
 from .attack import apgd_train
 from .fgsm import fgsm_train
 
@@ -66,6 +67,48 @@ def make_attack(attack='apgd', norm='Linf', eps=4. / 255., n_iter=2, verbose=Fal
     raise ValueError(attack)
 
 
+class GraphedAttack:
+    """`perturb(model, x, y)` replayed from a CUDA graph.
+
+    The attack is a fixed launch sequence: no host synchronisation, data-independent checkpoint schedule, every
+    data-dependent branch of the reference is a per-sample predicate on the device (attack.py).  With n_iter=2
+    it is ~750 launches of 10-150 us kernels per call, so at 1 process per GPU the Python/launch path is a visible
+    share of the step; one `cudaGraphLaunch` removes it.  The first `warmup` calls per input signature run
+    eagerly (cuDNN/cuBLAS heuristics, lazy module loading), the next one is captured -- after forgetting the
+    cached bf16/transposed parameter copies, so their re-derivation from the fp32 master parameters is part of
+    the graph and a replay after an optimiser step sees the new weights.  Inputs are copied into static buffers;
+    the returned tensors are the graph's static outputs, valid until the next call with the same signature."""
+
+    def __init__(self, perturb, warmup=2):
+        self.perturb = perturb
+        self.warmup = warmup
+        self.seen = {}
+        self.graphs = {}
+
+    def __call__(self, model, x, y):
+        from . import ops
+        key = (tuple(x.shape), x.dtype, tuple(x.stride()), tuple(y.shape), y.dtype, x.device.index, id(model))
+        hit = self.graphs.get(key)
+        if hit is None:
+            n = self.seen.get(key, 0)
+            self.seen[key] = n + 1
+            if n < self.warmup or not x.is_cuda:
+                return self.perturb(model, x, y)
+            sx, sy = x.detach().clone(), y.detach().clone()
+            ops.invalidate_derived()
+            graph = torch.cuda.CUDAGraph()
+            n0 = _abi.LAUNCHES['count']
+            with torch.cuda.graph(graph, capture_error_mode='thread_local'):
+                out = self.perturb(model, sx, sy)
+            hit = self.graphs[key] = (graph, sx, sy, out, _abi.LAUNCHES['count'] - n0)
+        graph, sx, sy, out, n_kernels = hit
+        sx.copy_(x, non_blocking=True)
+        sy.copy_(y, non_blocking=True)
+        graph.replay()
+        _abi.LAUNCHES['count'] += n_kernels               # kernels of this library inside the replayed graph
+        return out
+
+
 class DeviceEma:
     """EMA of the parameters kept on the device: one fused multi-tensor lerp per step
     (replaces timm ModelEmaV2(decay=0.9999, device='cpu'), main.py:882-887,996-997)."""
@@ -85,10 +128,14 @@ class AdvTrainStep:
 
     def __init__(self, base_model, attack='apgd', norm='Linf', eps=4. / 255., n_iter=2, lr=1e-3, weight_decay=0.05,
                  label_smoothing=0., ema=False, distributed=False, device=None, autocast_dtype=torch.bfloat16,
-                 channels_last=True, mixup_fn=None, perturb=None):
+                 channels_last=True, mixup_fn=None, perturb=None, graph_attack=False):
         self.device = device
         # `perturb` overrides the attack callable (same (model, x, y) contract as main.py:283)
         perturb = perturb if perturb is not None else make_attack(attack, norm, eps, n_iter, mixup_fn=mixup_fn)
+        self.eager_perturb = perturb
+        if graph_attack and perturb is not None and attack == 'apgd':      # fgsm draws fresh noise per call: stays eager
+            perturb = GraphedAttack(perturb)
+        self.graphed_perturb = perturb
         if channels_last:
             base_model = base_model.to(memory_format=torch.channels_last)      # misc.use_channel_last (main.py:815-817)
         model = WrappedModel(base_model, perturb) if perturb is not None else base_model
@@ -109,6 +156,11 @@ class AdvTrainStep:
         self.label_smoothing = label_smoothing
         self.mixup_fn = mixup_fn
         self.autocast_dtype = autocast_dtype
+
+    def use_graph(self, on):
+        """switch the attack between its CUDA-graph replay and the eager launch sequence (same kernels)"""
+        if self.perturb:
+            self.raw.perturb = self.graphed_perturb if on else self.eager_perturb
 
     def loss(self, output, target):
         if target.dim() == 2:                                                   # timm SoftTargetCrossEntropy (main.py:461-466)
