@@ -31,18 +31,26 @@ def test_graphed_attack_equals_eager_and_tracks_weight_updates(cuda_dev):
 
 
 def test_train_step_with_graphed_attack_matches_eager(cuda_dev):
-    """three optimiser steps, graph on vs off, same seeds: identical losses and parameters"""
+    """Inside real optimiser steps (bf16 autocast, channels_last parameters, fused AdamW): at every step the
+    replayed attack returns bit for bit what the eager launch sequence returns on the same parameter state.
+    (Whole training runs are not compared: the weight-gradient kernels accumulate with atomics, so two eager
+    runs already differ in the last bits of the parameters after one step.)"""
     from revisiting_at_b200 import convnext
     from revisiting_at_b200.train_step import AdvTrainStep
     base = convnext.build('convnext_tiny', normalize=True, seed=0)
     g = torch.Generator().manual_seed(2)
     batches = [(torch.rand(8, 3, 64, 64, generator=g).to(cuda_dev), torch.randint(0, 1000, (8,), generator=g).to(cuda_dev))
-               for _ in range(5)]
-    out = []
-    for graph in (False, True):
-        step = AdvTrainStep(copy.deepcopy(base), 'apgd', 'Linf', 4. / 255., 2, device=cuda_dev, graph_attack=graph)
-        losses = [step(x, y).item() for x, y in batches]
-        out.append((losses, [p.detach().clone() for p in step.raw.parameters()]))
-    assert out[0][0] == out[1][0], (out[0][0], out[1][0])
-    for a, b in zip(out[0][1], out[1][1]):
-        assert torch.equal(a, b)
+               for _ in range(6)]
+    step = AdvTrainStep(copy.deepcopy(base), 'apgd', 'Linf', 4. / 255., 2, device=cuda_dev, graph_attack=True)
+    graphed, eager = step.graphed_perturb, step.eager_perturb
+    checked = []
+
+    def spy(model, x, y):
+        ref = [t.clone() for t in eager(model, x, y)]
+        out = graphed(model, x, y)
+        checked.append(all(torch.equal(a, b) for a, b in zip(out, ref)))
+        return out
+    step.raw.perturb = spy
+    losses = [step(x, y).item() for x, y in batches]
+    assert checked == [True] * 6, checked
+    assert len(graphed.graphs) == 1 and all(l == l and l < 20 for l in losses), losses
