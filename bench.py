@@ -55,6 +55,8 @@ def parse():
                     help='convnext_tiny = BASELINE configs[1] (the metric line); the others are secondary workloads')
     ap.add_argument('--batch', type=int, default=None, help='images per GPU (default: the BASELINE config of --arch)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--ema', type=int, default=None, help='on-device EMA of the parameters (default: on for convnext_base = config 4)')
+    ap.add_argument('--label-smoothing', type=float, default=None, help='default 0.1 for convnext_base (config 4), else 0')
     ap.add_argument('--no-graph', action='store_true', help='launch the attack kernel by kernel instead of replaying its CUDA graph')
     ap.add_argument('--cpu-seconds', type=float, default=20.0, help='budget of the cpu_baseline sample')
     return ap.parse_args()
@@ -84,12 +86,13 @@ def build_oracle(arch):
     return convnext_oracle.build(arch, normalize=True, seed=0)
 
 
-def workload_config(n_gpus, batch, arch=ARCH):
+def workload_config(n_gpus, batch, arch=ARCH, ema=False, label_smoothing=0.):
     name, _, which = WORKLOADS[arch]
     return {'workload': f'{name} APGD l-inf 4/255 n_iter={N_ITER} adversarial train step, bf16 autocast, '
                         f'batch {batch}/GPU, 3x{RES}x{RES} ({which})',
             'arch': arch, 'batch_per_gpu': batch, 'global_batch': batch * n_gpus, 'resolution': RES,
             'norm': 'Linf', 'eps': '4/255', 'n_iter': N_ITER, 'parallelism': f'dp{n_gpus}',
+            'ema': bool(ema), 'label_smoothing': label_smoothing,
             'l2_policy': 'inputs_exceed_l2 (per-step working set >> 126 MB; image-sized passes stream 385 MB)'}
 
 
@@ -207,7 +210,7 @@ def run_reference(args):
     sample = f'{args.steps} steps of {batch} images (bounded sample of the {args.batch}/GPU step), fp32, {cores} threads'
     line = {'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps, 'higher_is_better': True, 'scaling': 'weak',
-            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(args.gpus, args.batch, args.arch),
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(args.gpus, args.batch, args.arch, args.ema, args.label_smoothing),
             'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
             'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
@@ -235,7 +238,7 @@ def run_b200(args):
     batch = args.batch
     model = build_engine(args.arch)
     step = AdvTrainStep(model, 'apgd', 'Linf', EPS, N_ITER, distributed=distributed, device=dev,
-                        graph_attack=not args.no_graph)
+                        graph_attack=not args.no_graph, ema=bool(args.ema), label_smoothing=args.label_smoothing)
 
     pool = 2
     host = [synth_batch(batch, 1234 + 17 * rank + i) for i in range(pool)]
@@ -328,7 +331,7 @@ def run_b200(args):
     line = {
         'metric': METRIC, 'value': imgs / (ms * 1e-3), 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
         'warmup': n_warm, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
-        'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic', 'config': workload_config(world, batch, args.arch),
+        'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic', 'config': workload_config(world, batch, args.arch, args.ema, args.label_smoothing),
         'e2e': {'value': imgs / (ms_e2e * 1e-3), 'unit': UNIT,
                 'h2d_bytes_per_step': batch * N_FTS * 4 + batch * 8, 'd2h_bytes_per_step': 4,
                 'ms_per_step': ms_e2e / args.steps},
@@ -356,6 +359,10 @@ def main():
     args = parse()
     if args.batch is None:
         args.batch = WORKLOADS[args.arch][1]
+    if args.ema is None:
+        args.ema = int(args.arch == 'convnext_base')
+    if args.label_smoothing is None:
+        args.label_smoothing = 0.1 if args.arch == 'convnext_base' else 0.
     if args.impl == 'reference':
         run_reference(args)
     else:

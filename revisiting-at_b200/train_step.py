@@ -144,7 +144,11 @@ class AdvTrainStep:
         self.ema = DeviceEma(model) if ema else None                           # created before the DDP wrap (main.py:884)
         if distributed:
             ids = [device.index] if (device is not None and device.type == 'cuda') else None
-            model = nn.parallel.DistributedDataParallel(model, device_ids=ids)   # main.py:890
+            # main.py:890.  broadcast_buffers=False: the only buffers are the normaliser's constant mean/std, and the
+            # per-forward re-broadcast would bump their version counters, i.e. force a device->host read of the 3+3
+            # constants (a host synchronisation) in front of every fused first-stem-stage launch.
+            model = nn.parallel.DistributedDataParallel(model, device_ids=ids, broadcast_buffers=False,
+                                                        gradient_as_bucket_view=True)
         self.model = model
         self.perturb = perturb is not None
         decay, no_decay = [], []
