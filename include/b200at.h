@@ -30,6 +30,7 @@ extern "C" {
 /* loss codes: criterion_dict keys 'ce' / 'dlr' (autopgd_train_clean.py:113-114) */
 #define B200AT_LOSS_CE 0
 #define B200AT_LOSS_DLR 1
+#define B200AT_LOSS_DLR_TARGETED 2 /* only through b200at_loss_bookkeep_targeted */
 
 int b200at_abi_version(void);
 
@@ -50,6 +51,14 @@ int b200at_loss_bookkeep(const void* logits, int logits_dtype, const int64_t* y_
                          void* dlogits, float* loss_out, float* state, float* loss_steps, int64_t B, int64_t C,
                          int iter, int n_iter, int ckpt_k, int norm_kind, int loss_kind, float step_full,
                          float step_min, int64_t n_fts, void* stream);
+
+/* Same kernel with the targeted DLR loss (autopgd_train_clean.py:106-111 `dlr_loss_targeted`; the loss of
+ * AutoAttack's APGD-T, AA_eval.py:226-239):  -(z_y - z_t) / (z_(1) - (z_(3) + z_(4)) / 2 + 1e-12), y_target [B] int64.
+ * The prediction / robust mask still compares with y_hard.  C >= 4. */
+int b200at_loss_bookkeep_targeted(const void* logits, int logits_dtype, const int64_t* y_hard, const int64_t* y_target,
+                                  void* dlogits, float* loss_out, float* state, float* loss_steps, int64_t B,
+                                  int64_t C, int iter, int n_iter, int ckpt_k, int norm_kind, float step_full,
+                                  float step_min, int64_t n_fts, void* stream);
 
 /* autopgd_train_clean.py:213-226,260 fused with the image side of :304, :321-324, :345-346:
  * one pass that (1) applies the pending x_best / grad_best / x_best_adv writes and the restore from

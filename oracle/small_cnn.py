@@ -24,3 +24,19 @@ def from_fixture(g) -> SmallCNN:
     sd = {k: torch.from_numpy(np.asarray(g['w_' + k.replace('.', '_')])) for k in m.state_dict()}
     m.load_state_dict(sd)
     return m.eval()
+
+
+class SensitiveNet(nn.Module):
+    """Small model whose predictions flip under perturbations of a few /255 (conv -> dense -> dense): exercises the
+    restart / target-class compaction of the AutoAttack protocol, which the mean-pooled SmallCNN never triggers."""
+    def __init__(self, C=10, hw=16, k=3.0):
+        super().__init__()
+        self.c1 = nn.Conv2d(3, 8, 3, stride=2, padding=1)
+        self.fc1 = nn.Linear(8 * (hw // 2) ** 2, 32)
+        self.fc2 = nn.Linear(32, C)
+        self.k = k
+
+    def forward(self, x):
+        h = F.gelu(self.c1(x))
+        h = F.gelu(self.fc1(h.flatten(1)))
+        return self.fc2(h) * self.k

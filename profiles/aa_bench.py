@@ -1,0 +1,64 @@
+"""Throughput of the AutoAttack-compatible evaluation (BASELINE config 5): APGD-CE + APGD-T (9 targets), 100
+iterations, l-inf 4/255, ConvNeXt-L-CvSt at 320x320, random-init weights, synthetic points, one GPU's share.
+
+    python profiles/aa_bench.py [--arch convnext_large] [--res 320] [--n 100] [--bs 100] [--iters 100] [--targets 9]
+
+With random-init weights and labels = the model's own predictions every point starts robust, and almost none is
+broken, so all 1 + targets runs execute on the full batch: the worst case of the protocol (no compaction savings).
+Prints one JSON line: points/s, attack forward+backward evaluations/s, ms per APGD iteration."""
+import argparse
+import json
+import os
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import revisiting_at_b200  # noqa: E402,F401
+from revisiting_at_b200 import _abi, autoattack, convnext  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument('--arch', default='convnext_large')
+ap.add_argument('--res', type=int, default=320)
+ap.add_argument('--n', type=int, default=100)
+ap.add_argument('--bs', type=int, default=100)
+ap.add_argument('--iters', type=int, default=100)
+ap.add_argument('--targets', type=int, default=9)
+ap.add_argument('--norm', default='Linf')
+a = ap.parse_args()
+dev = torch.device('cuda:0')
+torch.backends.cudnn.benchmark = True
+m = convnext.build(a.arch, normalize=True, seed=0).to(dev).eval()
+g = torch.Generator().manual_seed(0)
+x = torch.rand(a.n, 3, a.res, a.res, generator=g).to(dev)
+with torch.no_grad():
+    y = torch.cat([m(x[i:i + a.bs]).float().max(1)[1] for i in range(0, a.n, a.bs)])
+eps = {'Linf': 4 / 255., 'L2': 2., 'L1': 75.}[a.norm]
+adv = autoattack.AutoAttack(m, norm=a.norm, eps=eps, version='standard', seed=0, verbose=False, device=dev)
+adv.attacks_to_run = ['apgd-ce', 'apgd-t']
+adv.apgd.n_iter = adv.apgd_targeted.n_iter = a.iters
+adv.apgd.n_iter_orig = adv.apgd_targeted.n_iter_orig = a.iters
+adv.apgd_targeted.n_target_classes = a.targets
+# warm-up: a short evaluation (cuDNN/cuBLAS heuristics, lazy module loads)
+w = autoattack.AutoAttack(m, norm=a.norm, eps=eps, version='standard', seed=0, verbose=False, device=dev)
+w.attacks_to_run = ['apgd-ce', 'apgd-t']
+w.apgd.n_iter = w.apgd_targeted.n_iter = 3
+w.apgd.n_iter_orig = w.apgd_targeted.n_iter_orig = 3
+w.apgd_targeted.n_target_classes = 1
+w.run_standard_evaluation(x[:a.bs], y[:a.bs], bs=a.bs)
+torch.cuda.synchronize()
+n0 = _abi.LAUNCHES['count']
+t0 = time.time()
+x_adv = adv.run_standard_evaluation(x, y, bs=a.bs)
+torch.cuda.synchronize()
+dt = time.time() - t0
+runs = 1 + a.targets
+evals = a.n * runs * (a.iters + 1)
+print(json.dumps({'metric': 'aa_eval_points_per_sec', 'value': a.n / dt, 'unit': 'points/s', 'seconds': dt,
+                  'config': {'workload': f'AutoAttack standard [apgd-ce, apgd-t x{a.targets}] {a.iters} iterations, '
+                                         f'{a.norm} eps={eps:.5f}, {a.arch}-CvSt at {a.res}x{a.res}, {a.n} points, bs {a.bs} '
+                                         '(BASELINE.json configs[4], one GPU)'},
+                  'model_evaluations_per_sec': evals / dt, 'ms_per_apgd_iteration': 1e3 * dt / (runs * (a.iters + 1) * ((a.n + a.bs - 1) // a.bs)),
+                  'robust_accuracy': adv.results, 'gpu_launches': _abi.LAUNCHES['count'] - n0,
+                  'max_abs_delta': (x_adv - x).abs().max().item()}))

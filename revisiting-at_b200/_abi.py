@@ -22,7 +22,7 @@ ST_ROWS = 20
 LOG_MAX_SLOTS = 8
 F_IMPROVED, F_WRITE_ADV, F_RESTORE = 1, 2, 4
 NORMS = {'Linf': 0, 'L2': 1, 'L1': 2}
-LOSSES = {'ce': 0, 'dlr': 1}
+LOSSES = {'ce': 0, 'dlr': 1, 'dlr-targeted': 2}
 _DT = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
 
 _lib = None
@@ -85,6 +85,7 @@ def _declare(L):
         'b200at_l2_step': [P, P, P, P, P, P, P, P, P, P, I64, I64, F, F, P],
         'b200at_l1_step': [P, P, P, P, P, P, P, P, P, I64, I64, F, P],
         'b200at_loss_bookkeep': [P, I, P, P, P, P, P, P, I64, I64, I, I, I, I, I, F, F, I64, P],
+        'b200at_loss_bookkeep_targeted': [P, I, P, P, P, P, P, P, I64, I64, I, I, I, I, F, F, I64, P],
         'b200at_fgsm_start': [P, P, P, I64, F, F, I, P],
         'b200at_fgsm_step': [P, P, P, P, I64, F, F, I, P],
     }
@@ -183,7 +184,7 @@ def flush_best(x_adv, x_best, x_best_adv, state):
 
 
 def loss_bookkeep(logits, y, dlogits, loss_out, state, loss_steps, it, n_iter, ckpt_k, norm, loss, step_full,
-                  step_min, n_fts):
+                  step_min, n_fts, y_target=None):
     if not logits.is_cuda or logits.dim() != 2 or not logits.is_contiguous() or logits.dtype not in _DT:
         raise B200atError(f'logits must be a contiguous CUDA [B,C] fp32/bf16/fp16 tensor, got '
                           f'{tuple(logits.shape)} {logits.dtype}')
@@ -198,6 +199,15 @@ def loss_bookkeep(logits, y, dlogits, loss_out, state, loss_steps, it, n_iter, c
     if dlogits is not None and (dlogits.dtype != logits.dtype or dlogits.shape != logits.shape
                                 or not dlogits.is_contiguous()):
         raise B200atError('dlogits must match logits')
+    if loss == 'dlr-targeted':
+        if y_target is None or y_target.dtype != torch.int64 or y_target.shape != (B,) or y.dim() != 1:
+            raise B200atError("loss 'dlr-targeted' needs hard labels and an int64 [B] y_target")
+        with _Timed('loss_bookkeep'):
+            _check(lib().b200at_loss_bookkeep_targeted(_p(logits), _DT[logits.dtype], yh, _p(y_target.contiguous()),
+                                                       _p(dlogits), _p(loss_out), _p(state), _p(loss_steps), B, C, it,
+                                                       n_iter, ckpt_k, NORMS[norm], step_full, step_min, n_fts,
+                                                       _stream()), 'loss_bookkeep_targeted')
+        return
     with _Timed('loss_bookkeep'):
         _check(lib().b200at_loss_bookkeep(_p(logits), _DT[logits.dtype], yh, ys, _p(dlogits), _p(loss_out),
                                           _p(state), _p(loss_steps), B, C, it, n_iter, ckpt_k, NORMS[norm],

@@ -88,11 +88,16 @@ def _dense_like_input(x):
 
 
 def run_apgd(be, model, x, y, norm, eps, n_iter=10, use_rs=False, loss='ce', verbose=False, mixup=None,
-             is_train=True, log_slots=None):
+             is_train=True, log_slots=None, x_init=None, y_target=None, l1_restart_state=False):
+    """`x_init`, `y_target`, `l1_restart_state`: the extras of AutoAttack's `APGDAttack.attack_single_run`
+    (start point instead of clamp(x); targeted DLR; l1 top-k / sparsity initialised from the start point) --
+    reached through `autoattack.py`, never through `apgd_train`, whose signature stays the reference's."""
     assert not model.training                                     # autopgd_train_clean.py:125
     if use_rs:
         raise TypeError('exceptions must derive from BaseException')   # `raise NotImplemented` (:137)
-    if loss not in _SUPPORTED_LOSS:
+    if loss == 'dlr-targeted' and y_target is not None:
+        pass                                                      # autoattack.APGDAttack_targeted
+    elif loss not in _SUPPORTED_LOSS:
         if loss in ('softloss', 'dlr-targeted'):
             # in the reference's table (:113-114) but not drivable through apgd_train's call sites
             raise TypeError(f'loss {loss!r} cannot be driven through apgd_train')
@@ -114,11 +119,13 @@ def run_apgd(be, model, x, y, norm, eps, n_iter=10, use_rs=False, loss='ce', ver
     topk0 = (.05 if is_train else .2) if norm == 'L1' else 0.
     sched = checkpoint_schedule(norm, n_iter)
     soft = mixup is not None
-    if loss == 'dlr' and (soft or y.dim() != 1):
-        raise _abi.B200atError("loss 'dlr' needs hard labels")
+    if loss in ('dlr', 'dlr-targeted') and (soft or y.dim() != 1):
+        raise _abi.B200atError(f"loss {loss!r} needs hard labels")
+    tkw = {'y_target': y_target} if loss == 'dlr-targeted' else {}
 
     log_slots = LOG_SLOTS if log_slots is None else log_slots
-    use_log = norm == 'Linf' and 1 <= n_iter and n_iter + 1 <= min(log_slots, _abi.LOG_MAX_SLOTS)
+    use_log = (norm == 'Linf' and 1 <= n_iter and n_iter + 1 <= min(log_slots, _abi.LOG_MAX_SLOTS)
+               and x_init is None)
     grad_buf = None
     state = torch.empty(_abi.ST_ROWS, B, device=dev, dtype=torch.float32)
     loss_steps = torch.zeros(max(n_iter, 1), B, device=dev, dtype=torch.float32)
@@ -139,7 +146,7 @@ def run_apgd(be, model, x, y, norm, eps, n_iter=10, use_rs=False, loss='ce', ver
             lg = lg.contiguous()
         dl = torch.empty_like(lg) if need_grad else None
         be.loss_bookkeep(lg, y, dl, None, state, loss_steps, it, n_iter, sched[it] if it >= 0 else 0, norm, loss,
-                         step_full, step_min, n_fts)
+                         step_full, step_min, n_fts, **tkw)
         if not need_grad:
             return None
         t0 = time.time()
@@ -179,6 +186,18 @@ def run_apgd(be, model, x, y, norm, eps, n_iter=10, use_rs=False, loss='ce', ver
     buf_a, buf_b = torch.empty_like(x), torch.empty_like(x)
     x_best, x_best_adv, grad_best = torch.empty_like(x), torch.empty_like(x), torch.empty_like(x)
     be.init(x, buf_a, state, step_full, topk0)
+    if x_init is not None:
+        # autoattack `attack_single_run`: x_adv = x_init.clamp(0, 1) as the first iterate (random start / the
+        # previous stage's x_best of the l1 large-eps schedule)
+        torch.clamp(x_init.detach().to(torch.float32), 0., 1., out=buf_a)
+        if norm == 'L1':
+            nnz = (buf_a != x).reshape(B, -1).sum(-1)
+            state[_abi.ST_SP_ADV] = nnz.to(torch.int32).view(torch.float32)    # L0(x_adv - x) of the start point
+            if l1_restart_state:
+                # topk = L0(x_adv - x) / n_fts / 1.5 ; sp_old = L0(x_adv - x)   (autopgd_base.py, x_init branch)
+                sp = nnz.to(torch.float32)
+                state[_abi.ST_TOPK] = sp / n_fts / 1.5
+                state[_abi.ST_SP_OLD] = sp
     grad = evaluate(buf_a, -1, True)
     cur, old, first = buf_a, buf_a, True
     for i in range(n_iter):

@@ -504,6 +504,7 @@ struct LossArgs {
   const void* logits;
   const int64_t* y_hard;  // [B] or null
   const float* y_soft;    // [B][C] or null
+  const int64_t* y_target;  // [B] or null (targeted DLR only)
   void* dlogits;          // [B][C] same dtype as logits, or null
   float* loss_out;        // [B] or null
   float* st;
@@ -558,6 +559,8 @@ __global__ void __launch_bounds__(128) loss_bookkeep_kernel(LossArgs p) {
     loss = warp_sum(acc);
   } else {
     // DLR (:99-104): -(z_y - z_other) / (z_(1) - z_(3) + 1e-12); top-3 by two more masked argmax sweeps
+    // targeted DLR (:106-111): -(z_y - z_t) / (z_(1) - (z_(3) + z_(4)) / 2 + 1e-12); one more sweep for z_(4)
+    const bool targeted = p.loss_kind == B200AT_LOSS_DLR_TARGETED;
     float m2 = ninf, m3 = ninf; int i2 = 0x7fffffff, i3 = 0x7fffffff;
     for (int c = lane; c < p.C; c += 32) {
       const float v = to_f32<T>(z[c]);
@@ -570,6 +573,31 @@ __global__ void __launch_bounds__(128) loss_bookkeep_kernel(LossArgs p) {
     }
     warp_argmax(m3, i3);
     const float zy = to_f32<T>(z[label]);
+    if (targeted) {
+      float m4 = ninf; int i4 = 0x7fffffff;
+      for (int c = lane; c < p.C; c += 32) {
+        const float v = to_f32<T>(z[c]);
+        if (c != i1 && c != i2 && c != i3 && better(v, c, m4, i4)) { m4 = v; i4 = c; }
+      }
+      warp_argmax(m4, i4);
+      const int it = (int)p.y_target[b];
+      const float num = zy - to_f32<T>(z[it]);
+      const float den = (m1 - 0.5f * (m3 + m4)) + 1e-12f;
+      loss = -num / den;
+      if (dz) {
+        // d(-num/den) = -(e_y - e_t)/den + num/den^2 * (e_1 - e_3/2 - e_4/2)
+        const float q = num / (den * den);
+        for (int c = lane; c < p.C; c += 32) {
+          float gz = 0.0f;
+          if (c == label) gz -= 1.0f / den;
+          if (c == it) gz += 1.0f / den;
+          if (c == i1) gz += q;
+          if (c == i3) gz -= 0.5f * q;
+          if (c == i4) gz -= 0.5f * q;
+          dz[c] = from_f32<T>(gz);
+        }
+      }
+    } else {
     const int io = pred ? i2 : i1;
     const float zo = pred ? m2 : m1;
     const float den = (m1 - m3) + 1e-12f;
@@ -586,6 +614,7 @@ __global__ void __launch_bounds__(128) loss_bookkeep_kernel(LossArgs p) {
         if (c == i3) gz -= q;
         dz[c] = from_f32<T>(gz);
       }
+    }
     }
   }
   if (lane == 0) {
@@ -728,16 +757,20 @@ int b200at_fgsm_step(const float* x, const float* x_adv, const float* grad, floa
   return (int)cudaGetLastError();
 }
 
-int b200at_loss_bookkeep(const void* logits, int logits_dtype, const int64_t* y_hard, const float* y_soft,
-                         void* dlogits, float* loss_out, float* state, float* loss_steps, int64_t B, int64_t C,
-                         int iter, int n_iter, int ckpt_k, int norm_kind, int loss_kind, float step_full,
-                         float step_min, int64_t n_fts, void* stream) {
+static int launch_loss_bookkeep(const void* logits, int logits_dtype, const int64_t* y_hard, const float* y_soft,
+                                const int64_t* y_target, void* dlogits, float* loss_out, float* state,
+                                float* loss_steps, int64_t B, int64_t C, int iter, int n_iter, int ckpt_k,
+                                int norm_kind, int loss_kind, float step_full, float step_min, int64_t n_fts,
+                                void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   if (B <= 0) return (int)cudaSuccess;
   if ((y_hard == nullptr) == (y_soft == nullptr)) return (int)cudaErrorInvalidValue;
   if (loss_kind == B200AT_LOSS_DLR && (y_soft != nullptr || C < 3)) return (int)cudaErrorInvalidValue;
-  LossArgs p{logits, y_hard, y_soft, dlogits, loss_out, state, loss_steps, (int)B, (int)C, iter, n_iter, ckpt_k,
-             norm_kind, loss_kind, step_full, step_min, (float)n_fts};
+  if (loss_kind == B200AT_LOSS_DLR_TARGETED && (y_soft != nullptr || y_target == nullptr || C < 4))
+    return (int)cudaErrorInvalidValue;
+  if (loss_kind < B200AT_LOSS_CE || loss_kind > B200AT_LOSS_DLR_TARGETED) return (int)cudaErrorInvalidValue;
+  LossArgs p{logits, y_hard, y_soft, y_target, dlogits, loss_out, state, loss_steps, (int)B, (int)C, iter, n_iter,
+             ckpt_k, norm_kind, loss_kind, step_full, step_min, (float)n_fts};
   const int grid = (int)((B + 3) / 4);
   switch (logits_dtype) {
     case B200AT_DT_F32: loss_bookkeep_kernel<float><<<grid, 128, 0, s>>>(p); break;
@@ -746,6 +779,24 @@ int b200at_loss_bookkeep(const void* logits, int logits_dtype, const int64_t* y_
     default: return (int)cudaErrorInvalidValue;
   }
   return (int)cudaGetLastError();
+}
+
+int b200at_loss_bookkeep(const void* logits, int logits_dtype, const int64_t* y_hard, const float* y_soft,
+                         void* dlogits, float* loss_out, float* state, float* loss_steps, int64_t B, int64_t C,
+                         int iter, int n_iter, int ckpt_k, int norm_kind, int loss_kind, float step_full,
+                         float step_min, int64_t n_fts, void* stream) {
+  if (loss_kind == B200AT_LOSS_DLR_TARGETED) return (int)cudaErrorInvalidValue;   // needs the targeted entry point
+  return launch_loss_bookkeep(logits, logits_dtype, y_hard, y_soft, nullptr, dlogits, loss_out, state, loss_steps, B, C,
+                              iter, n_iter, ckpt_k, norm_kind, loss_kind, step_full, step_min, n_fts, stream);
+}
+
+int b200at_loss_bookkeep_targeted(const void* logits, int logits_dtype, const int64_t* y_hard, const int64_t* y_target,
+                                  void* dlogits, float* loss_out, float* state, float* loss_steps, int64_t B,
+                                  int64_t C, int iter, int n_iter, int ckpt_k, int norm_kind, float step_full,
+                                  float step_min, int64_t n_fts, void* stream) {
+  return launch_loss_bookkeep(logits, logits_dtype, y_hard, nullptr, y_target, dlogits, loss_out, state, loss_steps, B,
+                              C, iter, n_iter, ckpt_k, norm_kind, B200AT_LOSS_DLR_TARGETED, step_full, step_min, n_fts,
+                              stream);
 }
 
 }  // extern "C"

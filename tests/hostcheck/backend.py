@@ -94,11 +94,18 @@ class HostBackend:
         B, n = x_adv.shape[0], x_adv[0].numel()
         self.L.hc_flush(_p(x_adv), _p(x_best), _p(x_best_adv), _p(state), B, n, self._vec(n))
 
+    def l1_projection(self, x, d, eps):
+        from oracle.apgd_oracle import l1_projection_rows
+        return l1_projection_rows(x, d, eps)
+
     def loss_bookkeep(self, logits, y, dlogits, loss_out, state, loss_steps, it, n_iter, ckpt_k, norm, loss,
-                      step_full, step_min, n_fts):
+                      step_full, step_min, n_fts, y_target=None):
         z = logits.detach().float().requires_grad_(True)
         if loss == 'ce':
             li = F.cross_entropy(z, y, reduction='none')
+        elif loss == 'dlr-targeted':
+            from oracle.autoattack_oracle import dlr_targeted_rows
+            li = dlr_targeted_rows(z, y, y_target)
         else:
             from oracle.apgd_oracle import dlr_rows
             li = dlr_rows(z, y)

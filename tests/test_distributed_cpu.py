@@ -106,3 +106,44 @@ def test_ddp_step_matches_single_process(tmp_path):
     res = torch.load(out)
     assert res['ranks_equal'] and res['loss_finite'], res
     assert res['max_diff_vs_single'] < 1e-4, res     # AdamW amplifies fp32 sum-order noise of the mean gradient
+
+
+def _aa_worker(rank, world, port, out):
+    _setup(rank, world, port)
+    import revisiting_at_b200  # noqa: F401
+    from revisiting_at_b200 import autoattack as aa
+    from hostcheck.backend import HostBackend
+    from oracle.small_cnn import SensitiveNet
+    torch.manual_seed(0)
+    model = SensitiveNet().eval()
+    g = torch.Generator().manual_seed(1)
+    x = torch.rand(10, 3, 16, 16, generator=g)
+    with torch.no_grad():
+        y = model(x).max(1)[1]
+
+    def evaluate(xs, ys, shard):
+        adv = aa.AutoAttack(model, norm='Linf', eps=8 / 255., version='standard', seed=7, verbose=False, device='cpu',
+                            backend=HostBackend(4))
+        adv.attacks_to_run = ['apgd-ce', 'apgd-t']
+        adv.apgd.n_iter = adv.apgd_targeted.n_iter = 6
+        adv.apgd_targeted.n_target_classes = 2
+        adv.apgd.rng_device = adv.apgd_targeted.rng_device = 'cpu'
+        return adv.run_standard_evaluation(xs, ys, bs=5, shard=shard), adv.results
+
+    sharded, res = evaluate(x, y, True)                 # every rank gets the full, gathered result
+    if rank == 0:
+        parts = [evaluate(x[lo:lo + 5], y[lo:lo + 5], False)[0] for lo in (0, 5)]   # the shards, one process
+        with torch.no_grad():
+            rob = (model(sharded).max(1)[1] == y).float().mean().item()
+        torch.save({'equal': torch.equal(sharded, torch.cat(parts)), 'results': res, 'robust': rob}, out)
+    dist.destroy_process_group()
+
+
+def test_autoattack_evaluation_shards_by_rank(tmp_path):
+    """run_standard_evaluation under a process group: contiguous shards per rank, one all-gather at the end; equal
+    to evaluating the two shards in one process, and the reported robust accuracy is the global one."""
+    out = str(tmp_path / 'res.pt')
+    mp.spawn(_aa_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    res = torch.load(out)
+    assert res['equal'], res
+    assert abs(res['results']['apgd-t'] - res['robust']) < 1e-6 and res['results']['clean'] == 1.0, res
