@@ -25,6 +25,18 @@ int b200at_ln_fwd(const void* x, const float* w, const float* b, void* y, float*
 int b200at_ln_bwd(const void* dy, const void* x, const float* w, const float* b, const float* mean, const float* rstd,
                   void* dx, float* dw, float* db, int64_t M, int64_t C, int fuse_gelu, void* stream);
 
+/* The LayerNorm in front of a downsample layer (models/convnext.py:79-82: LayerNorm(channels_first) -> Conv2d(k=2, s=2)),
+ * writing its result in the "2x2 patch" layout [B][H/2][W/2][2][2][C] (pixel (b,h,w) -> row 4*((b*H/2+h/2)*W/2+w/2) +
+ * 2*(h&1) + (w&1)), so that the stride-2 2x2 convolution becomes b200at_gemm_bf16 over [B*H/2*W/2][4C] rows with the
+ * weight reordered to [Cout][kh][kw][Cin].  x: NHWC bf16 [B][H][W][C]; mean / rstd are indexed by the INPUT pixel.
+ * H, W even. */
+int b200at_ln_fwd_patch2(const void* x, const float* w, const float* b, void* y, float* mean, float* rstd, int64_t B,
+                         int64_t H, int64_t W, int64_t C, float eps, void* stream);
+/* input gradient of the above: dy is in the patch layout (what the GEMM's input gradient produces), dx NHWC */
+int b200at_ln_bwd_patch2(const void* dy, const void* x, const float* w, const float* b, const float* mean,
+                         const float* rstd, void* dx, float* dw, float* db, int64_t B, int64_t H, int64_t W, int64_t C,
+                         void* stream);
+
 /* models/convnext.py:30-31: h = GELU(z + bias) on the 4C hidden (z = x @ W1^T from the GEMM), N % 8 == 0 */
 int b200at_bias_gelu_fwd(const void* z, const float* bias, void* h, int64_t M, int64_t N, void* stream);
 /* dz = dh * GELU'(z + bias); if dbias is non-null also ACCUMULATES the pwconv1 bias gradient

@@ -92,6 +92,8 @@ def _declare(L):
     sig.update({
         'b200at_ln_fwd': [P, P, P, P, P, P, I64, I64, F, I, P],
         'b200at_ln_bwd': [P, P, P, P, P, P, P, P, P, I64, I64, I, P],
+        'b200at_ln_fwd_patch2': [P, P, P, P, P, P, I64, I64, I64, I64, F, P],
+        'b200at_ln_bwd_patch2': [P, P, P, P, P, P, P, P, P, I64, I64, I64, I64, P],
         'b200at_bias_gelu_fwd': [P, P, P, I64, I64, P],
         'b200at_bias_gelu_bwd': [P, P, P, P, P, I64, I64, P],
         'b200at_colsum_bf16': [P, P, I64, I64, P],
@@ -293,6 +295,29 @@ def ln_bwd(dy, x, w, b, mean, rstd, dx, dw, db, gelu):
                                    int(gelu), _stream()), 'ln_bwd')
 
 
+def ln_fwd_patch2(x, w, b, y, mean, rstd, eps):
+    """LayerNorm over C of NHWC x [B,H,W,C], written in the 2x2-patch layout y [B*H/2*W/2, 4C]."""
+    B, H, W, C = x.shape
+    M = B * H * W
+    if y.numel() != x.numel():
+        raise B200atError('ln_fwd_patch2: y size')
+    with _Timed('ln_fwd_patch2'):
+        _check(lib().b200at_ln_fwd_patch2(_act(x, 'x'), _par(w, 'w', C), _par(b, 'b', C), _act(y, 'y'),
+                                          _par(mean, 'mean', M), _par(rstd, 'rstd', M), B, H, W, C, eps, _stream()),
+               'ln_fwd_patch2')
+
+
+def ln_bwd_patch2(dy, x, w, b, mean, rstd, dx, dw, db):
+    B, H, W, C = x.shape
+    M = B * H * W
+    if dy.numel() != x.numel() or dx.shape != x.shape:
+        raise B200atError('ln_bwd_patch2: sizes')
+    with _Timed('ln_bwd_patch2'):
+        _check(lib().b200at_ln_bwd_patch2(_act(dy, 'dy'), _act(x, 'x'), _par(w, 'w', C), _par(b, 'b', C),
+                                          _par(mean, 'mean', M), _par(rstd, 'rstd', M), _act(dx, 'dx'),
+                                          _par(dw, 'dw', C), _par(db, 'db', C), B, H, W, C, _stream()), 'ln_bwd_patch2')
+
+
 def bias_gelu_fwd(z, bias, h):
     M, N = z.shape
     with _Timed('bias_gelu_fwd'):
@@ -442,3 +467,19 @@ def attn_bwd(qkv, o, d_o, lse, dqkv, heads, scale):
     with _Timed('attn_bwd'):
         _check(lib().b200at_attn_bwd(_act(qkv, 'qkv'), _act(o, 'o'), _act(d_o, 'd_o'), _par(lse, 'lse', B * heads * N),
                                      _act(dqkv, 'dqkv'), B, N, heads, scale, _stream()), 'attn_bwd')
+
+
+def l1_projection(x2, y2, eps1):
+    """`L1_projection(x2, y2, eps1)` (autopgd_train_clean.py:24-91): the correction delta with x2 + y2 + delta inside
+    {||. - x2||_1 <= eps1} and [0,1]^n, through the projection half of the l1 step kernels (a zero gradient makes the
+    step half the identity, so the kernels see u = x2 + y2 and project it).  Tolerance-level (1e-6), like every l1
+    result."""
+    if not x2.is_cuda:
+        raise B200atError('L1_projection: CUDA tensors only (no CPU path)')
+    x = x2.detach().to(torch.float32).contiguous()
+    u = (x + y2.detach().to(torch.float32)).contiguous()
+    B = x.shape[0]
+    state = torch.zeros(ST_ROWS, max(B, 1), device=x.device, dtype=torch.float32)
+    out = torch.empty_like(x)
+    l1_step(x, u, out, torch.zeros_like(x), out, out, out, state, float(eps1))
+    return (out - u).view_as(x2)

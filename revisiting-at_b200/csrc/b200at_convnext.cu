@@ -55,11 +55,23 @@ __device__ __forceinline__ float group_sum(float v) {
   return v;
 }
 
+// Row of pixel (b, h, w) in the "2x2 patch" layout [B][H/2][W/2][2][2][C]: the 4 pixels of a stride-2 2x2 window are
+// adjacent, so the downsample convolution (models/convnext.py:79-82) is a plain GEMM over rows of 4C channels.
+// pW == 0: identity.
+__device__ __forceinline__ int64_t patch2_row(int64_t row, int pH, int pW) {
+  if (pW == 0) return row;
+  const int w = (int)(row % pW);
+  const int64_t t = row / pW;
+  const int h = (int)(t % pH);
+  const int64_t b = t / pH;
+  return (((b * (pH >> 1) + (h >> 1)) * (pW >> 1) + (w >> 1)) << 2) + ((h & 1) << 1) + (w & 1);
+}
+
 template <int G, int VPL, bool GELU>
 __global__ void __launch_bounds__(kLnThreads) ln_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ w,
                                                             const float* __restrict__ b, bf16* __restrict__ y,
                                                             float* __restrict__ mean, float* __restrict__ rstd,
-                                                            int64_t M, int C, float eps) {
+                                                            int64_t M, int C, float eps, int pH, int pW) {
   const int gl = threadIdx.x % G;                       // lane within the row group
   const int nv = C >> 2;
   constexpr int kRows = kLnThreads / G;                 // rows per CTA iteration
@@ -102,7 +114,7 @@ __global__ void __launch_bounds__(kLnThreads) ln_fwd_kernel(const bf16* __restri
     }
     const float rs = rsqrtf(group_sum<G>(q) * inv_c + eps);
     if (!live) continue;
-    uint2* yr = reinterpret_cast<uint2*>(y + row * C);
+    uint2* yr = reinterpret_cast<uint2*>(y + patch2_row(row, pH, pW) * C);
 #pragma unroll
     for (int j = 0; j < VPL; ++j) {
       const int v = gl + G * j;
@@ -127,7 +139,7 @@ __global__ void __launch_bounds__(kLnThreads) ln_bwd_kernel(const bf16* __restri
                                                             const float* __restrict__ mean,
                                                             const float* __restrict__ rstd, bf16* __restrict__ dx,
                                                             float* __restrict__ dw, float* __restrict__ db,
-                                                            int64_t M, int C) {
+                                                            int64_t M, int C, int pH, int pW) {
   extern __shared__ float red[];  // PGRAD: [2][C] accumulated with shared-memory atomics
   const int gl = threadIdx.x % G;
   const int nv = C >> 2;
@@ -152,7 +164,7 @@ __global__ void __launch_bounds__(kLnThreads) ln_bwd_kernel(const bf16* __restri
   for (int64_t row = (int64_t)blockIdx.x * kRows + threadIdx.x / G; row < rows_pad; row += (int64_t)gridDim.x * kRows) {
     const bool live = row < M;
     const uint2* xr = reinterpret_cast<const uint2*>(x + row * C);
-    const uint2* gr = reinterpret_cast<const uint2*>(dy + row * C);
+    const uint2* gr = reinterpret_cast<const uint2*>(dy + patch2_row(live ? row : 0, pH, pW) * C);
     const float mu = live ? mean[row] : 0.f, rs = live ? rstd[row] : 0.f;
     float xh[VPL][4], g[VPL][4];
     float s1 = 0.f, s2 = 0.f;
@@ -643,12 +655,12 @@ inline int ln_grid(int64_t M, int G) {
 
 template <bool GELU>
 int launch_ln_fwd(const bf16* x, const float* w, const float* b, bf16* y, float* mean, float* rstd, int64_t M, int C,
-                  float eps, cudaStream_t s) {
+                  float eps, cudaStream_t s, int pH = 0, int pW = 0) {
   int G, VPL;
   ln_shape(C / 4, G, VPL);
   const int g = ln_grid(M, G);
 #define B200AT_CASE(GG, V) \
-  if (G == GG && VPL == V) { ln_fwd_kernel<GG, V, GELU><<<g, kLnThreads, 0, s>>>(x, w, b, y, mean, rstd, M, C, eps); return (int)cudaGetLastError(); }
+  if (G == GG && VPL == V) { ln_fwd_kernel<GG, V, GELU><<<g, kLnThreads, 0, s>>>(x, w, b, y, mean, rstd, M, C, eps, pH, pW); return (int)cudaGetLastError(); }
   B200AT_LN_FOR_ALL(B200AT_CASE)
 #undef B200AT_CASE
   return (int)cudaErrorInvalidValue;
@@ -656,13 +668,13 @@ int launch_ln_fwd(const bf16* x, const float* w, const float* b, bf16* y, float*
 
 template <bool GELU, bool PGRAD>
 int launch_ln_bwd(const bf16* dy, const bf16* x, const float* w, const float* b, const float* mean, const float* rstd,
-                  bf16* dx, float* dw, float* db, int64_t M, int C, cudaStream_t s) {
+                  bf16* dx, float* dw, float* db, int64_t M, int C, cudaStream_t s, int pH = 0, int pW = 0) {
   int G, VPL;
   ln_shape(C / 4, G, VPL);
   const int g = ln_grid(M, G);
   const size_t sm = PGRAD ? sizeof(float) * 2 * C : 0;
 #define B200AT_CASE(GG, V) \
-  if (G == GG && VPL == V) { ln_bwd_kernel<GG, V, GELU, PGRAD><<<g, kLnThreads, sm, s>>>(dy, x, w, b, mean, rstd, dx, dw, db, M, C); return (int)cudaGetLastError(); }
+  if (G == GG && VPL == V) { ln_bwd_kernel<GG, V, GELU, PGRAD><<<g, kLnThreads, sm, s>>>(dy, x, w, b, mean, rstd, dx, dw, db, M, C, pH, pW); return (int)cudaGetLastError(); }
   B200AT_LN_FOR_ALL(B200AT_CASE)
 #undef B200AT_CASE
   return (int)cudaErrorInvalidValue;
@@ -729,6 +741,28 @@ int b200at_ln_bwd(const void* dy, const void* x, const float* w, const float* b,
   if (fuse_gelu) return pg ? B200AT_GO(true, true) : B200AT_GO(true, false);
   return pg ? B200AT_GO(false, true) : B200AT_GO(false, false);
 #undef B200AT_GO
+}
+
+int b200at_ln_fwd_patch2(const void* x, const float* w, const float* b, void* y, float* mean, float* rstd, int64_t B,
+                         int64_t H, int64_t W, int64_t C, float eps, void* stream) {
+  if (B <= 0) return 0;
+  if (C % 4 || C > 1536 || H % 2 || W % 2 || H <= 0 || W <= 0) return (int)cudaErrorInvalidValue;
+  return launch_ln_fwd<false>((const bf16*)x, w, b, (bf16*)y, mean, rstd, B * H * W, (int)C, eps, (cudaStream_t)stream,
+                              (int)H, (int)W);
+}
+
+int b200at_ln_bwd_patch2(const void* dy, const void* x, const float* w, const float* b, const float* mean,
+                         const float* rstd, void* dx, float* dw, float* db, int64_t B, int64_t H, int64_t W, int64_t C,
+                         void* stream) {
+  if (B <= 0) return 0;
+  if (C % 4 || C > 1536 || H % 2 || W % 2 || H <= 0 || W <= 0) return (int)cudaErrorInvalidValue;
+  if ((dw != nullptr) != (db != nullptr)) return (int)cudaErrorInvalidValue;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t M = B * H * W;
+  return dw ? launch_ln_bwd<false, true>((const bf16*)dy, (const bf16*)x, w, b, mean, rstd, (bf16*)dx, dw, db, M, (int)C,
+                                         s, (int)H, (int)W)
+            : launch_ln_bwd<false, false>((const bf16*)dy, (const bf16*)x, w, b, mean, rstd, (bf16*)dx, dw, db, M, (int)C,
+                                          s, (int)H, (int)W);
 }
 
 int b200at_bias_gelu_fwd(const void* z, const float* bias, void* h, int64_t M, int64_t N, void* stream) {

@@ -162,9 +162,11 @@ def _f32(t):
 # which pwconv GEMMs run on the hand-written tcgen05 kernel (the rest: cuBLAS + the elementwise kernels).
 #   'residual'  pwconv2 forward with layer-scale + bias + residual fused in the epilogue
 #   'dgrad1'    d(t2) = dz W1                     (no epilogue; same speed as cuBLAS, one library call less)
-#   'gelu'      pwconv1 forward with bias + GELU fused (+ pre-activation saved)
-#   'gelu_grad' dz = (dout W2g) * GELU'(z)        fused
-TCGEN05 = set(filter(None, os.environ.get('B200AT_TCGEN05', 'residual,dgrad1').split(',')))
+#   'fc1'       pwconv1 forward, plain (bias rides in the GELU kernel): 3-9 % faster than cuBLAS at these shapes
+#   'dgrad2'    da = dout (gamma W2)              (plain; same shapes as 'fc1')
+#   'gelu'      pwconv1 forward with bias + GELU fused (+ pre-activation saved)   [slower: epilogue-bound]
+#   'gelu_grad' dz = (dout W2g) * GELU'(z)        fused                           [slower: epilogue-bound]
+TCGEN05 = set(filter(None, os.environ.get('B200AT_TCGEN05', 'residual,dgrad1,fc1,dgrad2').split(',')))
 
 _WCACHE = {}
 _PCACHE = {}
@@ -193,6 +195,20 @@ def invalidate_derived(keep_tags=('host3',)):
     for k in [k for k in _PCACHE if k[1] not in keep_tags]:
         del _PCACHE[k]
     _WCACHE.clear()
+
+
+# Fused optimisers (torch._fused_adamw_ & co.) update the parameters in place WITHOUT moving their version counters, so
+# the version check above cannot see an optimiser step: every optimiser's step() therefore drops the cache through
+# torch's global post-step hook.  (copy_ / add_ / load_state_dict / foreach optimisers do bump the counters.)
+def _after_optimizer_step(*_args, **_kw):
+    invalidate_derived()
+
+
+try:
+    from torch.optim.optimizer import register_optimizer_step_post_hook as _register_post_hook
+    _OPT_HOOK = _register_post_hook(_after_optimizer_step)
+except ImportError:                                          # very old torch: callers must invalidate themselves
+    _OPT_HOOK = None
 
 
 def _taps(dw_w):
@@ -270,7 +286,10 @@ class _ConvNeXtBlock(Function):
             a = _gemm(t2.view(M, C), P['w1b'], _abi.EPI_BIAS_GELU, bias=b1f, c2=z)
             zb = None
         else:
-            z = t2.view(M, C) @ P['w1b'].t()                            # cuBLAS; bias added inside the kernels
+            if 'fc1' in TCGEN05:
+                z = _gemm(t2.view(M, C), P['w1b'])                      # bias added inside the GELU kernels
+            else:
+                z = t2.view(M, C) @ P['w1b'].t()                        # cuBLAS
             a = torch.empty_like(z)
             _abi.bias_gelu_fwd(z, b1f, a)
             zb = b1f
@@ -303,7 +322,7 @@ class _ConvNeXtBlock(Function):
             if pg:
                 _abi.colsum_bf16(dz, db1)
         else:
-            da = d2 @ P['w2g']                                          # [M,4C]  (layer scale already folded)
+            da = _gemm(d2, P['w2gt']) if 'dgrad2' in TCGEN05 else d2 @ P['w2g']   # [M,4C]  (layer scale folded)
             dz = torch.empty_like(da)
             zero = ctx.zb if ctx.zb is not None else torch.zeros(4 * C, device=dout.device, dtype=torch.float32)
             _abi.bias_gelu_bwd(da, z, zero, dz, db1)                    # pwconv1 bias gradient rides along
@@ -399,9 +418,60 @@ def stem_layer(x, cw, cb, lw, lb, stride, first, mean=None, std=None):
     return layer_norm(y, lw, lb, 1e-6, gelu=True)
 
 
+class _Downsample(Function):
+    """LayerNorm -> Conv2d(kernel 2, stride 2) (models/convnext.py:79-82) as one autograd node: the LN kernel writes
+    its result in the 2x2-patch layout, so the convolution is the tcgen05 GEMM [B*H/2*W/2, 4C] x [Cout, 4C]^T with
+    the bias in its epilogue, and the input gradient is the GEMM with the transposed weight followed by the LN
+    backward reading the patch layout.  No cuDNN, no separate bias-add / layout kernels."""
+
+    @staticmethod
+    def forward(ctx, x, ln_w, ln_b, cw, cb):
+        x = x.contiguous()
+        B, H, W, C = x.shape
+        Co = cw.shape[0]
+        M = B * H * W
+        lnw, lnb = _f32(ln_w), _f32(ln_b)
+        wk = _derived(cw, 'patch2', lambda w: w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).to(BF16).contiguous())
+        t = torch.empty(M // 4, 4 * C, device=x.device, dtype=BF16)
+        mean = torch.empty(M, device=x.device, dtype=torch.float32)
+        rstd = torch.empty_like(mean)
+        _abi.ln_fwd_patch2(x, lnw, lnb, t, mean, rstd, 1e-6)
+        y = _gemm(t, wk, _abi.EPI_BIAS, bias=_f32(cb))
+        ctx.param_grads = not _INPUT_GRAD_ONLY[0]
+        ctx.save_for_backward(x, mean, rstd, lnw, lnb, cw, t if ctx.param_grads else None)
+        return y.view(B, H // 2, W // 2, Co)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, mean, rstd, lnw, lnb, cw, t = ctx.saved_tensors
+        B, H, W, C = x.shape
+        Co = cw.shape[0]
+        dy2 = dy.contiguous().view(-1, Co)
+        wkt = _derived(cw, 'patch2_t', lambda w: w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).to(BF16).t().contiguous())
+        dt = _gemm(dy2, wkt)                                            # [M/4, 4C], patch layout
+        pg = _wants(ctx, 1, 2, 3, 4)
+        dlw = torch.zeros_like(lnw) if pg else None
+        dlb = torch.zeros_like(lnb) if pg else None
+        dx = torch.empty_like(x)
+        _abi.ln_bwd_patch2(dt, x, lnw, lnb, mean, rstd, dx, dlw, dlb)
+        if not pg:
+            return dx, None, None, None, None
+        dwk = (dy2.t() @ t).float()                                     # [Co, (kh, kw, Cin)]
+        dcw = dwk.view(Co, 2, 2, C).permute(0, 3, 1, 2)
+        dcb = torch.zeros(Co, device=dy.device, dtype=torch.float32)
+        _abi.colsum_bf16(dy2, dcb)
+        return dx, dlw, dlb, dcw, dcb
+
+
+DOWNSAMPLE_GEMM = os.environ.get('B200AT_DOWNSAMPLE', 'gemm') == 'gemm'
+
+
 def downsample(x, ln_w, ln_b, cw, cb):
-    """LN over C (kernel) -> conv2x2 s2 (cuDNN).  NHWC bf16 in/out."""
-    y = layer_norm(x, ln_w, ln_b, 1e-6).permute(0, 3, 1, 2)
+    """LN over C -> conv2x2 s2.  NHWC bf16 in/out."""
+    B, H, W, C = x.shape
+    if DOWNSAMPLE_GEMM and H % 2 == 0 and W % 2 == 0 and cw.shape[0] % 16 == 0 and C % 8 == 0:
+        return _Downsample.apply(x, ln_w, ln_b, cw, cb)
+    y = layer_norm(x, ln_w, ln_b, 1e-6).permute(0, 3, 1, 2)            # odd sizes: library convolution
     y = F.conv2d(y, _cast(cw), _cast(cb), stride=2)
     return y.permute(0, 2, 3, 1)
 

@@ -17,7 +17,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import _abi
+from . import _abi, ops
 from .attack import apgd_train
 from .fgsm import fgsm_train
 
@@ -86,7 +86,6 @@ class GraphedAttack:
         self.graphs = {}
 
     def __call__(self, model, x, y):
-        from . import ops
         key = (tuple(x.shape), x.dtype, tuple(x.stride()), tuple(y.shape), y.dtype, x.device.index, id(model))
         hit = self.graphs.get(key)
         if hit is None:
@@ -183,6 +182,7 @@ class AdvTrainStep:
             loss = self.loss(output, target)
         loss.backward()                                                         # DDP all-reduce overlaps here
         self.optimizer.step()
+        ops.invalidate_derived()          # fused optimisers do not move the parameters' version counters (see ops.py)
         if self.ema is not None:
             self.ema.update()
         return loss.detach()

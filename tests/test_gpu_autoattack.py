@@ -21,9 +21,15 @@ def test_dlr_targeted_kernel_vs_reference_formula(cuda_dev, dtype):
     """-(z_y - z_t) / (z_(1) - (z_(3) + z_(4)) / 2 + 1e-12) and its gradient (autopgd_train_clean.py:106-111)"""
     import revisiting_at_b200  # noqa: F401
     from revisiting_at_b200 import _abi
-    B, C = 37, 1000
     g = torch.Generator().manual_seed(12)
-    z = (torch.randn(B, C, generator=g) * 3).to(cuda_dev).to(dtype)
+    if dtype == torch.float32:
+        B, C = 37, 1000
+        z = (torch.randn(B, C, generator=g) * 3).to(cuda_dev)
+    else:
+        # bf16 logits: distinct, exactly representable values (k/8, k < 200), so that the order statistics have no
+        # ties -- with ties the (sub)gradient depends on the sort's arbitrary tie order, in the reference too
+        B, C = 37, 200
+        z = torch.stack([torch.randperm(C, generator=g) for _ in range(B)]).float().div(8).sub(12).to(cuda_dev).to(dtype)
     y = torch.randint(0, C, (B,), generator=g).to(cuda_dev)
     y[:10] = z[:10].float().argmax(1)
     yt = torch.randint(0, C, (B,), generator=g).to(cuda_dev)
@@ -129,3 +135,18 @@ def test_evaluation_on_convnext_engine(cuda_dev):
         pred = m(x_adv).float().max(1)[1]
     assert bool((pred[changed] != y[changed]).all())
     assert adv.results['clean'] == 1.0 and adv.results['apgd-t'] <= adv.results['apgd-ce'] <= 1.0
+
+
+def test_l1_projection_export(cuda_dev):
+    """`L1_projection` (exported next to apgd_train, autopgd_train_clean.py:24-91) vs its CPU restatement"""
+    import autopgd_train_clean as product
+    from oracle.apgd_oracle import l1_projection_rows
+    g = torch.Generator().manual_seed(3)
+    x = torch.rand(5, 3, 12, 12, generator=g)
+    d = torch.randn(5, 3, 12, 12, generator=g) * 0.3
+    d[0] *= 0.001                                    # already inside the ball: only the box matters
+    want = l1_projection_rows(x, d, 4.0)
+    got = product.L1_projection(x.to(cuda_dev), d.to(cuda_dev), 4.0).cpu()
+    assert (got - want).abs().max() <= 2e-6, (got - want).abs().max()
+    z = x + d + got
+    assert (z - x).abs().flatten(1).sum(1).max() <= 4.0 * (1 + 1e-5) and z.min() >= -1e-6 and z.max() <= 1 + 1e-6

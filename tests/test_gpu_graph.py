@@ -54,3 +54,17 @@ def test_train_step_with_graphed_attack_matches_eager(cuda_dev):
     losses = [step(x, y).item() for x, y in batches]
     assert checked == [True] * 6, checked
     assert len(graphed.graphs) == 1 and all(l == l and l < 20 for l in losses), losses
+    # the forward really runs on the UPDATED parameters (fused AdamW does not move version counters: a stale
+    # kernel-side weight copy would show up here): engine logits == fp32 oracle logits on the trained state
+    from oracle import convnext_oracle as co
+    o = co.build('convnext_tiny', normalize=True, seed=0)
+    o.load_state_dict({k[len('base_model.'):]: v.detach().cpu().float().contiguous()
+                       for k, v in step.raw.state_dict().items()})
+    o0 = co.build('convnext_tiny', normalize=True, seed=0)
+    x = batches[0][0][:4]
+    step.raw.base_model.eval()
+    with torch.no_grad():
+        got = step.raw.base_model(x).float().cpu()
+        want, stale = o.eval()(x.cpu()), o0.eval()(x.cpu())
+    assert (got - want).abs().max() <= 5e-2, (got - want).abs().max()
+    assert (want - stale).abs().max() > 0.2            # the six steps moved the logits far beyond that tolerance

@@ -178,6 +178,38 @@ def test_block_function_fwd_bwd(ops, cuda_dev, shape, tc, monkeypatch):
     assert torch.equal(dx2, got[0])
 
 
+@pytest.mark.parametrize('shape,Co', [((2, 56, 56, 96), 192), ((3, 14, 14, 384), 768), ((1, 6, 10, 128), 256)])
+def test_downsample_gemm_matches_reference(ops, cuda_dev, shape, Co):
+    """LayerNorm -> Conv2d(k=2, s=2) (models/convnext.py:79-82) through the patch-layout LN kernel + tcgen05 GEMM"""
+    B, H, W, C = shape
+    g = torch.Generator(device='cuda').manual_seed(H + C)
+    rnd = lambda *s, k=1.0: (torch.randn(*s, generator=g, device=cuda_dev) * k)
+    x = rnd(B, H, W, C).to(BF16)
+    P = dict(ln_w=1 + rnd(C, k=0.1), ln_b=rnd(C, k=0.1), cw=rnd(Co, C, 2, 2, k=0.05), cb=rnd(Co, k=0.1))
+    P = {k: v.requires_grad_() for k, v in P.items()}
+    names = list(P)
+    dout = rnd(B, H // 2, W // 2, Co).to(BF16)
+    xr = x.float().requires_grad_()
+    t = F.layer_norm(xr, (C,), P['ln_w'], P['ln_b'], 1e-6)
+    ref = F.conv2d(t.permute(0, 3, 1, 2), P['cw'], P['cb'], stride=2).permute(0, 2, 3, 1)
+    rg = torch.autograd.grad(ref, [xr] + [P[n] for n in names], dout.float())
+    xt = x.clone().requires_grad_()
+    out = ops.downsample(xt, *[P[n] for n in names])
+    assert out.shape == ref.shape
+    _close(out, ref, atol=4e-2)
+    got = torch.autograd.grad(out, [xt] + [P[n] for n in names], dout)
+    _close(got[0], rg[0], atol=4e-2, rtol=3e-2)
+    for n, a, r in zip(names, got[1:], rg[1:]):
+        assert a.shape == r.shape, n
+        cs = F.cosine_similarity(a.flatten().float(), r.flatten(), dim=0).item()
+        assert cs > 0.995, (n, cs)
+        assert abs(a.float().norm().item() / r.norm().item() - 1) < 0.03, n
+    with ops.input_grad_only():
+        out2 = ops.downsample(xt, *[P[n] for n in names])
+    (dx2,) = torch.autograd.grad(out2, [xt], dout)
+    assert torch.equal(dx2, got[0])
+
+
 def test_convnext_engine_matches_oracle(cuda_dev):
     """ConvNeXt-T-CvSt, same seed-0 weights: bf16 engine on the GPU vs fp32 oracle on the CPU.
     Tolerances: logits 5e-2 absolute (|logit| ~ 1, ~40 bf16 layers); input gradient cosine >= 0.98."""

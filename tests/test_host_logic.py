@@ -100,3 +100,24 @@ def test_fgsm_host_path_bit_exact(vec):
                     ('rs_skip', dict(use_rs=True, alpha=1.0, noise_level=0.5, skip_projection=True))):
         out = fgsm.run_fgsm(HostBackend(vec), model, x, y, eps, noise=_t(g['noise_' + tag]), **kw)
         assert same(out, _t(g['out_' + tag])), tag
+
+
+def test_derived_parameter_copies_follow_a_fused_optimizer_step():
+    """torch's fused optimisers update parameters in place without moving `_version`; the kernel-side copies
+    (bf16 / transposed / folded weights) must still be rebuilt after `optimizer.step()`."""
+    from revisiting_at_b200 import ops
+    p = torch.nn.Parameter(torch.randn(8, 8))
+    first = ops._derived(p, 'unit_test_copy', lambda w: w.clone())
+    assert ops._derived(p, 'unit_test_copy', lambda w: w.clone()) is first          # cached
+    try:
+        opt = torch.optim.AdamW([p], lr=0.1, fused=True)
+    except RuntimeError:
+        pytest.skip('no fused optimiser on this device')
+    p.grad = torch.ones_like(p)
+    v = p._version
+    opt.step()
+    again = ops._derived(p, 'unit_test_copy', lambda w: w.clone())
+    assert torch.equal(again, p.detach()) and not torch.equal(again, first), (v, p._version)
+    with torch.no_grad():
+        p.mul_(2.)                                                                    # plain in-place ops: version check
+    assert torch.equal(ops._derived(p, 'unit_test_copy', lambda w: w.clone()), p.detach())
