@@ -16,7 +16,12 @@ B, N, H, D = 256, 197, 6, 384
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
 
+ONCE = '--once' in sys.argv          # one launch per kernel (for ncu)
+
+
 def timeit(fn, reps=10):
+    if ONCE:
+        fn(); torch.cuda.synchronize(); return float('nan')
     fn(); torch.cuda.synchronize()
     ts = []
     for _ in range(reps):
@@ -40,6 +45,8 @@ t = timeit(lambda: _abi.attn_fwd(qkv, o, lse, H, 0.125))
 print(f'{"attn_fwd (mma.sync, hand-written)":44s} {t:8.1f} {fl_f / t / 1e6:8.1f}')
 t = timeit(lambda: _abi.attn_bwd(qkv, o, d_o, lse, dqkv, H, 0.125))
 print(f'{"attn_bwd (mma.sync, hand-written)":44s} {t:8.1f} {2.5 * fl_f / t / 1e6:8.1f}')
+if ONCE:
+    sys.exit(0)
 q, k, v = (z.contiguous().requires_grad_() for z in qkv.view(B, N, 3, H, 64).permute(2, 0, 3, 1, 4).unbind(0))
 t = timeit(lambda: F.scaled_dot_product_attention(q, k, v))
 print(f'{"torch SDPA fwd (library, pre-permuted q/k/v)":44s} {t:8.1f} {fl_f / t / 1e6:8.1f}')

@@ -158,13 +158,14 @@ attn_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ o, float* __res
   for (int jb = 0; jb < nkb; ++jb) {
     float s[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
     mma_rowmajor_b(s, qa, Ks, jb * 16, lane);
+    if (jb == nkb - 1) {                                          // only the last block has columns beyond the sequence
 #pragma unroll
-    for (int nt = 0; nt < 2; ++nt)
+      for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int col = jb * 16 + nt * 8 + 2 * t + (e & 1);
-        s[nt][e] = col < N ? s[nt][e] * c : -INFINITY;
-      }
+        for (int e = 0; e < 4; ++e)
+          if (jb * 16 + nt * 8 + 2 * t + (e & 1) >= N) s[nt][e] = -INFINITY;
+    }
+    // running maxima are kept on the raw scores (c > 0 preserves the order); the scale enters through one FFMA
     float x0 = fmaxf(fmaxf(s[0][0], s[0][1]), fmaxf(s[1][0], s[1][1]));
     float x1 = fmaxf(fmaxf(s[0][2], s[0][3]), fmaxf(s[1][2], s[1][3]));
     x0 = fmaxf(x0, __shfl_xor_sync(0xffffffffu, x0, 1));
@@ -172,13 +173,14 @@ attn_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ o, float* __res
     x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, 1));
     x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, 2));
     const float n0 = fmaxf(m0, x0), n1 = fmaxf(m1, x1);          // finite from block 0 on (column 0 is always live)
-    const float a0 = ex2(m0 - n0), a1 = ex2(m1 - n1);
+    const float a0 = ex2((m0 - n0) * c), a1 = ex2((m1 - n1) * c);
     m0 = n0; m1 = n1;
+    const float o0 = -n0 * c, o1 = -n1 * c;
     float p[2][4];
 #pragma unroll
     for (int nt = 0; nt < 2; ++nt) {
-      p[nt][0] = ex2(s[nt][0] - n0); p[nt][1] = ex2(s[nt][1] - n0);
-      p[nt][2] = ex2(s[nt][2] - n1); p[nt][3] = ex2(s[nt][3] - n1);
+      p[nt][0] = ex2(fmaf(s[nt][0], c, o0)); p[nt][1] = ex2(fmaf(s[nt][1], c, o0));
+      p[nt][2] = ex2(fmaf(s[nt][2], c, o1)); p[nt][3] = ex2(fmaf(s[nt][3], c, o1));
     }
     l0 = l0 * a0 + (p[0][0] + p[0][1] + p[1][0] + p[1][1]);
     l1 = l1 * a1 + (p[0][2] + p[0][3] + p[1][2] + p[1][3]);
@@ -195,8 +197,8 @@ attn_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ o, float* __res
   store_tile(ob, (int64_t)H * kD, r0, g, t, N, acc, 1.f / l0, 1.f / l1);
   if (t == 0) {
     float* lb = lse + ((int64_t)b * H + h) * N;
-    if (r0 + g < N) lb[r0 + g] = m0 + log2f(l0);
-    if (r0 + g + 8 < N) lb[r0 + g + 8] = m1 + log2f(l1);
+    if (r0 + g < N) lb[r0 + g] = m0 * c + log2f(l0);
+    if (r0 + g + 8 < N) lb[r0 + g + 8] = m1 * c + log2f(l1);
   }
 }
 
@@ -274,9 +276,9 @@ attn_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o, const 
       for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const int col = jb * 16 + nt * 8 + 2 * t + (e & 1);
           const float L = (e < 2) ? L0 : L1, D = (e < 2) ? D0 : D1;
-          const float p = col < N ? ex2(s[nt][e] * c - L) : 0.f;
+          float p = ex2(fmaf(s[nt][e], c, -L));
+          if (jb == nkb - 1 && jb * 16 + nt * 8 + 2 * t + (e & 1) >= N) p = 0.f;   // columns beyond the sequence
           ds[nt][e] = p * (dp[nt][e] - D) * scale;
         }
       const uint32_t da[4] = {pack2(ds[0][0], ds[0][1]), pack2(ds[0][2], ds[0][3]), pack2(ds[1][0], ds[1][1]),
@@ -306,7 +308,8 @@ attn_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o, const 
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int qi = ib * 16 + nt * 8 + 2 * t + (e & 1);
-          const float p = qi < N ? ex2(st[nt][e] * c - Ls[qi]) : 0.f;
+          // queries beyond the sequence have dO = 0 and D = 0 (zero-filled tiles): their finite p contributes nothing
+          const float p = ex2(fmaf(st[nt][e], c, -Ls[qi]));
           pt[nt][e] = p;
           dst[nt][e] = p * (dpt[nt][e] - Ds[qi]) * scale;
         }

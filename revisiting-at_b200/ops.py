@@ -168,24 +168,47 @@ def _f32(t):
 #   'gelu_grad' dz = (dout W2g) * GELU'(z)        fused                           [slower: epilogue-bound]
 TCGEN05 = set(filter(None, os.environ.get('B200AT_TCGEN05', 'residual,dgrad1,fc1,dgrad2').split(',')))
 
-_WCACHE = {}
-_PCACHE = {}
+_PCACHE = {}     # (ids of the source parameters, tag) -> (stamp, value, weakrefs of the parameters)
+
+
+def _stamp(params):
+    return tuple((p._version, p.data_ptr()) for p in params)
+
+
+def _derived_multi(params, tag, fn):
+    """Kernel-side copy derived from one or several parameters (cast / transposed / flipped / folded), rebuilt only
+    when one of them changes; shared by the 4 forwards + 3 backwards of a step."""
+    key = (tuple(id(p) for p in params), tag)
+    hit = _PCACHE.get(key)
+    if hit is not None and hit[0] == _stamp(params) and all(r() is p for r, p in zip(hit[2], params)):
+        return hit[1]                                        # same live tensor objects, same storage, not written since
+    with torch.no_grad():
+        val = fn(*[p.detach() for p in params])
+    if len(_PCACHE) > 8192:                                  # models that came and went (tests)
+        for k in [k for k, v in _PCACHE.items() if any(r() is None for r in v[2])]:
+            del _PCACHE[k]
+    _PCACHE[key] = (_stamp(params), val, tuple(weakref.ref(p) for p in params))
+    return val
 
 
 def _derived(param, tag, fn):
-    """Kernel-side copy of a parameter (cast / transposed / flipped), rebuilt only when the parameter changes
-    (its version counter moves once per optimiser step); shared by the 4 forwards + 3 backwards of a step."""
-    key = (id(param), tag)
-    hit = _PCACHE.get(key)
-    if hit is not None and hit[2]() is param and hit[0] == (param._version, param.data_ptr()):
-        return hit[1]                                        # same live tensor object, same storage, not written since
-    with torch.no_grad():
-        val = fn(param.detach())
-    if len(_PCACHE) > 4096:                                  # models that came and went (tests)
-        for k in [k for k, v in _PCACHE.items() if v[2]() is None]:
-            del _PCACHE[k]
-    _PCACHE[key] = ((param._version, param.data_ptr()), val, weakref.ref(param))
-    return val
+    return _derived_multi((param,), tag, fn)
+
+
+def snapshot_derived():
+    """The current cache entries (used right after a CUDA-graph capture: they are the graph's own buffers)."""
+    return dict(_PCACHE)
+
+
+def install_derived(snapshot):
+    """Declare the snapshot's values current for the parameters as they are now.  Only valid when something has
+    just recomputed them in place from the current parameters -- i.e. right after replaying the CUDA graph whose
+    capture produced them; the training forward that follows then reuses the graph's weight copies instead of
+    deriving its own."""
+    for key, (_, val, refs) in snapshot.items():
+        params = [r() for r in refs]
+        if all(p is not None for p in params):
+            _PCACHE[key] = (_stamp(params), val, refs)
 
 
 def invalidate_derived(keep_tags=('host3',)):
@@ -194,7 +217,6 @@ def invalidate_derived(keep_tags=('host3',)):
     INSIDE the graph and every replay re-derives them from the (in-place updated) fp32 master parameters."""
     for k in [k for k in _PCACHE if k[1] not in keep_tags]:
         del _PCACHE[k]
-    _WCACHE.clear()
 
 
 # Fused optimisers (torch._fused_adamw_ & co.) update the parameters in place WITHOUT moving their version counters, so
@@ -226,26 +248,16 @@ def _bf16(p):
 
 
 def _prepared(w1, w2, b2, gamma):
-    """bf16 / transposed / layer-scale-folded copies of the block's MLP weights, rebuilt only when a
-    parameter changes (once per optimiser step; shared by the 4 forwards + 3 backwards of a step)."""
-    key = (id(w1), id(w2), id(b2), id(gamma))
-    ver = (w1._version, w2._version, b2._version, gamma._version, w1.data_ptr(), w2.data_ptr())
-    hit = _WCACHE.get(key)
-    if hit is not None and hit[0] == ver and hit[2]() is w1 and hit[3]() is w2:
-        return hit[1]
-    with torch.no_grad():
-        gf = gamma.detach().float()
-        w1b = w1.detach().to(BF16).contiguous()                         # [4C, C]   pwconv1: t2 @ w1b^T
+    """bf16 / transposed / layer-scale-folded copies of the block's MLP weights."""
+    def build(w1, w2, b2, gamma):
+        gf = gamma.float()
+        w1b = w1.to(BF16).contiguous()                                  # [4C, C]   pwconv1: t2 @ w1b^T
         w1t = w1b.t().contiguous()                                      # [C, 4C]   dt2 = dz @ w1b  == dz @ w1t^T
-        w2g = (gf[:, None] * w2.detach().float()).to(BF16).contiguous()  # [C, 4C]   gamma folded: a @ w2g^T
+        w2g = (gf[:, None] * w2.float()).to(BF16).contiguous()          # [C, 4C]   gamma folded: a @ w2g^T
         w2gt = w2g.t().contiguous()                                     # [4C, C]   da = dout @ w2g == dout @ w2gt^T
-        b2g = (gf * b2.detach().float()).contiguous()
-        prep = dict(w1b=w1b, w1t=w1t, w2g=w2g, w2gt=w2gt, b2g=b2g, gf=gf.contiguous())
-    if len(_WCACHE) > 1024:
-        for k in [k for k, v in _WCACHE.items() if v[2]() is None]:
-            del _WCACHE[k]
-    _WCACHE[key] = (ver, prep, weakref.ref(w1), weakref.ref(w2))
-    return prep
+        b2g = (gf * b2.float()).contiguous()
+        return dict(w1b=w1b, w1t=w1t, w2g=w2g, w2gt=w2gt, b2g=b2g, gf=gf.contiguous())
+    return _derived_multi((w1, w2, b2, gamma), 'convnext_mlp', build)
 
 
 def _gemm(a, w, epi=_abi.EPI_NONE, bias=None, aux=None, c2=None):
@@ -492,19 +504,14 @@ ATTENTION_KERNEL = os.environ.get('B200AT_ATTN', 'kernel')     # 'sdpa' = librar
 
 
 def _vit_prepared(wqkv, wproj, w1, w2):
-    key = (id(wqkv), id(wproj), id(w1), id(w2))
-    ver = tuple(w._version for w in (wqkv, wproj, w1, w2)) + (wqkv.data_ptr(), w2.data_ptr())
-    hit = _WCACHE.get(key)
-    if hit is not None and hit[0] == ver and hit[2]() is wqkv and hit[3]() is w2:
-        return hit[1]
-    with torch.no_grad():
+    def build(*ws):
         prep = {}
-        for name, w in (('qkv', wqkv), ('proj', wproj), ('w1', w1), ('w2', w2)):
-            wb = w.detach().to(BF16).contiguous()
+        for name, w in zip(('qkv', 'proj', 'w1', 'w2'), ws):
+            wb = w.to(BF16).contiguous()
             prep[name] = wb                                   # [out, in]: y = x @ wb^T
             prep[name + '_t'] = wb.t().contiguous()           # [in, out]: dx = dy @ wb == dy @ (wb^T)^T
-    _WCACHE[key] = (ver, prep, weakref.ref(wqkv), weakref.ref(w2))
-    return prep
+        return prep
+    return _derived_multi((wqkv, wproj, w1, w2), 'vit_block', build)
 
 
 class _Attention(Function):

@@ -99,13 +99,40 @@ class GraphedAttack:
             n0 = _abi.LAUNCHES['count']
             with torch.cuda.graph(graph, capture_error_mode='thread_local'):
                 out = self.perturb(model, sx, sy)
-            hit = self.graphs[key] = (graph, sx, sy, out, _abi.LAUNCHES['count'] - n0)
-        graph, sx, sy, out, n_kernels = hit
+            hit = self.graphs[key] = (graph, sx, sy, out, _abi.LAUNCHES['count'] - n0, ops.snapshot_derived())
+        graph, sx, sy, out, n_kernels, derived = hit
         sx.copy_(x, non_blocking=True)
         sy.copy_(y, non_blocking=True)
         graph.replay()
+        ops.install_derived(derived)                      # the replay just re-derived these from the current parameters
         _abi.LAUNCHES['count'] += n_kernels               # kernels of this library inside the replayed graph
         return out
+
+
+class DevicePrefetcher:
+    """Pinned host batches -> device, one batch ahead on a copy stream: the device side of the reference's input path
+    (`DataLoader(pin_memory=True)` workers + `images.cuda(non_blocking=True)`, main.py:961-966), so that the 77 MB
+    image copy of step i+1 runs under the compute of step i instead of in front of it."""
+
+    def __init__(self, device):
+        self.device = device
+        self.stream = torch.cuda.Stream(device)
+        self.queue = []
+
+    def submit(self, *host_tensors):
+        with torch.cuda.stream(self.stream):
+            dev = tuple(t.to(self.device, non_blocking=True) for t in host_tensors)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        self.queue.append((dev, ev))
+
+    def get(self):
+        dev, ev = self.queue.pop(0)
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(ev)
+        for t in dev:
+            t.record_stream(cur)                       # allocated on the copy stream, consumed on the compute stream
+        return dev
 
 
 class DeviceEma:
