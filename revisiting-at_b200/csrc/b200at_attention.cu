@@ -11,11 +11,13 @@
 // Forward: online softmax over 16-key blocks, P stays in registers (accumulator layout == A-fragment
 // layout), saves the per-row log2-sum-exp.  Backward: pass A (warp = 16 query rows) recomputes P and
 // produces dQ; pass B (warp = 16 key rows) recomputes P^T and produces dK, dV -- no atomics, deterministic.
-// Operands whose contraction index is not contiguous in the row-major token layout (V in P V, K in dS K,
-// dO in P^T dO, Q in dS^T Q) are staged transposed in shared memory by the loading phase.
+// Operands whose contraction index is the token index (V in P V, K in dS K, dO in P^T dO, Q in dS^T Q) are read from
+// the row-major shared tiles through ldmatrix.trans.  The backward runs as two kernels (dQ; dK+dV), 7 warps per CTA
+// and 60 KB of shared memory each, so 21 warps share an SM (B200AT_ATTN_BWD=1 selects the older single-kernel form).
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/b200at_model.h"
 
@@ -91,6 +93,24 @@ __device__ __forceinline__ float ex2(float x) {       // 2^x, MUFU.EX2; ex2(-inf
   return y;
 }
 
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t* r, const bf16* p) {
+  const uint32_t addr = (uint32_t)__cvta_generic_to_shared(p);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+// acc[8][4] (16 x 64) += A(16 x 16 tokens, one fragment) . T[c0 .. c0+15][0..63]   (T row-major [token][channel])
+__device__ __forceinline__ void mma_tokens_b(float (*acc)[4], const uint32_t* a, const bf16* tile, int c0, int lane) {
+#pragma unroll
+  for (int dp = 0; dp < 4; ++dp) {
+    // stored 8x8 blocks (tokens x channels): (c0, 16dp), (c0+8, 16dp), (c0, 16dp+8), (c0+8, 16dp+8); transposed on load,
+    // thread (g, t) gets (T[.. + 2t][.. + g], T[.. + 2t + 1][.. + g]) = the B-fragment word with k = token, n = channel
+    const bf16* row = tile + (c0 + ((lane >> 3) & 1) * 8 + (lane & 7)) * kRS + dp * 16 + (lane >> 4) * 8;
+    uint32_t b[4];
+    ldmatrix_x4_trans(b, row);
+    mma16816(acc[2 * dp], a, b[0], b[1]);
+    mma16816(acc[2 * dp + 1], a, b[2], b[3]);
+  }
+}
 // 16-byte chunk `ch` (8 bf16) of token row `tok` of one head: zero beyond the sequence
 __device__ __forceinline__ uint4 load_chunk(const bf16* base, int64_t row_stride, int tok, int ch, int N) {
   uint4 v = make_uint4(0u, 0u, 0u, 0u);
@@ -122,20 +142,18 @@ __device__ __forceinline__ void store_tile(bf16* out, int64_t row_stride, int r0
 __global__ void __launch_bounds__(32 * kMaxBlocks, 2)
 attn_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ o, float* __restrict__ lse, int N, int H, float c) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int nkb = (N + 15) >> 4, npad = nkb << 4, ts = npad + 8;
+  const int nkb = (N + 15) >> 4, npad = nkb << 4;
   bf16* Ks = reinterpret_cast<bf16*>(smem_raw);          // [npad][kRS]
-  bf16* Vt = Ks + npad * kRS;                            // [64][ts]
+  bf16* Vs = Ks + npad * kRS;                            // [npad][kRS]
   const int b = blockIdx.x / H, h = blockIdx.x % H;
   const int64_t rs = 3 * (int64_t)H * kD;                // qkv row stride (elements)
   const bf16* qb = qkv + (int64_t)b * N * rs + h * kD;
   const bf16* kb = qb + H * kD;
   const bf16* vb = kb + H * kD;
-  // consecutive lanes take consecutive tokens of one 16-byte chunk: the 2-byte transposed stores of a warp fall
-  // into 16 consecutive words of one row and the 16-byte row-major stores into distinct bank groups
   for (int idx = threadIdx.x; idx < npad * 8; idx += blockDim.x) {
-    const int tok = idx % npad, ch = idx / npad;
+    const int tok = idx >> 3, ch = idx & 7;                // 8 lanes = one 128-byte token row: coalesced
     store_rowmajor(Ks, tok, ch, load_chunk(kb, rs, tok, ch, N));
-    store_transposed(Vt, ts, tok, ch, load_chunk(vb, rs, tok, ch, N));
+    store_rowmajor(Vs, tok, ch, load_chunk(vb, rs, tok, ch, N));
   }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int r0 = warp * 16;
@@ -189,7 +207,7 @@ attn_fwd_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ o, float* __res
       for (int dt = 0; dt < 8; ++dt) { acc[dt][0] *= a0; acc[dt][1] *= a0; acc[dt][2] *= a1; acc[dt][3] *= a1; }
     }
     const uint32_t pa[4] = {pack2(p[0][0], p[0][1]), pack2(p[0][2], p[0][3]), pack2(p[1][0], p[1][1]), pack2(p[1][2], p[1][3])};
-    mma_transposed_b(acc, pa, Vt, ts, jb * 16, lane);
+    mma_tokens_b(acc, pa, Vs, jb * 16, lane);                     // V row-major, transposed by ldmatrix
   }
   l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
   l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
@@ -325,9 +343,202 @@ attn_bwd_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o, const 
   }
 }
 
+
+// ------------------------------------------------------------------- backward, split form (default)
+// Two kernels instead of one, each with only row-major tiles in shared memory (60 KB) and 7 warps per CTA (two
+// CTAs per (image, head)), so three CTAs = 21 warps share an SM instead of one CTA of 13: the single-kernel form is
+// latency-bound at 28 % issue utilisation (profiles/r01_attention_ncu_v2.txt).  Operands whose contraction index is
+// the token index (K in dS K, dO in P^T dO, Q in dS^T Q) come straight from the row-major tiles through
+// ldmatrix.trans -- no transposed staging copies, no 2-byte scatter stores.
+// A fragments (16 rows x 64) straight from global memory (rows beyond the sequence: zero)
+__device__ __forceinline__ void load_a_frags_global(const bf16* base, int64_t rs, int r0, int g, int t, int N,
+                                                    uint32_t (*a)[4]) {
+  const int ra = r0 + g, rb = r0 + g + 8;
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    a[kk][0] = ra < N ? *reinterpret_cast<const uint32_t*>(base + (int64_t)ra * rs + kk * 16 + 2 * t) : 0u;
+    a[kk][1] = rb < N ? *reinterpret_cast<const uint32_t*>(base + (int64_t)rb * rs + kk * 16 + 2 * t) : 0u;
+    a[kk][2] = ra < N ? *reinterpret_cast<const uint32_t*>(base + (int64_t)ra * rs + kk * 16 + 8 + 2 * t) : 0u;
+    a[kk][3] = rb < N ? *reinterpret_cast<const uint32_t*>(base + (int64_t)rb * rs + kk * 16 + 8 + 2 * t) : 0u;
+  }
+}
+__device__ __forceinline__ float dot_bf16x2(uint32_t a, uint32_t b) {
+  const float2 x = __bfloat1622float2(*reinterpret_cast<const bf162*>(&a));
+  const float2 y = __bfloat1622float2(*reinterpret_cast<const bf162*>(&b));
+  return fmaf(x.x, y.x, x.y * y.y);
+}
+
+constexpr int kSplitWarps = 7;       // warps per CTA of the split kernels; 2 CTAs cover the <= 13 row blocks
+
+// dQ: warp = 16 query rows; K, V of the head in shared memory
+__global__ void __maxnreg__(96)
+attn_bwd_dq_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o, const bf16* __restrict__ d_o,
+                   const float* __restrict__ lse, bf16* __restrict__ dqkv, int N, int H, float c, float scale) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int nkb = (N + 15) >> 4, npad = nkb << 4;
+  bf16* Ks = reinterpret_cast<bf16*>(smem_raw);
+  bf16* Vs = Ks + npad * kRS;
+  const int bh = blockIdx.x >> 1, half = blockIdx.x & 1;
+  const int b = bh / H, h = bh % H;
+  const int64_t rs = 3 * (int64_t)H * kD, os = (int64_t)H * kD;
+  const bf16* qb = qkv + (int64_t)b * N * rs + h * kD;
+  const bf16* kb = qb + H * kD;
+  const bf16* vb = kb + H * kD;
+  const bf16* gb = d_o + (int64_t)b * N * os + h * kD;
+  const bf16* ob = o + (int64_t)b * N * os + h * kD;
+  for (int idx = threadIdx.x; idx < npad * 8; idx += blockDim.x) {
+    const int tok = idx >> 3, ch = idx & 7;                 // 8 lanes = one 128-byte token row: coalesced
+    store_rowmajor(Ks, tok, ch, load_chunk(kb, rs, tok, ch, N));
+    store_rowmajor(Vs, tok, ch, load_chunk(vb, rs, tok, ch, N));
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int rbk = half * kSplitWarps + warp;                // this warp's block of 16 query rows
+  const int r0 = rbk * 16;
+  uint32_t qa[4][4], ga[4][4];
+  float D0 = 0.f, D1 = 0.f, L0 = 0.f, L1 = 0.f;
+  if (rbk < nkb) {
+    load_a_frags_global(qb, rs, r0, g, t, N, qa);
+    load_a_frags_global(gb, os, r0, g, t, N, ga);
+    uint32_t oa[4][4];
+    load_a_frags_global(ob, os, r0, g, t, N, oa);
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      D0 += dot_bf16x2(ga[kk][0], oa[kk][0]) + dot_bf16x2(ga[kk][2], oa[kk][2]);
+      D1 += dot_bf16x2(ga[kk][1], oa[kk][1]) + dot_bf16x2(ga[kk][3], oa[kk][3]);
+    }
+    const float* lb = lse + ((int64_t)b * H + h) * N;
+    if (r0 + g < N) L0 = lb[r0 + g];
+    if (r0 + g + 8 < N) L1 = lb[r0 + g + 8];
+  }
+  D0 += __shfl_xor_sync(0xffffffffu, D0, 1); D0 += __shfl_xor_sync(0xffffffffu, D0, 2);
+  D1 += __shfl_xor_sync(0xffffffffu, D1, 1); D1 += __shfl_xor_sync(0xffffffffu, D1, 2);
+  __syncthreads();
+  if (rbk >= nkb) return;
+  float dq[8][4];
+#pragma unroll
+  for (int dt = 0; dt < 8; ++dt) dq[dt][0] = dq[dt][1] = dq[dt][2] = dq[dt][3] = 0.f;
+  for (int jb = 0; jb < nkb; ++jb) {
+    float s[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+    float dp[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+    mma_rowmajor_b(s, qa, Ks, jb * 16, lane);
+    mma_rowmajor_b(dp, ga, Vs, jb * 16, lane);
+    float ds[2][4];
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float L = (e < 2) ? L0 : L1, D = (e < 2) ? D0 : D1;
+        float p = ex2(fmaf(s[nt][e], c, -L));
+        if (jb == nkb - 1 && jb * 16 + nt * 8 + 2 * t + (e & 1) >= N) p = 0.f;   // columns beyond the sequence
+        ds[nt][e] = p * (dp[nt][e] - D) * scale;
+      }
+    const uint32_t da[4] = {pack2(ds[0][0], ds[0][1]), pack2(ds[0][2], ds[0][3]), pack2(ds[1][0], ds[1][1]),
+                            pack2(ds[1][2], ds[1][3])};
+    mma_tokens_b(dq, da, Ks, jb * 16, lane);
+  }
+  store_tile(dqkv + (int64_t)b * N * rs + h * kD, rs, r0, g, t, N, dq, 1.f, 1.f);
+}
+
+// dK, dV: warp = 16 key rows; Q, dO of the head (+ log-sum-exp, D per query) in shared memory
+__device__ __forceinline__ void attn_bwd_dkv_body(const bf16* __restrict__ qkv, const bf16* __restrict__ o,
+                                                  const bf16* __restrict__ d_o, const float* __restrict__ lse,
+                                                  bf16* __restrict__ dqkv, int N, int H, float c, float scale) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int nkb = (N + 15) >> 4, npad = nkb << 4;
+  bf16* Qs = reinterpret_cast<bf16*>(smem_raw);
+  bf16* Gs = Qs + npad * kRS;
+  float* Ls = reinterpret_cast<float*>(Gs + npad * kRS);
+  float* Ds = Ls + npad;
+  const int bh = blockIdx.x >> 1, half = blockIdx.x & 1;
+  const int b = bh / H, h = bh % H;
+  const int64_t rs = 3 * (int64_t)H * kD, os = (int64_t)H * kD;
+  const bf16* qb = qkv + (int64_t)b * N * rs + h * kD;
+  const bf16* kb = qb + H * kD;
+  const bf16* vb = kb + H * kD;
+  const bf16* gb = d_o + (int64_t)b * N * os + h * kD;
+  const bf16* ob = o + (int64_t)b * N * os + h * kD;
+  for (int idx = threadIdx.x; idx < npad * 8; idx += blockDim.x) {
+    const int tok = idx >> 3, ch = idx & 7;
+    const uint4 gg = load_chunk(gb, os, tok, ch, N), oo = load_chunk(ob, os, tok, ch, N);
+    store_rowmajor(Qs, tok, ch, load_chunk(qb, rs, tok, ch, N));
+    store_rowmajor(Gs, tok, ch, gg);
+    // D[tok] = sum_d dO * O: the 8 chunks of a token are 8 consecutive lanes (npad * 8 and blockDim are multiples of 32)
+    const bf16* ge = reinterpret_cast<const bf16*>(&gg);
+    const bf16* oe = reinterpret_cast<const bf16*>(&oo);
+    float d = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) d = fmaf(__bfloat162float(ge[i]), __bfloat162float(oe[i]), d);
+    d += __shfl_xor_sync(0xffffffffu, d, 1);
+    d += __shfl_xor_sync(0xffffffffu, d, 2);
+    d += __shfl_xor_sync(0xffffffffu, d, 4);
+    if (ch == 0) {
+      Ds[tok] = d;
+      Ls[tok] = tok < N ? lse[((int64_t)b * H + h) * N + tok] : 0.f;
+    }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int rbk = half * kSplitWarps + warp;                // this warp's block of 16 key rows
+  const int r0 = rbk * 16;
+  uint32_t ka[4][4], va[4][4];
+  if (rbk < nkb) {
+    load_a_frags_global(kb, rs, r0, g, t, N, ka);
+    load_a_frags_global(vb, rs, r0, g, t, N, va);
+  }
+  __syncthreads();
+  if (rbk >= nkb) return;
+  float dk[8][4], dv[8][4];
+#pragma unroll
+  for (int dt = 0; dt < 8; ++dt) {
+    dk[dt][0] = dk[dt][1] = dk[dt][2] = dk[dt][3] = 0.f;
+    dv[dt][0] = dv[dt][1] = dv[dt][2] = dv[dt][3] = 0.f;
+  }
+  for (int ib = 0; ib < nkb; ++ib) {
+    float st[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+    float dpt[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+    mma_rowmajor_b(st, ka, Qs, ib * 16, lane);
+    mma_rowmajor_b(dpt, va, Gs, ib * 16, lane);
+    uint32_t pa[4], da[4];
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) {
+      float pt[4], dst[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int qi = ib * 16 + nt * 8 + 2 * t + (e & 1);
+        // queries beyond the sequence have dO = 0 and D = 0 (zero-filled tiles): their finite p contributes nothing
+        pt[e] = ex2(fmaf(st[nt][e], c, -Ls[qi]));
+        dst[e] = pt[e] * (dpt[nt][e] - Ds[qi]) * scale;
+      }
+      pa[2 * nt] = pack2(pt[0], pt[1]); pa[2 * nt + 1] = pack2(pt[2], pt[3]);
+      da[2 * nt] = pack2(dst[0], dst[1]); da[2 * nt + 1] = pack2(dst[2], dst[3]);
+    }
+    mma_tokens_b(dv, pa, Gs, ib * 16, lane);
+    mma_tokens_b(dk, da, Qs, ib * 16, lane);
+  }
+  bf16* dk_out = dqkv + (int64_t)b * N * rs + H * kD + h * kD;
+  store_tile(dk_out, rs, r0, g, t, N, dk, 1.f, 1.f);
+  store_tile(dk_out + H * kD, rs, r0, g, t, N, dv, 1.f, 1.f);
+}
+
+// two register budgets of the same body: 96 (three CTAs = 21 warps per SM, spills) / 128 (two CTAs, none; default)
+__global__ void __maxnreg__(96)
+attn_bwd_dkv_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o, const bf16* __restrict__ d_o,
+                    const float* __restrict__ lse, bf16* __restrict__ dqkv, int N, int H, float c, float scale) {
+  attn_bwd_dkv_body(qkv, o, d_o, lse, dqkv, N, H, c, scale);
+}
+__global__ void __maxnreg__(128)
+attn_bwd_dkv128_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o, const bf16* __restrict__ d_o,
+                       const float* __restrict__ lse, bf16* __restrict__ dqkv, int N, int H, float c, float scale) {
+  attn_bwd_dkv_body(qkv, o, d_o, lse, dqkv, N, H, c, scale);
+}
+
+size_t split_smem(int N, bool with_rows) {
+  const int npad = (N + 15) / 16 * 16;
+  return (size_t)(2 * npad * kRS) * sizeof(bf16) + (with_rows ? 2 * npad * sizeof(float) : 0);
+}
+
 size_t fwd_smem(int N) {
   const int npad = (N + 15) / 16 * 16;
-  return (size_t)(npad * kRS + kD * (npad + 8)) * sizeof(bf16);
+  return (size_t)(2 * npad * kRS) * sizeof(bf16);
 }
 size_t bwd_smem(int N) {
   const int npad = (N + 15) / 16 * 16;
@@ -354,6 +565,23 @@ int b200at_attn_bwd(const void* qkv, const void* o, const void* d_o, const float
                     int64_t H, float scale, void* stream) {
   if (B <= 0) return 0;
   if (N <= 0 || N > 16 * kMaxBlocks || H <= 0) return (int)cudaErrorInvalidValue;
+  static const bool single = []() { const char* v = getenv("B200AT_ATTN_BWD"); return v && v[0] == '1'; }();
+  if (!single) {
+    const float c2 = scale * 1.4426950408889634f;
+    const size_t sa = split_smem((int)N, false), sb = split_smem((int)N, true);
+    cudaError_t e1 = cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sa);
+    if (e1 != cudaSuccess) return (int)e1;
+    // measured (profiles/r01_vit_bench_v4.txt): 128 registers / 2 CTAs per SM 363 us, 96 registers / 3 CTAs 484 us (spills)
+    static const bool dkv128 = []() { const char* v = getenv("B200AT_ATTN_DKV_REGS"); return !(v && atoi(v) == 96); }();
+    auto dkv = dkv128 ? attn_bwd_dkv128_kernel : attn_bwd_dkv_kernel;
+    e1 = cudaFuncSetAttribute(dkv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb);
+    if (e1 != cudaSuccess) return (int)e1;
+    attn_bwd_dq_kernel<<<(unsigned)(2 * B * H), 32 * kSplitWarps, sa, (cudaStream_t)stream>>>(
+        (const bf16*)qkv, (const bf16*)o, (const bf16*)d_o, lse, (bf16*)dqkv, (int)N, (int)H, c2, scale);
+    dkv<<<(unsigned)(2 * B * H), 32 * kSplitWarps, sb, (cudaStream_t)stream>>>(
+        (const bf16*)qkv, (const bf16*)o, (const bf16*)d_o, lse, (bf16*)dqkv, (int)N, (int)H, c2, scale);
+    return (int)cudaGetLastError();
+  }
   const size_t smem = bwd_smem((int)N);
   cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
