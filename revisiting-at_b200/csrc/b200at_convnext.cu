@@ -510,18 +510,33 @@ __global__ void __launch_bounds__(DwTile<TH, TW, NB>::kThreads, 2)
     const int n = n0 + img, w = w0 + col;
     if (n < p.B && w < p.W) {
       const bool second = w + 1 < p.W;
+      const int64_t off0 = (((int64_t)n * p.H + h0) * p.W + w) * p.C + c0 + cp * 2;
+      const int64_t rstride = (int64_t)p.W * p.C;
+      if (ADD) {
+        // residual-gradient join fused into the input-gradient pass.  All loads first (read-only path), then the
+        // stores: interleaved, every load had to wait behind the previous store (y and add may alias as far as the
+        // compiler knows), which serialised 2*TH memory round trips per tile (dgrad 200 us vs forward 131 us).
+        uint32_t a0[TH], a1[TH];
+#pragma unroll
+        for (int r = 0; r < TH; ++r) {
+          a0[r] = 0u; a1[r] = 0u;
+          if (h0 + r < p.H) {
+            a0[r] = __ldg(reinterpret_cast<const uint32_t*>(p.add + off0 + r * rstride));
+            if (second) a1[r] = __ldg(reinterpret_cast<const uint32_t*>(p.add + off0 + r * rstride + p.C));
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < TH; ++r) {
+          const float2 f0 = __bfloat1622float2(*reinterpret_cast<const bf162*>(&a0[r]));
+          const float2 f1 = __bfloat1622float2(*reinterpret_cast<const bf162*>(&a1[r]));
+          acc0[r].x += f0.x; acc0[r].y += f0.y;
+          acc1[r].x += f1.x; acc1[r].y += f1.y;
+        }
+      }
 #pragma unroll
       for (int r = 0; r < TH; ++r) {
         if (h0 + r < p.H) {
-          const int64_t off = (((int64_t)n * p.H + h0 + r) * p.W + w) * p.C + c0 + cp * 2;
-          if (ADD) {  // residual-gradient join fused into the input-gradient pass
-            const float2 a = __bfloat1622float2(*reinterpret_cast<const bf162*>(p.add + off));
-            acc0[r].x += a.x; acc0[r].y += a.y;
-            if (second) {
-              const float2 a1 = __bfloat1622float2(*reinterpret_cast<const bf162*>(p.add + off + p.C));
-              acc1[r].x += a1.x; acc1[r].y += a1.y;
-            }
-          }
+          const int64_t off = off0 + r * rstride;
           *reinterpret_cast<bf162*>(p.y + off) = __floats2bfloat162_rn(acc0[r].x, acc0[r].y);
           if (second) *reinterpret_cast<bf162*>(p.y + off + p.C) = __floats2bfloat162_rn(acc1[r].x, acc1[r].y);
         }
