@@ -59,6 +59,7 @@ def parse():
     ap.add_argument('--label-smoothing', type=float, default=None, help='default 0.1 for convnext_base (config 4), else 0')
     ap.add_argument('--no-graph', action='store_true', help='launch the attack kernel by kernel instead of replaying its CUDA graph')
     ap.add_argument('--cpu-seconds', type=float, default=20.0, help='budget of the cpu_baseline sample')
+    ap.add_argument('--res', type=int, default=RES, help='image side (224 = the metric line; 320 = the secondary resolution of north_star)')
     return ap.parse_args()
 
 
@@ -93,7 +94,7 @@ def workload_config(n_gpus, batch, arch=ARCH, ema=False, label_smoothing=0.):
             'arch': arch, 'batch_per_gpu': batch, 'global_batch': batch * n_gpus, 'resolution': RES,
             'norm': 'Linf', 'eps': '4/255', 'n_iter': N_ITER, 'parallelism': f'dp{n_gpus}',
             'ema': bool(ema), 'label_smoothing': label_smoothing,
-            'l2_policy': 'inputs_exceed_l2 (per-step working set >> 126 MB; image-sized passes stream 385 MB)'}
+            'l2_policy': f'inputs_exceed_l2 (per-step working set >> 126 MB; image-sized passes stream {20 * batch * N_FTS / 1e6:.0f} MB)'}
 
 
 def synth_batch(batch, seed):
@@ -104,9 +105,10 @@ def synth_batch(batch, seed):
 
 
 ENGINE_NOTE = {
-    False: 'hand-written NHWC bf16 kernels: fused first stem stage, dwconv7 fwd/dgrad/wgrad, LayerNorm, bias+GELU, '
-           'tcgen05 GEMM (pwconv2+scale+residual, pwconv1 dgrad); cuBLAS for pwconv1 fwd / weight-gradient GEMMs, '
-           'cuDNN for the strided stem/downsample convs',
+    False: 'hand-written NHWC bf16 kernels: fused first stem stage, dwconv7 fwd/dgrad/wgrad, LayerNorm (+patch layout for '
+           'the downsample), bias+GELU, tcgen05 GEMM for every forward / input-gradient GEMM (pwconv1, pwconv2+scale+bias+'
+           'residual, both dgrads, downsample conv2x2s2); cuBLAS for the weight-gradient GEMMs, cuDNN for the strided '
+           '3x3 stem convs outside the fused first stage',
     True: 'hand-written kernels: fused first stem stage, LayerNorm(+GELU), bias+GELU, mma.sync attention fwd/bwd, '
           'tcgen05 GEMM (qkv+bias, proj/fc2+bias+residual, fc1, all input-gradient GEMMs); cuBLAS for weight-gradient '
           'GEMMs, cuDNN for stem convs 2-4',
@@ -334,7 +336,7 @@ def run_b200(args):
     achieved = alg_bytes / (k1_ms * 1e-3) / 1e9
     traffic = None
     tp = os.path.join(ROOT, 'profiles', 'k1_linf_step_traffic.json')
-    if os.path.exists(tp):
+    if os.path.exists(tp) and RES == 224 and batch == 128 and args.arch == ARCH:   # the capture is of this shape
         traffic = json.load(open(tp)).get('dram_bytes_per_launch')
     line = {
         'metric': METRIC, 'value': imgs / (ms * 1e-3), 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
@@ -366,7 +368,9 @@ def run_b200(args):
 
 
 def main():
+    global RES, N_FTS
     args = parse()
+    RES, N_FTS = args.res, 3 * args.res * args.res
     if args.batch is None:
         args.batch = WORKLOADS[args.arch][1]
     if args.ema is None:
