@@ -141,6 +141,7 @@ class DeviceEma:
 
     def __init__(self, model, decay=0.9999):
         self.decay = decay
+        self.model = model
         self.params = [p for p in model.parameters()]
         self.shadow = [p.detach().clone() for p in self.params]
 
@@ -148,13 +149,23 @@ class DeviceEma:
     def update(self):
         torch._foreach_lerp_(self.shadow, [p.detach() for p in self.params], 1. - self.decay)
 
+    def state_dict(self):
+        """EMA weights (+ the model's buffers) under the model's own key names: what timm's
+        `get_state_dict(model_ema)` hands to `weights_ema_N.pt` (main.py:741)."""
+        shadow = {id(p): s for p, s in zip(self.params, self.shadow)}
+        out = {}
+        for k, v in self.model.state_dict(keep_vars=True).items():
+            out[k] = shadow.get(id(v), v).detach().clone()
+        return out
+
 
 class AdvTrainStep:
     """One adversarial training step on one rank (main.py:961-997)."""
 
     def __init__(self, base_model, attack='apgd', norm='Linf', eps=4. / 255., n_iter=2, lr=1e-3, weight_decay=0.05,
                  label_smoothing=0., ema=False, distributed=False, device=None, autocast_dtype=torch.bfloat16,
-                 channels_last=True, mixup_fn=None, perturb=None, graph_attack=False):
+                 channels_last=True, mixup_fn=None, perturb=None, graph_attack=False, param_groups=None,
+                 optimizer='adamw', momentum=0.9):
         self.device = device
         # `perturb` overrides the attack callable (same (model, x, y) contract as main.py:283)
         perturb = perturb if perturb is not None else make_attack(attack, norm, eps, n_iter, mixup_fn=mixup_fn)
@@ -177,12 +188,18 @@ class AdvTrainStep:
                                                         gradient_as_bucket_view=True)
         self.model = model
         self.perturb = perturb is not None
-        decay, no_decay = [], []
-        for n, p in self.raw.named_parameters():                               # main.py:395-459 param groups
-            (no_decay if p.ndim <= 1 else decay).append(p)
-        self.optimizer = torch.optim.AdamW(
-            [{'params': decay, 'weight_decay': weight_decay}, {'params': no_decay, 'weight_decay': 0.}],
-            lr=lr, betas=(0.9, 0.95), fused=True if (device is not None and device.type == 'cuda') else False)
+        if param_groups is not None:                                           # the driver's per-arch rule (main.py:395-452)
+            groups = [g for g in param_groups(self.raw.named_parameters()) if g['params']]
+        else:
+            decay, no_decay = [], []
+            for n, p in self.raw.named_parameters():
+                (no_decay if p.ndim <= 1 else decay).append(p)
+            groups = [{'params': decay, 'weight_decay': weight_decay}, {'params': no_decay, 'weight_decay': 0.}]
+        on_gpu = device is not None and device.type == 'cuda'
+        if optimizer == 'sgd':                                                 # main.py:454-457
+            self.optimizer = torch.optim.SGD(groups, lr=lr, momentum=momentum)
+        else:
+            self.optimizer = torch.optim.AdamW(groups, lr=lr, betas=(0.9, 0.95), fused=on_gpu)
         self.label_smoothing = label_smoothing
         self.mixup_fn = mixup_fn
         self.autocast_dtype = autocast_dtype
