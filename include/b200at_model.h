@@ -101,6 +101,20 @@ int b200at_stem0_bwd_input(const void* dy, const float* x, const float* mean3, c
 int b200at_gemm_bf16(const void* a, const void* b, void* c, void* c2, const void* aux, const float* bias,
                      int64_t M, int64_t N, int64_t K, int epilogue, void* stream);
 
+/* The whole MLP of a ConvNeXt block as one tcgen05 kernel per direction (models/convnext.py:42-49: pwconv1 -> GELU ->
+ * pwconv2 -> layer scale -> + residual), hidden activation kept on chip:
+ *   backward == 0:  out = residual + GELU(a wa^T + bias1) wb^T + bias2      a = LN output t2 [M][C], wa = W1 [4C][C],
+ *                   wb = gamma*W2 [C][4C], bias2 = gamma*b2; z [M][4C] RECEIVES the pre-activation a wa^T (no bias);
+ *                   p_out (nullable) receives GELU(z + bias1) (kept only when weight gradients will be needed)
+ *   backward != 0:  out = ((a wa^T) * GELU'(z + bias1)) wb^T                a = dL/dout [M][C], wa = (gamma*W2)^T [4C][C],
+ *                   wb = W1^T [C][4C]; z is READ; p_out (nullable) receives dz = dL/dz; bias2 / residual ignored
+ * All matrices bf16 row-major (K contiguous), fp32 accumulation in TMEM, biases fp32.  C in {96, 192}
+ * (b200at_mlp_fused_supported); other widths: b200at_gemm_bf16 + b200at_bias_gelu_*. */
+int b200at_mlp_fused_supported(int64_t C);
+int b200at_mlp_fused(const void* a, const void* wa, const void* wb, const float* bias1, const float* bias2,
+                     const void* residual, void* z, void* p_out, void* out, int64_t M, int64_t C, int backward,
+                     void* stream);
+
 /* Multi-head self-attention of the ViT-S-CvSt blocks (timm 0.8 vision_transformer.Attention.forward, un-vendored;
  * call sites utils_architecture.py:271-301):  q,k,v = qkv.reshape(B,N,3,H,64).permute(2,0,3,1,4);
  * o = softmax(q k^T * scale) v, written as [B][N][H*64].  qkv: bf16 [B][N][3][H][64]; lse: fp32 [B][H][N], the

@@ -95,6 +95,17 @@ def main():
         timeit(f'gemm dz GELU_GRAD [{M}x{N4}x{C}]',
                lambda: _abi.gemm_bf16(x2, w1, hh, _abi.EPI_GELU_GRAD, aux=z), 2. * (M * C + 2 * M * N4), fl)
         timeit(f'gemm dgrad1 NONE [{M}x{C}x{N4}]', lambda: _abi.gemm_bf16(dh, w2, out, _abi.EPI_NONE), 2. * (M * N4 + M * C), fl)
+        if _abi.mlp_fused_supported(C):
+            w2t = w2.t().contiguous()       # [4C, C]
+            w1t = w1.t().contiguous()       # [C, 4C]
+            timeit(f'mlp fused fwd (z out) [{M}x{C}x{N4}]',
+                   lambda: _abi.mlp_fused(x2, w1, w2, b4, z, out, bias2=bias, residual=xr), 2. * (3 * M * C + M * N4), 2 * fl)
+            timeit(f'mlp fused fwd (z,a out) [{M}x{C}x{N4}]',
+                   lambda: _abi.mlp_fused(x2, w1, w2, b4, z, out, bias2=bias, residual=xr, p_out=hh), 2. * (3 * M * C + 2 * M * N4), 2 * fl)
+            timeit(f'mlp fused bwd (z in) [{M}x{C}x{N4}]',
+                   lambda: _abi.mlp_fused(x2, w2t, w1t, b4, z, out, backward=True), 2. * (2 * M * C + M * N4), 2 * fl)
+            timeit(f'mlp fused bwd (z in, dz out) [{M}x{C}x{N4}]',
+                   lambda: _abi.mlp_fused(x2, w2t, w1t, b4, z, out, p_out=hh, backward=True), 2. * (2 * M * C + 2 * M * N4), 2 * fl)
         del x, dy, y, z, hh, dh
         torch.cuda.empty_cache()
 

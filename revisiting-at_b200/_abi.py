@@ -103,6 +103,8 @@ def _declare(L):
         'b200at_dwconv7_fwd': [P, P, P, P, P, I64, I64, I64, I64, P],
         'b200at_dwconv7_wgrad': [P, P, P, P, I64, I64, I64, I64, P],
         'b200at_gemm_bf16': [P, P, P, P, P, P, I64, I64, I64, I, P],
+        'b200at_mlp_fused_supported': [I64],
+        'b200at_mlp_fused': [P, P, P, P, P, P, P, P, P, I64, I64, I, P],
         'b200at_stem0_fwd': [P, P, P, P, P, P, P, P, I64, I64, I64, I64, F, P],
         'b200at_stem0_bwd_input': [P, P, P, P, P, P, P, P, P, I64, I64, I64, I64, F, P],
         'b200at_attn_fwd': [P, P, P, I64, I64, I64, F, P],
@@ -448,6 +450,30 @@ def gemm_bf16(a, b, c, epilogue=EPI_NONE, bias=None, aux=None, c2=None):
                                       _act(c2, 'c2') if c2 is not None else c_void_p(0),
                                       _act(aux, 'aux') if aux is not None else c_void_p(0),
                                       _par(bias, 'bias', N), M, N, K, epilogue, _stream()), 'gemm_bf16')
+
+
+def mlp_fused_supported(C):
+    return bool(lib().b200at_mlp_fused_supported(C))
+
+
+def mlp_fused(a, wa, wb, bias1, z, out, bias2=None, residual=None, p_out=None, backward=False):
+    """The block's MLP in one tcgen05 kernel (include/b200at_model.h: b200at_mlp_fused).  a [M,C], wa [4C,C], wb [C,4C],
+    z [M,4C] (written forward / read backward), out [M,C]; p_out [M,4C] optional (GELU output / dz)."""
+    M, C = a.shape
+    if tuple(wa.shape) != (4 * C, C) or tuple(wb.shape) != (C, 4 * C) or tuple(z.shape) != (M, 4 * C) \
+            or tuple(out.shape) != (M, C):
+        raise B200atError(f'mlp_fused shapes: a {tuple(a.shape)} wa {tuple(wa.shape)} wb {tuple(wb.shape)} '
+                          f'z {tuple(z.shape)} out {tuple(out.shape)}')
+    for t, nm, shp in ((residual, 'residual', (M, C)), (p_out, 'p_out', (M, 4 * C))):
+        if t is not None and tuple(t.shape) != shp:
+            raise B200atError(f'mlp_fused {nm} must be {shp}')
+    null = c_void_p(0)
+    with _Timed('mlp_fused_bwd' if backward else 'mlp_fused_fwd'):
+        _check(lib().b200at_mlp_fused(_act(a, 'a'), _act(wa, 'wa'), _act(wb, 'wb'), _par(bias1, 'bias1', 4 * C),
+                                      _par(bias2, 'bias2', C) if bias2 is not None else null,
+                                      _act(residual, 'residual') if residual is not None else null,
+                                      _act(z, 'z'), _act(p_out, 'p_out') if p_out is not None else null,
+                                      _act(out, 'out'), M, C, 1 if backward else 0, _stream()), 'mlp_fused')
 
 
 def attn_fwd(qkv, o, lse, heads, scale):

@@ -18,6 +18,7 @@ UNITS = [
     ('b200at_attack.cu', ['-fmad=false']),
     ('b200at_convnext.cu', []),
     ('b200at_gemm.cu', []),
+    ('b200at_mlp.cu', []),
     ('b200at_stem.cu', []),
     ('b200at_attention.cu', []),
 ]

@@ -166,7 +166,18 @@ def _f32(t):
 #   'dgrad2'    da = dout (gamma W2)              (plain; same shapes as 'fc1')
 #   'gelu'      pwconv1 forward with bias + GELU fused (+ pre-activation saved)   [slower: epilogue-bound]
 #   'gelu_grad' dz = (dout W2g) * GELU'(z)        fused                           [slower: epilogue-bound]
+#   'mlp'       the whole MLP (pwconv1 -> GELU -> pwconv2 + scale + bias + residual, and its input gradient) as ONE
+#               kernel per direction with the 4C hidden kept on chip (csrc/b200at_mlp.cu), for C in {96, 192}
 TCGEN05 = set(filter(None, os.environ.get('B200AT_TCGEN05', 'residual,dgrad1,fc1,dgrad2').split(',')))
+_MLP_OK = {}
+
+
+def _mlp_fused(C):
+    if 'mlp' not in TCGEN05:
+        return False
+    if C not in _MLP_OK:
+        _MLP_OK[C] = _abi.mlp_fused_supported(C)
+    return _MLP_OK[C]
 
 _PCACHE = {}     # (ids of the source parameters, tag) -> (stamp, value, weakrefs of the parameters)
 
@@ -293,7 +304,15 @@ class _ConvNeXtBlock(Function):
         mean = torch.empty(M, device=x.device, dtype=torch.float32)
         rstd = torch.empty_like(mean)
         _abi.ln_fwd(t1, lnw, lnb, t2, mean, rstd, 1e-6, False)
-        if 'gelu' in TCGEN05:
+        fused = _mlp_fused(C)
+        if fused:
+            z = torch.empty(M, 4 * C, device=x.device, dtype=BF16)      # pre-activation WITHOUT the bias
+            a = torch.empty_like(z) if pg else None                     # only the weight gradients need it
+            out = torch.empty_like(x)
+            _abi.mlp_fused(t2.view(M, C), P['w1b'], P['w2g'], b1f, z, out.view(M, C), bias2=P['b2g'],
+                           residual=x.view(M, C), p_out=a)
+            zb = b1f
+        elif 'gelu' in TCGEN05:
             z = torch.empty(M, 4 * C, device=x.device, dtype=BF16)      # pre-activation INCLUDING the bias
             a = _gemm(t2.view(M, C), P['w1b'], _abi.EPI_BIAS_GELU, bias=b1f, c2=z)
             zb = None
@@ -305,7 +324,9 @@ class _ConvNeXtBlock(Function):
             a = torch.empty_like(z)
             _abi.bias_gelu_fwd(z, b1f, a)
             zb = b1f
-        if 'residual' in TCGEN05:
+        if fused:
+            pass
+        elif 'residual' in TCGEN05:
             out = _gemm(a, P['w2g'], _abi.EPI_RESIDUAL, bias=P['b2g'], aux=x.view(M, C)).view(B, H, W, C)
         else:
             z2 = a @ P['w2g'].t()
@@ -329,7 +350,14 @@ class _ConvNeXtBlock(Function):
         pg = ctx.param_grads and any(ctx.needs_input_grad[1:])
         d2 = dout.view(M, C)
         db1 = torch.zeros(4 * C, device=dout.device, dtype=torch.float32) if pg else None
-        if 'gelu_grad' in TCGEN05 and ctx.zb is None:
+        dt2 = None
+        if _mlp_fused(C) and ctx.zb is not None:
+            dz = torch.empty_like(z) if pg else None                    # only the weight gradients need it
+            dt2 = torch.empty_like(dout)
+            _abi.mlp_fused(d2, P['w2gt'], P['w1t'], ctx.zb, z, dt2.view(M, C), p_out=dz, backward=True)
+            if pg:
+                _abi.colsum_bf16(dz, db1)
+        elif 'gelu_grad' in TCGEN05 and ctx.zb is None:
             dz = _gemm(d2, P['w2gt'], _abi.EPI_GELU_GRAD, aux=z)
             if pg:
                 _abi.colsum_bf16(dz, db1)
@@ -338,7 +366,9 @@ class _ConvNeXtBlock(Function):
             dz = torch.empty_like(da)
             zero = ctx.zb if ctx.zb is not None else torch.zeros(4 * C, device=dout.device, dtype=torch.float32)
             _abi.bias_gelu_bwd(da, z, zero, dz, db1)                    # pwconv1 bias gradient rides along
-        if 'dgrad1' in TCGEN05:
+        if dt2 is not None:
+            pass
+        elif 'dgrad1' in TCGEN05:
             dt2 = _gemm(dz, P['w1t']).view(B, H, W, C)
         else:
             dt2 = (dz @ P['w1b']).view(B, H, W, C)

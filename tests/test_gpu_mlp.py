@@ -1,0 +1,129 @@
+"""GPU: the fused MLP kernel (b200at_mlp_fused: pwconv1 -> GELU -> pwconv2 + bias + residual in one tcgen05 kernel, and
+its input gradient) against (a) the unfused kernels it replaces (tcgen05 GEMM + bias/GELU kernels), which round the
+hidden tensor to bf16 at the same places -- agreement to one bf16 step of the output -- and (b) torch fp32 on the
+same bf16 operands (models/convnext.py:42-49).  Ragged M, more tiles than SMs (several tiles per CTA through every
+barrier phase), with and without the optional hidden output, and the whole block through autograd."""
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
+BF16 = torch.bfloat16
+
+
+@pytest.fixture(scope='module')
+def abi(cuda_dev):
+    import revisiting_at_b200  # noqa: F401
+    from revisiting_at_b200 import _abi
+    return _abi
+
+
+def _close(got, want, what, rel=1e-2, ab=2e-2):
+    got, want = got.float(), want.float()
+    err = (got - want).abs()
+    bad = err > rel * want.abs() + ab
+    assert not bool(bad.any()), (f'{what}: max err {err.max().item():.4g}, {int(bad.sum())} bad of {bad.numel()}, '
+                                 f'first bad at {bad.nonzero()[0].tolist()}')
+
+
+def _data(C, M, dev, seed):
+    g = torch.Generator(device='cuda').manual_seed(seed)
+    r = lambda *s, scale=1.: (torch.randn(*s, generator=g, device=dev) * scale).to(BF16)
+    return dict(t2=r(M, C), x=r(M, C), dout=r(M, C), w1=r(4 * C, C, scale=C ** -0.5), w2=r(C, 4 * C, scale=(4 * C) ** -0.5),
+                b1=torch.randn(4 * C, generator=g, device=dev) * 0.5, b2=torch.randn(C, generator=g, device=dev))
+
+
+@pytest.mark.parametrize('C,M', [(96, 128), (96, 128 * 5 + 37), (192, 300), (192, 128 * 3), (96, 148 * 128 * 2 + 64 + 128 * 30),
+                                 (192, 148 * 128 + 128 * 77 + 5)])
+def test_fused_forward(abi, cuda_dev, C, M):
+    d = _data(C, M, cuda_dev, C + M)
+    nan = lambda *s: torch.full(s, float('nan'), device=cuda_dev, dtype=BF16)
+    z, a, out = nan(M, 4 * C), nan(M, 4 * C), nan(M, C)
+    abi.mlp_fused(d['t2'], d['w1'], d['w2'], d['b1'], z, out, bias2=d['b2'], residual=d['x'], p_out=a)
+    torch.cuda.synchronize()
+    # (a) the unfused kernels
+    z_u, a_u, out_u = nan(M, 4 * C), nan(M, 4 * C), nan(M, C)
+    abi.gemm_bf16(d['t2'], d['w1'], z_u, abi.EPI_NONE)
+    abi.bias_gelu_fwd(z_u, d['b1'], a_u)
+    abi.gemm_bf16(a_u, d['w2'], out_u, abi.EPI_RESIDUAL, bias=d['b2'], aux=d['x'])
+    _close(z, z_u, 'pre-activation vs the plain GEMM', rel=2 ** -7, ab=1e-3)
+    a_own = nan(M, 4 * C)
+    abi.bias_gelu_fwd(z, d['b1'], a_own)
+    assert torch.equal(a, a_own), 'GELU output differs from bias_gelu_fwd on the same z'
+    _close(out, out_u, 'out vs unfused', rel=2 ** -7, ab=1e-3)
+    # (b) fp32 reference
+    zr = d['t2'].float() @ d['w1'].float().t()
+    ar = F.gelu(zr.to(BF16).float() + d['b1'])
+    _close(z, zr, 'z')
+    _close(a, ar, 'a')
+    _close(out, d['x'].float() + ar.to(BF16).float() @ d['w2'].float().t() + d['b2'], 'out')
+    # without the optional hidden output: same z / out
+    z2, out2 = nan(M, 4 * C), nan(M, C)
+    abi.mlp_fused(d['t2'], d['w1'], d['w2'], d['b1'], z2, out2, bias2=d['b2'], residual=d['x'])
+    assert torch.equal(z2, z) and torch.equal(out2, out)
+
+
+@pytest.mark.parametrize('C,M', [(96, 128 * 5 + 37), (192, 300), (96, 148 * 128 * 2 + 64), (192, 148 * 128 + 128 * 77 + 5)])
+def test_fused_backward(abi, cuda_dev, C, M):
+    d = _data(C, M, cuda_dev, 7 * C + M)
+    nan = lambda *s: torch.full(s, float('nan'), device=cuda_dev, dtype=BF16)
+    z = (torch.randn(M, 4 * C, device=cuda_dev, generator=torch.Generator(device='cuda').manual_seed(3)) * 1.5).to(BF16)
+    w2t = d['w2'].t().contiguous()          # [4C, C]:  da = dout @ w2      == dout @ w2t^T
+    w1t = d['w1'].t().contiguous()          # [C, 4C]:  dt2 = dz @ w1       == dz @ w1t^T
+    dz, dt2 = nan(M, 4 * C), nan(M, C)
+    abi.mlp_fused(d['dout'], w2t, w1t, d['b1'], z, dt2, p_out=dz, backward=True)
+    torch.cuda.synchronize()
+    da_u, dz_u, dt2_u = nan(M, 4 * C), nan(M, 4 * C), nan(M, C)
+    abi.gemm_bf16(d['dout'], w2t, da_u, abi.EPI_NONE)
+    abi.bias_gelu_bwd(da_u, z, d['b1'], dz_u, None)
+    abi.gemm_bf16(dz_u, w1t, dt2_u, abi.EPI_NONE)
+    _close(dz, dz_u, 'dz vs bias_gelu_bwd', rel=2 ** -6, ab=2e-3)
+    _close(dt2, dt2_u, 'dt2 vs unfused', rel=2 ** -7, ab=1e-3)
+    zz = (z.float() + d['b1']).requires_grad_()
+    (gp,) = torch.autograd.grad(F.gelu(zz).sum(), zz)
+    dzr = (d['dout'].float() @ d['w2'].float()).to(BF16).float() * gp
+    _close(dz, dzr, 'dz')
+    _close(dt2, dzr.to(BF16).float() @ d['w1'].float(), 'dt2')
+    dt2b = nan(M, C)
+    abi.mlp_fused(d['dout'], w2t, w1t, d['b1'], z, dt2b, backward=True)
+    assert torch.equal(dt2b, dt2)
+
+
+def test_block_with_fused_mlp_matches_unfused_block(cuda_dev):
+    """the whole ConvNeXt block through autograd: fused-MLP path == three-kernel path (outputs, input gradient in the
+    attack's input-grad-only mode, and every parameter gradient of the training mode)"""
+    from revisiting_at_b200 import ops
+    torch.manual_seed(0)
+    for C, H in ((96, 12), (192, 10)):
+        x = torch.randn(4, H, H, C, device=cuda_dev).to(BF16)
+        ps = [torch.randn(C, 1, 7, 7, device=cuda_dev) * 0.1, torch.randn(C, device=cuda_dev) * 0.1,
+              1 + 0.1 * torch.randn(C, device=cuda_dev), 0.1 * torch.randn(C, device=cuda_dev),
+              torch.randn(4 * C, C, device=cuda_dev) * C ** -0.5, torch.randn(4 * C, device=cuda_dev) * 0.1,
+              torch.randn(C, 4 * C, device=cuda_dev) * (4 * C) ** -0.5, torch.randn(C, device=cuda_dev) * 0.1,
+              torch.rand(C, device=cuda_dev) + 0.5]
+        res = {}
+        saved = set(ops.TCGEN05)
+        try:
+            for mode in ('unfused', 'fused'):
+                ops.TCGEN05.discard('mlp')
+                if mode == 'fused':
+                    ops.TCGEN05.add('mlp')
+                xi = x.clone().requires_grad_()
+                pi = [p.clone().requires_grad_() for p in ps]
+                out = ops.convnext_block(xi, *pi)
+                g = torch.autograd.grad(out.float().square().sum(), [xi] + pi)
+                with ops.input_grad_only():
+                    xa = x.clone().requires_grad_()
+                    oa = ops.convnext_block(xa, *[p.detach() for p in ps])
+                (ga,) = torch.autograd.grad(oa.float().square().sum(), xa)
+                res[mode] = (out.detach(), g, ga)
+        finally:
+            ops.TCGEN05.clear(); ops.TCGEN05.update(saved)
+        (o0, g0, a0), (o1, g1, a1) = res['unfused'], res['fused']
+        _close(o1, o0, f'block out C={C}', rel=2 ** -6, ab=2e-2)
+        _close(a1, a0, f'attack input gradient C={C}', rel=3e-2, ab=3e-2 * a0.float().abs().max().item())
+        for k, (u, v) in enumerate(zip(g0, g1)):
+            scale = u.float().abs().max().item()
+            _close(v, u, f'gradient {k} C={C}', rel=3e-2, ab=3e-2 * scale)
