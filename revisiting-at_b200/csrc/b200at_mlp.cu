@@ -52,13 +52,14 @@ struct MlpCfg {
   static constexpr int PBytes = 128 * 128;                 // [128 rows x 128 B]
   static constexpr int OffW = AStages * ABytes;
   static constexpr int OffP = OffW + WStages * WStageBytes;
-  static constexpr int OffBias = OffP + 2 * PBytes;        // fp32 bias1[4C], bias2[C]
+  static constexpr int OffZ = OffP + 2 * PBytes;           // z chunk staging [2][128 rows x 128 B]
+  static constexpr int OffBias = OffZ + 2 * PBytes;        // fp32 bias1[4C], bias2[C]
   static constexpr int OffBars = OffBias + 5 * C * 4;
   static constexpr int Smem = 1024 + OffBars + 256;
-  static constexpr int TmemCols = (C + 2 * kChunk) <= 256 ? 256 : 512;
+  static constexpr int TmemCols = (2 * C + 2 * kChunk) <= 256 ? 256 : 512;   // acc_b[2] + acc_a[2]
   static_assert(C % 16 == 0 && C <= 256, "GEMM-b is one UMMA of N = C");
   static_assert(Smem <= 227 * 1024, "shared memory budget");
-  static_assert(C + 2 * kChunk <= 512, "TMEM budget");
+  static_assert(2 * C + 2 * kChunk <= 512, "TMEM budget");
 };
 
 struct MlpParams {
@@ -75,6 +76,8 @@ template <int C, int MODE>   // MODE 0 forward, 1 backward
 __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const __grid_constant__ CUtensorMap map_a,
                                                           const __grid_constant__ CUtensorMap map_wa,
                                                           const __grid_constant__ CUtensorMap map_wb,
+                                                          const __grid_constant__ CUtensorMap map_z,
+                                                          const __grid_constant__ CUtensorMap map_p,
                                                           const MlpParams p) {
   typedef MlpCfg<C> T;
   extern __shared__ __align__(1024) uint8_t mlp_smem_raw[];
@@ -82,20 +85,25 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const __grid_constant_
   uint8_t* sA = smem;
   uint8_t* sW = smem + T::OffW;
   uint8_t* sP = smem + T::OffP;
+  uint8_t* sZ = smem + T::OffZ;
   float* sBias1 = reinterpret_cast<float*>(smem + T::OffBias);
   float* sBias2 = sBias1 + 4 * C;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + T::OffBars);
   uint64_t* a_full = bars;            // [2]
   uint64_t* a_empty = bars + 2;       // [2]
-  uint64_t* w_full = bars + 4;        // [2]
-  uint64_t* w_empty = bars + 6;       // [2]
+  uint64_t* wa_full = bars + 4;       // [2]  GEMM-a weight chunk (released as soon as GEMM-a retires)
+  uint64_t* wa_empty = bars + 6;      // [2]
   uint64_t* ta_full = bars + 8;       // [2]  GEMM-a accumulator ready
   uint64_t* ta_empty = bars + 10;     // [2]
   uint64_t* p_full = bars + 12;       // [2]  operand chunk written
   uint64_t* p_empty = bars + 14;      // [2]
-  uint64_t* tb_full = bars + 16;      // GEMM-b accumulator complete
-  uint64_t* tb_empty = bars + 17;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+  uint64_t* tb_full = bars + 26;      // [2]  GEMM-b accumulator of a tile complete
+  uint64_t* tb_empty = bars + 28;     // [2]
+  uint64_t* z_full = bars + 18;       // [2]  z chunk in shared memory (forward: written by the warps; backward: TMA)
+  uint64_t* z_empty = bars + 20;      // [2]
+  uint64_t* wb_full = bars + 22;      // [2]  GEMM-b weight chunk
+  uint64_t* wb_empty = bars + 24;     // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 30);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -103,15 +111,19 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const __grid_constant_
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_wa) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_wb) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_z) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_p) : "memory");
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < 2; ++s) {
       mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1);
-      mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1);
-      mbar_init(&ta_full[s], 1); mbar_init(&ta_empty[s], kEpiWarps);
-      mbar_init(&p_full[s], kEpiWarps); mbar_init(&p_empty[s], 1);
+      mbar_init(&wa_full[s], 1); mbar_init(&wa_empty[s], 1);
+      mbar_init(&wb_full[s], 1); mbar_init(&wb_empty[s], 1);
+      mbar_init(&tb_full[s], 1); mbar_init(&tb_empty[s], kEpiWarps);
+      mbar_init(&ta_full[s], 1); mbar_init(&ta_empty[s], kEpiWarps / 2);
+      mbar_init(&p_full[s], kEpiWarps / 2); mbar_init(&p_empty[s], p.p_out ? 2 : 1);   // UMMA (+ the TMA store)
+      mbar_init(&z_full[s], MODE == 0 ? kEpiWarps / 2 : 1); mbar_init(&z_empty[s], MODE == 0 ? 1 : kEpiWarps / 2);
     }
-    mbar_init(tb_full, 1); mbar_init(tb_empty, kEpiWarps);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -126,49 +138,82 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_b = tmem_base;                       // acc_b: columns [0, C)
-  const uint32_t tmem_a = tmem_base + (uint32_t)C;         // acc_a[s]: columns C + 64 s
+  const uint32_t tmem_b = tmem_base;                       // acc_b[b]: columns [b C, (b+1) C), b = tile parity
+  const uint32_t tmem_a = tmem_base + (uint32_t)(2 * C);   // acc_a[s]: columns 2C + 64 s
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (elect_one()) {
+    // ------------------------------------------------------------------ TMA producers
+    // Three independent streams, one lane each, so that a stream blocked on its ring never delays another one:
+    // lane 0 the A tiles and the GEMM-a weight chunks (slot free as soon as GEMM-a retires: runs a full chunk ahead),
+    // lane 1 the GEMM-b weight chunks (slot free when GEMM-b of two chunks ago retires), lane 2 the saved
+    // pre-activation chunks of the backward pass.
+    if (lane == 0) {
       uint32_t g = 0;
       int t = 0;
       for (int tile = blockIdx.x; tile < p.tiles_m; tile += gridDim.x, ++t) {
         const int as = t % T::AStages;
         const uint32_t aph = (uint32_t)(t / T::AStages) & 1u;
-        mbar_wait(&a_empty[as], aph ^ 1u);
+        mbar_wait_relaxed(&a_empty[as], aph ^ 1u);
         mbar_expect_tx(&a_full[as], T::ABytes);
 #pragma unroll
         for (int kb = 0; kb < T::KB; ++kb)
           tma_load_2d(&map_a, &a_full[as], sA + as * T::ABytes + kb * (128 * 128), kb * 64, tile * 128);
         for (int j = 0; j < T::NC; ++j, ++g) {
           const int ws = (int)(g & 1u);
-          const uint32_t wph = (g >> 1) & 1u;
-          mbar_wait(&w_empty[ws], wph ^ 1u);
-          uint8_t* w = sW + ws * T::WStageBytes;
-          mbar_expect_tx(&w_full[ws], T::WStageBytes);
+          mbar_wait_relaxed(&wa_empty[ws], ((g >> 1) & 1u) ^ 1u);
+          uint8_t* wa = sW + ws * T::WaBytes;
+          mbar_expect_tx(&wa_full[ws], T::WaBytes);
 #pragma unroll
           for (int kb = 0; kb < T::KB; ++kb)
-            tma_load_2d(&map_wa, &w_full[ws], w + kb * (kChunk * 128), kb * 64, j * kChunk);
-          tma_load_2d(&map_wb, &w_full[ws], w + T::WaBytes, j * kChunk, 0);
+            tma_load_2d(&map_wa, &wa_full[ws], wa + kb * (kChunk * 128), kb * 64, j * kChunk);
+        }
+      }
+    } else if (lane == 1) {
+      uint32_t g = 0;
+      for (int tile = blockIdx.x; tile < p.tiles_m; tile += gridDim.x) {
+        for (int j = 0; j < T::NC; ++j, ++g) {
+          const int ws = (int)(g & 1u);
+          mbar_wait_relaxed(&wb_empty[ws], ((g >> 1) & 1u) ^ 1u);
+          mbar_expect_tx(&wb_full[ws], T::WbBytes);
+          tma_load_2d(&map_wb, &wb_full[ws], sW + 2 * T::WaBytes + ws * T::WbBytes, j * kChunk, 0);
+        }
+      }
+    } else if (lane == 2 && MODE == 1) {
+      uint32_t g = 0;
+      for (int tile = blockIdx.x; tile < p.tiles_m; tile += gridDim.x) {
+        for (int j = 0; j < T::NC; ++j, ++g) {
+          const int ws = (int)(g & 1u);
+          mbar_wait_relaxed(&z_empty[ws], ((g >> 1) & 1u) ^ 1u);
+          mbar_expect_tx(&z_full[ws], T::PBytes);
+          tma_load_2d(&map_z, &z_full[ws], sZ + ws * T::PBytes, j * kChunk, tile * 128);
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
+    // Issue order: GEMM-a of chunk g+2 goes out as soon as the elementwise stage has read acc_a of chunk g (ta_empty),
+    // i.e. BEFORE waiting for that stage to finish chunk g -- so a group of epilogue warps always finds its next
+    // accumulator complete and never waits for the tensor pipe; GEMM-b of chunk g follows when its operand is written.
     const uint32_t idesc_a = make_idesc(128, kChunk);
     const uint32_t idesc_b = make_idesc(128, C);
-    uint32_t g = 0;
-    int t = 0;
-    auto gemm_a = [&](uint32_t gg, const uint8_t* a_tile) {
+    const int my_tiles = (p.tiles_m - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const uint32_t total = (uint32_t)my_tiles * T::NC;     // chunks this CTA walks through
+    uint32_t a_waited = 0;                                 // A tiles whose arrival this warp has observed
+    auto gemm_a = [&](uint32_t gg) {
       const int s = (int)(gg & 1u);
       const uint32_t ph = (gg >> 1) & 1u;
-      mbar_wait(&w_full[s], ph);                           // weight chunk gg landed
+      const uint32_t tt = gg / T::NC;                      // local tile index of chunk gg
+      const int as = (int)(tt % T::AStages);
+      if (tt >= a_waited) {                                // first chunk of a tile: its A tile must have landed
+        mbar_wait(&a_full[as], (tt / T::AStages) & 1u);
+        a_waited = tt + 1;
+      }
+      mbar_wait(&wa_full[s], ph);                          // weight chunk gg landed
       mbar_wait(&ta_empty[s], ph ^ 1u);                    // the elementwise stage has drained acc_a[s]
       tc_fence_after();
       if (elect_one()) {
-        const uint8_t* wa = sW + s * T::WStageBytes;
+        const uint8_t* a_tile = sA + as * T::ABytes;
+        const uint8_t* wa = sW + s * T::WaBytes;
 #pragma unroll
         for (int k = 0; k < T::KSteps; ++k) {
           const uint64_t da = make_desc(a_tile + (k >> 2) * (128 * 128)) + (uint64_t)(2 * (k & 3));
@@ -176,140 +221,214 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const __grid_constant_
           umma(tmem_a + (uint32_t)(s * kChunk), da, db, idesc_a, k != 0);
         }
         umma_commit(&ta_full[s]);
+        umma_commit(&wa_empty[s]);
+        if (gg % T::NC == T::NC - 1) umma_commit(&a_empty[as]);   // last GEMM-a of the tile: A tile free when it retires
       }
       __syncwarp();
     };
-    for (int tile = blockIdx.x; tile < p.tiles_m; tile += gridDim.x, ++t) {
-      const int as = t % T::AStages;
-      const uint32_t aph = (uint32_t)(t / T::AStages) & 1u;
-      const uint8_t* a_tile = sA + as * T::ABytes;
-      mbar_wait(&a_full[as], aph);
+    auto gemm_b = [&](uint32_t gg) {
+      const int s = (int)(gg & 1u);
+      const uint32_t ph = (gg >> 1) & 1u;
+      const uint32_t tt = gg / T::NC;
+      const int j = (int)(gg % T::NC);
+      mbar_wait(&wb_full[s], ph);
+      mbar_wait(&p_full[s], ph);                           // operand chunk written by its group of epilogue warps
+      const int bb = (int)(tt & 1u);
+      if (j == 0) mbar_wait(&tb_empty[bb], ((tt >> 1) & 1u) ^ 1u);   // the tile two back has been drained from acc_b[bb]
       tc_fence_after();
-      gemm_a(g, a_tile);
-      for (int j = 0; j < T::NC; ++j, ++g) {
-        if (j + 1 < T::NC) {
-          gemm_a(g + 1, a_tile);
-        } else {
-          if (elect_one()) umma_commit(&a_empty[as]);      // every GEMM-a of this tile issued: A tile free when they retire
-          __syncwarp();
-        }
-        const int s = (int)(g & 1u);
-        const uint32_t ph = (g >> 1) & 1u;
-        mbar_wait(&p_full[s], ph);                         // operand chunk written by the 16 epilogue warps
-        if (j == 0) mbar_wait(tb_empty, (uint32_t)(t & 1) ^ 1u);   // previous tile's acc_b drained
-        tc_fence_after();
-        if (elect_one()) {
-          const uint64_t da = make_desc(sP + s * T::PBytes);
-          const uint64_t db = make_desc(sW + s * T::WStageBytes + T::WaBytes);
+      if (elect_one()) {
+        const uint64_t da = make_desc(sP + s * T::PBytes);
+        const uint64_t db = make_desc(sW + 2 * T::WaBytes + s * T::WbBytes);
 #pragma unroll
-          for (int k = 0; k < kChunk / 16; ++k)
-            umma(tmem_b, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc_b, (j | k) != 0);
-          umma_commit(&p_empty[s]);
-          umma_commit(&w_empty[s]);
-          if (j == T::NC - 1) umma_commit(tb_full);
-        }
-        __syncwarp();
+        for (int k = 0; k < kChunk / 16; ++k)
+          umma(tmem_b + (uint32_t)(bb * C), da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc_b, (j | k) != 0);
+        umma_commit(&p_empty[s]);
+        umma_commit(&wb_empty[s]);
+        if (j == T::NC - 1) umma_commit(&tb_full[bb]);
       }
+      __syncwarp();
+    };
+    if (total > 0) {
+      gemm_a(0);
+      gemm_a(1);
+      for (uint32_t g = 0; g < total; ++g) {
+        const bool next_tile = (g % T::NC) + 2 >= (uint32_t)T::NC;   // chunk g+2 belongs to the next tile
+        if (g + 2 < total && !next_tile) gemm_a(g + 2);
+        gemm_b(g);
+        if (g + 2 < total && next_tile) gemm_a(g + 2);     // may wait for the next A tile: keep GEMM-b ahead of it
+      }
+    }
+  } else if (warp == 2 || warp == 3) {
+    // ------------------------------------------------------------------ TMA stores of the hidden chunks (z forward; a / dz)
+    // warp 2 serves chunk parity 0, warp 3 parity 1: bulk-async groups are per thread, so each waits only for its own
+    // buffer to be read before handing it back.
+    if ((MODE == 0 || p.p_out != nullptr) && elect_one()) {
+      const int s = warp - 2;
+      for (int tile = blockIdx.x, t = 0; tile < p.tiles_m; tile += gridDim.x, ++t) {
+        for (int j = s; j < T::NC; j += 2) {
+          const uint32_t g = (uint32_t)(t * T::NC + j);
+          const uint32_t ph = (g >> 1) & 1u;
+          if (MODE == 0) {
+            mbar_wait_relaxed(&z_full[s], ph);               // the warps' writes are fenced into the async proxy
+            tma_store_2d(&map_z, sZ + s * T::PBytes, j * kChunk, tile * 128);   // rows past M are clipped
+            tma_store_commit();
+            tma_store_wait_read();                           // shared memory has been read: the buffer may be rewritten
+            mbar_arrive(&z_empty[s]);
+          }
+          if (p.p_out != nullptr) {
+            mbar_wait_relaxed(&p_full[s], ph);
+            tma_store_2d(&map_p, sP + s * T::PBytes, j * kChunk, tile * 128);
+            tma_store_commit();
+            tma_store_wait_read();
+            mbar_arrive(&p_empty[s]);
+          }
+        }
+      }
+      tma_store_wait_all();                                  // writes complete before the CTA exits
     }
   } else if (warp >= kEpiWarp0) {
     // ------------------------------------------------------------------ elementwise stage + final epilogue
+    // Two groups of 8 warps: group s owns chunk parity s, i.e. accumulator acc_a[s] and operand buffer P[s].  The
+    // groups run half a chunk period out of phase, so the latency one group exposes (TMEM load, proxy fence, barrier
+    // round trips) is covered by the other group's GELU arithmetic on the same schedulers.
     const int q = warp & 3;                                // TMEM lane quarter this warp may access
-    const int sub = (warp - kEpiWarp0) >> 2;               // 16-column slice of the chunk
+    const int grp = (warp - kEpiWarp0) >> 3;               // chunk parity handled by this warp
+    const int sub = ((warp - kEpiWarp0) >> 2) & 1;         // 32-column half of the chunk
+    const int sub4 = (warp - kEpiWarp0) >> 2;              // 0..3: slice of the final epilogue
     const int r = q * 32 + lane;                           // row inside the tile
     const uint32_t t_lane = (uint32_t)(q * 32) << 16;
-    const int pc = sub * 2;                                // first 16-byte piece of this thread in the 128-byte operand row
-    uint32_t g = 0;
-    int t = 0;
-    for (int tile = blockIdx.x; tile < p.tiles_m; tile += gridDim.x, ++t) {
-      const int row = tile * 128 + r;
-      const bool row_ok = row < p.M;
-      bf16* zrow = p.z + (int64_t)row * (4 * C) + sub * 16;
-      bf16* prow = p.p_out ? p.p_out + (int64_t)row * (4 * C) + sub * 16 : nullptr;
-      for (int j = 0; j < T::NC; ++j, ++g) {
-        const int s = (int)(g & 1u);
-        const uint32_t ph = (g >> 1) & 1u;
-        uint4 zlo = make_uint4(0u, 0u, 0u, 0u), zhi = zlo;
-        if (MODE == 1 && row_ok) {                          // saved pre-activation: in flight while GEMM-a finishes
-          zlo = __ldcs(reinterpret_cast<const uint4*>(zrow + j * kChunk));
-          zhi = __ldcs(reinterpret_cast<const uint4*>(zrow + j * kChunk) + 1);
-        }
-        mbar_wait(&ta_full[s], ph);
-        tc_fence_after();
-        uint32_t v[16];
-        tmem_ld16(tmem_a + t_lane + (uint32_t)(s * kChunk + sub * 16), v);
-        tmem_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&ta_empty[s]);
-        float f[16], zf[16];
+    const int pc = sub * 4;                                // first 16-byte piece of this thread in the 128-byte operand row
+    const int s = grp;
+    constexpr int kPieces = (C / 16 + 3) / 4;                // 16-column pieces of the result per warp (strided by 4)
+    uint4 res[kPieces][2];
+    // residual rows of a finished tile: requested one chunk of arithmetic before they are consumed
+    auto final_prefetch = [&](int tile_id) {
+      const int orow = tile_id * 128 + r;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
-        const float* b1 = sBias1 + j * kChunk + sub * 16;
-        uint4 lo = pack8(f), hi = pack8(f + 8);             // the value the unfused path stores in bf16 (z / da)
-        if (MODE == 0) {
-          if (row_ok) {
-            reinterpret_cast<uint4*>(zrow + j * kChunk)[0] = lo;
-            reinterpret_cast<uint4*>(zrow + j * kChunk)[1] = hi;
-          }
-          unpack8(lo, f); unpack8(hi, f + 8);
-#pragma unroll
-          for (int i = 0; i < 16; i += 4) {
-            const float4 b = *reinterpret_cast<const float4*>(b1 + i);
-            f[i] = b200at_gelu(f[i] + b.x); f[i + 1] = b200at_gelu(f[i + 1] + b.y);
-            f[i + 2] = b200at_gelu(f[i + 2] + b.z); f[i + 3] = b200at_gelu(f[i + 3] + b.w);
-          }
-        } else {
-          unpack8(lo, f); unpack8(hi, f + 8);
-          unpack8(zlo, zf); unpack8(zhi, zf + 8);
-#pragma unroll
-          for (int i = 0; i < 16; i += 4) {
-            const float4 b = *reinterpret_cast<const float4*>(b1 + i);
-            f[i] *= b200at_gelu_grad(zf[i] + b.x); f[i + 1] *= b200at_gelu_grad(zf[i + 1] + b.y);
-            f[i + 2] *= b200at_gelu_grad(zf[i + 2] + b.z); f[i + 3] *= b200at_gelu_grad(zf[i + 3] + b.w);
-          }
+      for (int i = 0; i < kPieces; ++i) {
+        const int piece = sub4 + 4 * i;
+        res[i][0] = res[i][1] = make_uint4(0u, 0u, 0u, 0u);
+        if (MODE == 0 && p.residual != nullptr && orow < p.M && piece < C / 16) {
+          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + (int64_t)orow * C + piece * 16);
+          res[i][0] = __ldg(rp); res[i][1] = __ldg(rp + 1);
         }
-        lo = pack8(f); hi = pack8(f + 8);
-        if (prow && row_ok) {
-          reinterpret_cast<uint4*>(prow + j * kChunk)[0] = lo;
-          reinterpret_cast<uint4*>(prow + j * kChunk)[1] = hi;
-        }
-        mbar_wait(&p_empty[s], ph ^ 1u);                    // GEMM-b that read this buffer two chunks ago has retired
-        uint8_t* prow_s = sP + s * T::PBytes + r * 128;     // K-major SWIZZLE_128B: 16-byte piece index ^ (row & 7)
-        *reinterpret_cast<uint4*>(prow_s + (((pc) ^ (r & 7)) << 4)) = lo;
-        *reinterpret_cast<uint4*>(prow_s + (((pc + 1) ^ (r & 7)) << 4)) = hi;
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the UMMA reads
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[s]);
       }
-      // ---- final epilogue of the tile: acc_b (+ bias2 + residual) -> bf16 -> global
-      mbar_wait(tb_full, (uint32_t)(t & 1));
+    };
+    // ---- final epilogue of a tile: acc_b[tile parity] (+ bias2 + residual) -> bf16 -> global
+    auto final_epilogue = [&](int tt, int tile_id) {
+      const int bb = tt & 1;
+      const int orow = tile_id * 128 + r;
+      const bool ok = orow < p.M;
+      mbar_wait(&tb_full[bb], (uint32_t)(tt >> 1) & 1u);
       tc_fence_after();
-      for (int piece = sub; piece < C / 16; piece += 4) {
-        uint32_t v[16];
-        tmem_ld16(tmem_b + t_lane + (uint32_t)(piece * 16), v);
-        tmem_ld_wait();
-        float f[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
-        if (MODE == 0) {
+      for (int i = 0; i < kPieces; ++i) {
+        const int piece = sub4 + 4 * i;
+        if (piece < C / 16) {
+          uint32_t v[16];
+          tmem_ld16(tmem_b + t_lane + (uint32_t)(bb * C + piece * 16), v);
+          tmem_ld_wait();
+          float f[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) f[i] += sBias2[piece * 16 + i];
-          if (p.residual && row_ok) {
-            float rr[16];
-            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + (int64_t)row * C + piece * 16);
-            unpack8(__ldg(rp), rr); unpack8(__ldg(rp + 1), rr + 8);
+          for (int k = 0; k < 16; ++k) f[k] = __uint_as_float(v[k]);
+          if (MODE == 0) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) f[i] += rr[i];
+            for (int k = 0; k < 16; ++k) f[k] += sBias2[piece * 16 + k];
+            if (p.residual != nullptr) {
+              float rr[16];
+              unpack8(res[i][0], rr); unpack8(res[i][1], rr + 8);
+#pragma unroll
+              for (int k = 0; k < 16; ++k) f[k] += rr[k];
+            }
           }
-        }
-        if (row_ok) {
-          uint4* op = reinterpret_cast<uint4*>(p.out + (int64_t)row * C + piece * 16);
-          op[0] = pack8(f); op[1] = pack8(f + 8);
+          if (ok) {
+            uint4* op = reinterpret_cast<uint4*>(p.out + (int64_t)orow * C + piece * 16);
+            op[0] = pack8(f); op[1] = pack8(f + 8);
+          }
         }
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tb_empty);
+      if (lane == 0) mbar_arrive(&tb_empty[bb]);
+    };
+    int t = 0;
+    for (int tile = blockIdx.x; tile < p.tiles_m; tile += gridDim.x, ++t) {
+      for (int j = grp; j < T::NC; j += 2) {
+        const uint32_t g = (uint32_t)(t * T::NC + j);
+        const uint32_t ph = (g >> 1) & 1u;
+        if (j == grp && t > 0) final_prefetch(tile - (int)gridDim.x);
+        uint8_t* zrow_s = sZ + s * T::PBytes + r * 128;     // same swizzled row layout as the operand buffer
+        uint4 zq[4];
+        if (MODE == 1) {                                    // saved pre-activation chunk, landed by TMA
+          mbar_wait(&z_full[s], ph);
+#pragma unroll
+          for (int h = 0; h < 4; ++h) zq[h] = *reinterpret_cast<const uint4*>(zrow_s + (((pc + h) ^ (r & 7)) << 4));
+          // the loads must have RETURNED before the buffer is handed back to the TMA producer (which now refills it
+          // at once): consuming the registers here makes the warp wait for them
+          asm volatile("" ::"r"(zq[0].x), "r"(zq[0].y), "r"(zq[0].z), "r"(zq[0].w), "r"(zq[1].x), "r"(zq[1].y),
+                       "r"(zq[1].z), "r"(zq[1].w), "r"(zq[2].x), "r"(zq[2].y), "r"(zq[2].z), "r"(zq[2].w), "r"(zq[3].x),
+                       "r"(zq[3].y), "r"(zq[3].z), "r"(zq[3].w)
+                       : "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&z_empty[s]);
+        } else {
+          mbar_wait(&z_empty[s], ph ^ 1u);                  // the TMA store of two chunks ago has read the buffer
+        }
+        mbar_wait(&ta_full[s], ph);
+        tc_fence_after();
+        uint32_t v[32];
+        tmem_ld16(tmem_a + t_lane + (uint32_t)(s * kChunk + sub * 32), v);
+        tmem_ld16(tmem_a + t_lane + (uint32_t)(s * kChunk + sub * 32 + 16), v + 16);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ta_empty[s]);
+        const float* b1 = sBias1 + j * kChunk + sub * 32;
+        uint4 stored[4];                                    // the values the unfused path stores in bf16 (z / da)
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          float f[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[h * 8 + i]);
+          stored[h] = pack8(f);
+          if (MODE == 0) *reinterpret_cast<uint4*>(zrow_s + (((pc + h) ^ (r & 7)) << 4)) = stored[h];
+        }
+        if (MODE == 0) {                                    // z chunk complete in shared memory -> TMA store (warp 2 / 3)
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&z_full[s]);
+        }
+        mbar_wait(&p_empty[s], ph ^ 1u);                    // GEMM-b (and the TMA store) of two chunks ago have read it
+        uint8_t* prow_s = sP + s * T::PBytes + r * 128;     // K-major SWIZZLE_128B: 16-byte piece index ^ (row & 7)
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {                       // 8 columns at a time
+          float f[8];
+          unpack8(stored[h], f);
+          const float4 ba = *reinterpret_cast<const float4*>(b1 + h * 8);
+          const float4 bb = *reinterpret_cast<const float4*>(b1 + h * 8 + 4);
+          const float bias[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+          if (MODE == 0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = b200at_gelu(f[i] + bias[i]);
+          } else {
+            float zf[8];
+            unpack8(zq[h], zf);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] *= b200at_gelu_grad(zf[i] + bias[i]);
+          }
+          *reinterpret_cast<uint4*>(prow_s + (((pc + h) ^ (r & 7)) << 4)) = pack8(f);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the UMMA reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[s]);
+        // the previous tile's result leaves after this warp's first chunk of the next tile: its GEMM-b has long
+        // retired by then (no wait), and the two groups drain at different times
+        if (j == grp && t > 0) final_epilogue(t - 1, tile - (int)gridDim.x);
+      }
+    }
+    if (t > 0) {
+      final_prefetch((int)blockIdx.x + (t - 1) * (int)gridDim.x);
+      final_epilogue(t - 1, (int)blockIdx.x + (t - 1) * (int)gridDim.x);
     }
   }
   tc_fence_before();
@@ -322,15 +441,15 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const __grid_constant_
 }
 
 template <int C, int MODE>
-int launch(const CUtensorMap& ma, const CUtensorMap& mwa, const CUtensorMap& mwb, const MlpParams& p, int grid,
-           cudaStream_t s) {
+int launch(const CUtensorMap& ma, const CUtensorMap& mwa, const CUtensorMap& mwb, const CUtensorMap& mz,
+           const CUtensorMap& mp, const MlpParams& p, int grid, cudaStream_t s) {
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(mlp_kernel<C, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, MlpCfg<C>::Smem);
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
-  mlp_kernel<C, MODE><<<grid, kThreads, MlpCfg<C>::Smem, s>>>(ma, mwa, mwb, p);
+  mlp_kernel<C, MODE><<<grid, kThreads, MlpCfg<C>::Smem, s>>>(ma, mwa, mwb, mz, mp, p);
   return (int)cudaGetLastError();
 }
 
@@ -351,15 +470,16 @@ extern "C" int b200at_mlp_fused(const void* a, const void* wa, const void* wb, c
   p.bias1 = bias1; p.bias2 = bias2; p.residual = (const bf16*)residual;
   p.z = (bf16*)z; p.p_out = (bf16*)p_out; p.out = (bf16*)out;
   p.M = (int)M; p.tiles_m = (int)((M + 127) / 128);
-  CUtensorMap ma, mwa, mwb;
+  CUtensorMap ma, mwa, mwb, mz, mp;
   if (!make_map_kmajor(&ma, a, M, C, 128) || !make_map_kmajor(&mwa, wa, 4 * C, C, kChunk) ||
-      !make_map_kmajor(&mwb, wb, C, 4 * C, (int)C))
+      !make_map_kmajor(&mwb, wb, C, 4 * C, (int)C) || !make_map_kmajor(&mz, z, M, 4 * C, 128) ||
+      !make_map_kmajor(&mp, p_out ? p_out : z, M, 4 * C, 128))
     return (int)cudaErrorUnknown;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = p.tiles_m < sms ? p.tiles_m : sms;
   cudaStream_t s = (cudaStream_t)stream;
-  if (C == 96) return backward ? launch<96, 1>(ma, mwa, mwb, p, grid, s) : launch<96, 0>(ma, mwa, mwb, p, grid, s);
-  return backward ? launch<192, 1>(ma, mwa, mwb, p, grid, s) : launch<192, 0>(ma, mwa, mwb, p, grid, s);
+  if (C == 96) return backward ? launch<96, 1>(ma, mwa, mwb, mz, mp, p, grid, s) : launch<96, 0>(ma, mwa, mwb, mz, mp, p, grid, s);
+  return backward ? launch<192, 1>(ma, mwa, mwb, mz, mp, p, grid, s) : launch<192, 0>(ma, mwa, mwb, mz, mp, p, grid, s);
 }
