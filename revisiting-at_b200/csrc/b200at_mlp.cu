@@ -23,6 +23,7 @@
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "b200at_gelu.cuh"
 #include "b200at_tcgen05.cuh"
@@ -70,6 +71,7 @@ struct MlpParams {
   bf16* p_out;          // [M][4C] or null: forward a = GELU(z + b1); backward dz
   bf16* out;            // [M][C]
   int M, tiles_m;
+  int debug;            // B200AT_MLP_DEBUG bits (race hunting): 1 final epilogue at the tile end, 2 skip the P store, 4 plain waits in the store warps
 };
 
 template <int C, int MODE>   // MODE 0 forward, 1 backward
@@ -276,8 +278,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const __grid_constant_
             mbar_arrive(&z_empty[s]);
           }
           if (p.p_out != nullptr) {
-            mbar_wait_relaxed(&p_full[s], ph);
-            tma_store_2d(&map_p, sP + s * T::PBytes, j * kChunk, tile * 128);
+            if (p.debug & 4) mbar_wait(&p_full[s], ph); else mbar_wait_relaxed(&p_full[s], ph);
+            if (!(p.debug & 2)) tma_store_2d(&map_p, sP + s * T::PBytes, j * kChunk, tile * 128);
             tma_store_commit();
             tma_store_wait_read();
             mbar_arrive(&p_empty[s]);
@@ -299,6 +301,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const __grid_constant_
     const uint32_t t_lane = (uint32_t)(q * 32) << 16;
     const int pc = sub * 4;                                // first 16-byte piece of this thread in the 128-byte operand row
     const int s = grp;
+    const uint32_t zrow_a = smem_u32(sZ) + (uint32_t)(s * T::PBytes + r * 128);   // this thread's row of the z chunk buffer
+    const uint32_t prow_a = smem_u32(sP) + (uint32_t)(s * T::PBytes + r * 128);   // ... of the operand chunk buffer
+    const uint32_t swz = (uint32_t)(r & 7);                 // SWIZZLE_128B: 16-byte piece index ^ (row & 7)
+    const uint32_t bias1_a = smem_u32(sBias1), bias2_a = smem_u32(sBias2);
+    const uint32_t scratch_a = smem_u32(bars + 31);
     constexpr int kPieces = (C / 16 + 3) / 4;                // 16-column pieces of the result per warp (strided by 4)
     uint4 res[kPieces][2];
     // residual rows of a finished tile: requested one chunk of arithmetic before they are consumed
@@ -333,7 +340,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const __grid_constant_
           for (int k = 0; k < 16; ++k) f[k] = __uint_as_float(v[k]);
           if (MODE == 0) {
 #pragma unroll
-            for (int k = 0; k < 16; ++k) f[k] += sBias2[piece * 16 + k];
+            for (int k = 0; k < 16; k += 4) {
+              const uint4 b = lds128(bias2_a + (uint32_t)((piece * 16 + k) * 4));
+              f[k] += __uint_as_float(b.x); f[k + 1] += __uint_as_float(b.y);
+              f[k + 2] += __uint_as_float(b.z); f[k + 3] += __uint_as_float(b.w);
+            }
             if (p.residual != nullptr) {
               float rr[16];
               unpack8(res[i][0], rr); unpack8(res[i][1], rr + 8);
@@ -357,18 +368,14 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const __grid_constant_
         const uint32_t g = (uint32_t)(t * T::NC + j);
         const uint32_t ph = (g >> 1) & 1u;
         if (j == grp && t > 0) final_prefetch(tile - (int)gridDim.x);
-        uint8_t* zrow_s = sZ + s * T::PBytes + r * 128;     // same swizzled row layout as the operand buffer
         uint4 zq[4];
         if (MODE == 1) {                                    // saved pre-activation chunk, landed by TMA
           mbar_wait(&z_full[s], ph);
 #pragma unroll
-          for (int h = 0; h < 4; ++h) zq[h] = *reinterpret_cast<const uint4*>(zrow_s + (((pc + h) ^ (r & 7)) << 4));
-          // the loads must have RETURNED before the buffer is handed back to the TMA producer (which now refills it
-          // at once): consuming the registers here makes the warp wait for them
-          asm volatile("" ::"r"(zq[0].x), "r"(zq[0].y), "r"(zq[0].z), "r"(zq[0].w), "r"(zq[1].x), "r"(zq[1].y),
-                       "r"(zq[1].z), "r"(zq[1].w), "r"(zq[2].x), "r"(zq[2].y), "r"(zq[2].z), "r"(zq[2].w), "r"(zq[3].x),
-                       "r"(zq[3].y), "r"(zq[3].z), "r"(zq[3].w)
-                       : "memory");
+          for (int h = 0; h < 4; ++h) zq[h] = lds128(zrow_a + ((((uint32_t)(pc + h)) ^ swz) << 4));
+          // the loads must have RETURNED before the buffer goes back to the TMA producer, which refills it at once
+          // (mbarrier.arrive does not wait for outstanding loads: seen as z of chunk g+2 in the registers of chunk g)
+          consume_loads(zq[0].x ^ zq[1].x ^ zq[2].x ^ zq[3].x, scratch_a);
           __syncwarp();
           if (lane == 0) mbar_arrive(&z_empty[s]);
         } else {
@@ -383,7 +390,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const __grid_constant_
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&ta_empty[s]);
-        const float* b1 = sBias1 + j * kChunk + sub * 32;
+        const uint32_t b1_a = bias1_a + (uint32_t)((j * kChunk + sub * 32) * 4);
         uint4 stored[4];                                    // the values the unfused path stores in bf16 (z / da)
 #pragma unroll
         for (int h = 0; h < 4; ++h) {
@@ -391,7 +398,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const __grid_constant_
 #pragma unroll
           for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[h * 8 + i]);
           stored[h] = pack8(f);
-          if (MODE == 0) *reinterpret_cast<uint4*>(zrow_s + (((pc + h) ^ (r & 7)) << 4)) = stored[h];
+          if (MODE == 0) sts128(zrow_a + ((((uint32_t)(pc + h)) ^ swz) << 4), stored[h]);
         }
         if (MODE == 0) {                                    // z chunk complete in shared memory -> TMA store (warp 2 / 3)
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -399,14 +406,13 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const __grid_constant_
           if (lane == 0) mbar_arrive(&z_full[s]);
         }
         mbar_wait(&p_empty[s], ph ^ 1u);                    // GEMM-b (and the TMA store) of two chunks ago have read it
-        uint8_t* prow_s = sP + s * T::PBytes + r * 128;     // K-major SWIZZLE_128B: 16-byte piece index ^ (row & 7)
 #pragma unroll
         for (int h = 0; h < 4; ++h) {                       // 8 columns at a time
           float f[8];
           unpack8(stored[h], f);
-          const float4 ba = *reinterpret_cast<const float4*>(b1 + h * 8);
-          const float4 bb = *reinterpret_cast<const float4*>(b1 + h * 8 + 4);
-          const float bias[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+          const uint4 ba = lds128(b1_a + (uint32_t)(h * 32)), bb = lds128(b1_a + (uint32_t)(h * 32 + 16));
+          const float bias[8] = {__uint_as_float(ba.x), __uint_as_float(ba.y), __uint_as_float(ba.z), __uint_as_float(ba.w),
+                                 __uint_as_float(bb.x), __uint_as_float(bb.y), __uint_as_float(bb.z), __uint_as_float(bb.w)};
           if (MODE == 0) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) f[i] = b200at_gelu(f[i] + bias[i]);
@@ -416,17 +422,18 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const __grid_constant_
 #pragma unroll
             for (int i = 0; i < 8; ++i) f[i] *= b200at_gelu_grad(zf[i] + bias[i]);
           }
-          *reinterpret_cast<uint4*>(prow_s + (((pc + h) ^ (r & 7)) << 4)) = pack8(f);
+          sts128(prow_a + ((((uint32_t)(pc + h)) ^ swz) << 4), pack8(f));
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the UMMA reads
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[s]);
         // the previous tile's result leaves after this warp's first chunk of the next tile: its GEMM-b has long
         // retired by then (no wait), and the two groups drain at different times
-        if (j == grp && t > 0) final_epilogue(t - 1, tile - (int)gridDim.x);
+        if (!(p.debug & 1) && j == grp && t > 0) final_epilogue(t - 1, tile - (int)gridDim.x);
       }
+      if (p.debug & 1) final_epilogue(t, tile);
     }
-    if (t > 0) {
+    if (t > 0 && !(p.debug & 1)) {
       final_prefetch((int)blockIdx.x + (t - 1) * (int)gridDim.x);
       final_epilogue(t - 1, (int)blockIdx.x + (t - 1) * (int)gridDim.x);
     }
@@ -470,6 +477,7 @@ extern "C" int b200at_mlp_fused(const void* a, const void* wa, const void* wb, c
   p.bias1 = bias1; p.bias2 = bias2; p.residual = (const bf16*)residual;
   p.z = (bf16*)z; p.p_out = (bf16*)p_out; p.out = (bf16*)out;
   p.M = (int)M; p.tiles_m = (int)((M + 127) / 128);
+  { const char* e = getenv("B200AT_MLP_DEBUG"); p.debug = e ? atoi(e) : 0; }
   CUtensorMap ma, mwa, mwb, mz, mp;
   if (!make_map_kmajor(&ma, a, M, C, 128) || !make_map_kmajor(&mwa, wa, 4 * C, C, kChunk) ||
       !make_map_kmajor(&mwb, wb, C, 4 * C, (int)C) || !make_map_kmajor(&mz, z, M, 4 * C, 128) ||

@@ -70,6 +70,29 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void*
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// explicit shared-space 16-byte accesses on a 32-bit shared address (pointer arithmetic on the re-aligned dynamic
+// shared-memory base makes the compiler fall back to generic LD.E / ST.E, with their descriptor moves and latency)
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+// Stall until the loads that produced `dep` have RETURNED: a data-dependent (practically never true) predicated store,
+// which the assembler can neither fold nor drop.  Needed before a shared-memory buffer is handed back to an
+// asynchronous writer (TMA): mbarrier.arrive does not wait for this warp's outstanding loads.
+__device__ __forceinline__ void consume_loads(uint32_t dep, uint32_t scratch_addr) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.eq.u32 p, %1, 0x9e3779b9;\n"
+      "@p st.shared.u32 [%0], %1;\n"
+      "}\n" ::"r"(scratch_addr),
+      "r"(dep)
+      : "memory");
+}
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile(
