@@ -101,6 +101,12 @@ int b200at_stem0_bwd_input(const void* dy, const float* x, const float* mean3, c
 int b200at_gemm_bf16(const void* a, const void* b, void* c, void* c2, const void* aux, const float* bias,
                      int64_t M, int64_t N, int64_t K, int epilogue, void* stream);
 
+/* The ImageNormalizer (utils_architecture.py:86-98) in front of the TRAINING forward's first (library) convolution, with
+ * the cast and the layout change: y[B][H][W][3] bf16 = (x[B][3][H][W] - mean) / std, fp32 arithmetic rounded once.
+ * mean3 / std3: 3 host floats each, null = identity. */
+int b200at_normalize_nhwc_bf16(const float* x, const float* mean3, const float* std3, void* y, int64_t B, int64_t H,
+                               int64_t W, void* stream);
+
 /* The whole MLP of a ConvNeXt block as one tcgen05 kernel per direction (models/convnext.py:42-49: pwconv1 -> GELU ->
  * pwconv2 -> layer scale -> + residual), hidden activation kept on chip:
  *   backward == 0:  out = residual + GELU(a wa^T + bias1) wb^T + bias2      a = LN output t2 [M][C], wa = W1 [4C][C],

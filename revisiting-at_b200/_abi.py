@@ -105,6 +105,7 @@ def _declare(L):
         'b200at_gemm_bf16': [P, P, P, P, P, P, I64, I64, I64, I, P],
         'b200at_mlp_fused_supported': [I64],
         'b200at_mlp_fused': [P, P, P, P, P, P, P, P, P, I64, I64, I, P],
+        'b200at_normalize_nhwc_bf16': [P, P, P, P, I64, I64, I64, P],
         'b200at_stem0_fwd': [P, P, P, P, P, P, P, P, I64, I64, I64, I64, F, P],
         'b200at_stem0_bwd_input': [P, P, P, P, P, P, P, P, P, I64, I64, I64, I64, F, P],
         'b200at_attn_fwd': [P, P, P, I64, I64, I64, F, P],
@@ -397,6 +398,16 @@ def stem0_fwd(x, mean3, std3, wk, bias, ln_w, ln_b, y, eps=1e-6):
         _check(lib().b200at_stem0_fwd(_x_nchw(x), m, sd, _par(wk, 'wk', 27 * C0), _par(bias, 'bias', C0),
                                       _par(ln_w, 'ln_w', C0), _par(ln_b, 'ln_b', C0), _act(y, 'y'), B, H, W, C0, eps,
                                       _stream()), 'stem0_fwd')
+
+
+def normalize_nhwc_bf16(x, mean3, std3, y):
+    """y[B,H,W,3] bf16 = (x[B,3,H,W] - mean) / std (fp32 arithmetic, one rounding); mean3 / std3: 3 python floats or None."""
+    B, _, H, W = x.shape
+    if tuple(y.shape) != (B, H, W, 3):
+        raise B200atError(f'normalize_nhwc_bf16: y shape {tuple(y.shape)}')
+    with _Timed('normalize_nhwc_bf16'):
+        _check(lib().b200at_normalize_nhwc_bf16(_x_nchw(x), _host3(mean3), _host3(std3), _act(y, 'y'), B, H, W, _stream()),
+               'normalize_nhwc_bf16')
 
 
 def stem0_bwd_input(dy, x, mean3, std3, wk, bias, ln_w, ln_b, dx, eps=1e-6):

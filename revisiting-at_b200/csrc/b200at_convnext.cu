@@ -555,6 +555,7 @@ __global__ void __launch_bounds__(256) dwconv7_wgrad_kernel(const bf16* __restri
                                                             int W, int C, int tiles_w, int tiles_h) {
   __shared__ __align__(16) bf162 tile[kDwIn][kDwIn][kDwCh / 2];
   __shared__ float2 red[16][kDwCh / 2];
+  __shared__ float2 red7[7][16][kDwCh / 2];
   const int cp = threadIdx.x & 15, t = threadIdx.x >> 4;
   const int cgroups = C / kDwCh;
   int bid = blockIdx.x;
@@ -587,7 +588,8 @@ __global__ void __launch_bounds__(256) dwconv7_wgrad_kernel(const bf16* __restri
       g[r] = __bfloat1622float2(*reinterpret_cast<const bf162*>(gin + ((int64_t)(h0 + r) * W + w0 + t) * C + c0 + cp * 2));
     gsum.x += g[r].x; gsum.y += g[r].y;
   }
-  // taps are produced one tap-column j at a time; reduce over the 16 column-threads through shared memory
+  // taps are produced one tap-column j at a time (7 taps per thread); the 16 column-threads' partial sums of all 7
+  // go to shared memory at once and 7 x 16 threads add them up: 2 barriers per tap column instead of 2 per tap
   for (int j = 0; j < 7; ++j) {
     float2 a[7];
 #pragma unroll
@@ -603,18 +605,17 @@ __global__ void __launch_bounds__(256) dwconv7_wgrad_kernel(const bf16* __restri
         }
       }
     }
+    __syncthreads();                       // previous column's sums have been read
 #pragma unroll
-    for (int i = 0; i < 7; ++i) {
-      __syncthreads();
-      red[t][cp] = a[i];
-      __syncthreads();
-      if (t == 0) {
-        float2 s = make_float2(0.f, 0.f);
+    for (int i = 0; i < 7; ++i) red7[i][t][cp] = a[i];
+    __syncthreads();
+    if (threadIdx.x < 7 * 16) {
+      const int i = threadIdx.x >> 4, c2 = threadIdx.x & 15;
+      float2 s = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int q = 0; q < 16; ++q) { s.x += red[q][cp].x; s.y += red[q][cp].y; }
-        atomicAdd(dw + (i * 7 + j) * C + c0 + cp * 2, s.x);
-        atomicAdd(dw + (i * 7 + j) * C + c0 + cp * 2 + 1, s.y);
-      }
+      for (int q = 0; q < 16; ++q) { s.x += red7[i][q][c2].x; s.y += red7[i][q][c2].y; }
+      atomicAdd(dw + (i * 7 + j) * C + c0 + c2 * 2, s.x);
+      atomicAdd(dw + (i * 7 + j) * C + c0 + c2 * 2 + 1, s.y);
     }
   }
   __syncthreads();

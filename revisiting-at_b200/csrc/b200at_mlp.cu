@@ -44,7 +44,7 @@ struct MlpCfg {
   static constexpr int KB = (C + 63) / 64;                 // k-blocks of GEMM-a (K = C; TMA zero-fills the tail)
   static constexpr int KSteps = C / 16;                    // UMMA K = 16 steps of GEMM-a
   static constexpr int NC = 4 * C / kChunk;                // chunks per tile
-  static constexpr int AStages = C <= 96 ? 2 : 1;
+  static constexpr int AStages = C <= 128 ? 2 : 1;
   static constexpr int WStages = 2;
   static constexpr int ABytes = KB * 128 * 128;            // KB x [128 rows x 128 B]
   static constexpr int WaBytes = KB * kChunk * 128;        // KB x [64 rows x 128 B]
@@ -462,7 +462,7 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mwa, const CUtensorMap& mwb
 
 }  // namespace
 
-extern "C" int b200at_mlp_fused_supported(int64_t C) { return C == 96 || C == 192; }
+extern "C" int b200at_mlp_fused_supported(int64_t C) { return C == 96 || C == 128 || C == 192; }
 
 extern "C" int b200at_mlp_fused(const void* a, const void* wa, const void* wb, const float* bias1, const float* bias2,
                                 const void* residual, void* z, void* p_out, void* out, int64_t M, int64_t C,
@@ -488,6 +488,7 @@ extern "C" int b200at_mlp_fused(const void* a, const void* wa, const void* wb, c
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = p.tiles_m < sms ? p.tiles_m : sms;
   cudaStream_t s = (cudaStream_t)stream;
+  if (C == 128) return backward ? launch<128, 1>(ma, mwa, mwb, mz, mp, p, grid, s) : launch<128, 0>(ma, mwa, mwb, mz, mp, p, grid, s);
   if (C == 96) return backward ? launch<96, 1>(ma, mwa, mwb, mz, mp, p, grid, s) : launch<96, 0>(ma, mwa, mwb, mz, mp, p, grid, s);
   return backward ? launch<192, 1>(ma, mwa, mwb, mz, mp, p, grid, s) : launch<192, 0>(ma, mwa, mwb, mz, mp, p, grid, s);
 }

@@ -167,8 +167,8 @@ def _f32(t):
 #   'gelu'      pwconv1 forward with bias + GELU fused (+ pre-activation saved)   [slower: epilogue-bound]
 #   'gelu_grad' dz = (dout W2g) * GELU'(z)        fused                           [slower: epilogue-bound]
 #   'mlp'       the whole MLP (pwconv1 -> GELU -> pwconv2 + scale + bias + residual, and its input gradient) as ONE
-#               kernel per direction with the 4C hidden kept on chip (csrc/b200at_mlp.cu), for C in {96, 192}
-TCGEN05 = set(filter(None, os.environ.get('B200AT_TCGEN05', 'residual,dgrad1,fc1,dgrad2').split(',')))
+#               kernel per direction with the 4C hidden kept on chip (csrc/b200at_mlp.cu), for C in {96, 128, 192}
+TCGEN05 = set(filter(None, os.environ.get('B200AT_TCGEN05', 'residual,dgrad1,fc1,dgrad2,mlp').split(',')))
 _MLP_OK = {}
 
 
@@ -449,7 +449,12 @@ def stem_layer(x, cw, cb, lw, lb, stride, first, mean=None, std=None):
             and (_INPUT_GRAD_ONLY[0] or not torch.is_grad_enabled())):
         wk = _derived(cw, 'stem0_wk', lambda w: w.float().reshape(w.shape[0], 27).t().contiguous())   # [27][C0]
         return _Stem0.apply(x.contiguous(), wk, _f32(cb), _f32(lw), _f32(lb), _host3(mean), _host3(std))
-    if first:
+    if first and x.dtype == torch.float32 and x.is_contiguous() and x.shape[1] == 3 and not x.requires_grad:
+        # training forward on the attack's (detached) output: normalise + cast + NHWC in one pass
+        t = torch.empty(x.shape[0], x.shape[2], x.shape[3], 3, device=x.device, dtype=BF16)
+        _abi.normalize_nhwc_bf16(x, _host3(mean), _host3(std), t)
+        x = t.permute(0, 3, 1, 2)                        # NHWC storage viewed as NCHW channels_last
+    elif first:
         if mean is not None:
             x = (x - mean) / std
         x = x.to(BF16).contiguous(memory_format=torch.channels_last)

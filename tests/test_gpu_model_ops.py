@@ -253,3 +253,20 @@ def test_convnext_engine_matches_oracle(cuda_dev):
         ref = od[n].grad
         cs = F.cosine_similarity(p.grad.flatten().cpu().float(), ref.flatten(), dim=0).item()
         assert cs >= 0.95 or ref.abs().max() < 1e-7, (n, cs)
+
+
+def test_normalize_nhwc_matches_the_eager_expression_bit_for_bit(cuda_dev):
+    """(x - mean) / std -> bf16 -> channels_last in one kernel == torch's four passes (utils_architecture.py:86-98)"""
+    import revisiting_at_b200  # noqa: F401
+    from revisiting_at_b200 import _abi
+    g = torch.Generator(device='cuda').manual_seed(3)
+    mean = torch.tensor([0.485, 0.456, 0.406], device=cuda_dev).view(1, 3, 1, 1)
+    std = torch.tensor([0.229, 0.224, 0.225], device=cuda_dev).view(1, 3, 1, 1)
+    for shape in ((5, 3, 33, 47), (16, 3, 224, 224)):
+        x = torch.rand(*shape, generator=g, device=cuda_dev)
+        y = torch.full((shape[0], shape[2], shape[3], 3), float('nan'), device=cuda_dev, dtype=torch.bfloat16)
+        _abi.normalize_nhwc_bf16(x, [float(v) for v in mean.flatten()], [float(v) for v in std.flatten()], y)
+        want = ((x - mean) / std).to(torch.bfloat16).permute(0, 2, 3, 1)
+        assert torch.equal(y, want)
+        _abi.normalize_nhwc_bf16(x, None, None, y)
+        assert torch.equal(y, x.to(torch.bfloat16).permute(0, 2, 3, 1))
