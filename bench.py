@@ -106,9 +106,9 @@ def synth_batch(batch, seed):
 
 ENGINE_NOTE = {
     False: 'hand-written NHWC bf16 kernels: fused first stem stage, dwconv7 fwd/dgrad/wgrad, LayerNorm (+patch layout for '
-           'the downsample), bias+GELU, tcgen05 GEMM for every forward / input-gradient GEMM (pwconv1, pwconv2+scale+bias+'
-           'residual, both dgrads, downsample conv2x2s2); cuBLAS for the weight-gradient GEMMs, cuDNN for the strided '
-           '3x3 stem convs outside the fused first stage',
+           'the downsample), fused tcgen05 MLP kernel per direction (pwconv1 -> GELU -> pwconv2+scale+bias+residual, hidden '
+           'on chip) for C <= 192, tcgen05 GEMM + bias/GELU kernels for the wider stages and the downsample conv2x2s2; '
+           'cuBLAS for the weight-gradient GEMMs, cuDNN for the strided 3x3 stem convs outside the fused first stage',
     True: 'hand-written kernels: fused first stem stage, LayerNorm(+GELU), bias+GELU, mma.sync attention fwd/bwd, '
           'tcgen05 GEMM (qkv+bias, proj/fc2+bias+residual, fc1, all input-gradient GEMMs); cuBLAS for weight-gradient '
           'GEMMs, cuDNN for stem convs 2-4',

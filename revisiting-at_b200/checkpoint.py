@@ -112,10 +112,12 @@ def reference_state_dict(model, prefix='module.'):
     """State dict under the reference's key names for `weights_N.pt` (main.py:739): `model` is the
     WrappedModel(Normalized(engine)) (or DDP of it); plain engines get the `base_model.model.` prefix added."""
     sd = model.state_dict()
+    normalised = any(_core(k).startswith('normalize.') for k in sd)      # `normalize_model` adds the `model.` level
     out = OrderedDict()
     for k, v in sd.items():
         c = _core(k)
-        out[prefix + 'base_model.' + (c if c.startswith('normalize.') else 'model.' + c)] = v.detach()
+        inner = c if (c.startswith('normalize.') or not normalised) else 'model.' + c
+        out[prefix + 'base_model.' + inner] = v.detach()
     return out
 
 
