@@ -80,7 +80,9 @@ def test_fused_backward(abi, cuda_dev, C, M):
     abi.bias_gelu_bwd(da_u, z, d['b1'], dz_u, None)
     abi.gemm_bf16(dz_u, w1t, dt2_u, abi.EPI_NONE)
     _close(dz, dz_u, 'dz vs bias_gelu_bwd', rel=2 ** -6, ab=2e-3)
-    _close(dt2, dt2_u, 'dt2 vs unfused', rel=2 ** -7, ab=1e-3)
+    # dz differs from the stand-alone kernel by one bf16 step in ~1e-4 of the elements (there `0.5 - h` is contracted
+    # into an FMA, here h is rounded first; deterministic: profiles/debug/mlp_determinism.py), and dt2 sums 4C of them
+    _close(dt2, dt2_u, 'dt2 vs unfused', rel=2 ** -6, ab=4e-3)
     zz = (z.float() + d['b1']).requires_grad_()
     (gp,) = torch.autograd.grad(F.gelu(zz).sum(), zz)
     dzr = (d['dout'].float() @ d['w2'].float()).to(BF16).float() * gp
