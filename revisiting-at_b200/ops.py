@@ -271,6 +271,22 @@ def _prepared(w1, w2, b2, gamma):
     return _derived_multi((w1, w2, b2, gamma), 'convnext_mlp', build)
 
 
+def _wgrad(dy2, x2):
+    """weight gradient dy2^T x2 (contraction over the M rows): library GEMM with fp32 output -- the split-K reduction
+    writes fp32 directly instead of bf16 followed by a cast kernel."""
+    return torch.mm(dy2.t(), x2, out_dtype=torch.float32)
+
+
+def _zeros_split(dev, *sizes):
+    """fp32 accumulators for the kernels that atomically add into them: ONE fill, views of the given sizes"""
+    buf = torch.zeros(sum(sizes), device=dev, dtype=torch.float32)
+    out, o = [], 0
+    for n in sizes:
+        out.append(buf[o:o + n])
+        o += n
+    return out
+
+
 def _gemm(a, w, epi=_abi.EPI_NONE, bias=None, aux=None, c2=None):
     c = torch.empty(a.shape[0], w.shape[0], device=a.device, dtype=BF16)
     _abi.gemm_bf16(a, w, c, epi, bias=bias, aux=aux, c2=c2)
@@ -349,7 +365,11 @@ class _ConvNeXtBlock(Function):
         M = B * H * W
         pg = ctx.param_grads and any(ctx.needs_input_grad[1:])
         d2 = dout.view(M, C)
-        db1 = torch.zeros(4 * C, device=dout.device, dtype=torch.float32) if pg else None
+        if pg:
+            db1, ddw, ddb, col, dlnw, dlnb = _zeros_split(dout.device, 4 * C, 49 * C, C, C, C, C)
+            ddw = ddw.view(49, C)
+        else:
+            db1 = dlnw = dlnb = None
         dt2 = None
         if _mlp_fused(C) and ctx.zb is not None:
             dz = torch.empty_like(z) if pg else None                    # only the weight gradients need it
@@ -373,8 +393,6 @@ class _ConvNeXtBlock(Function):
         else:
             dt2 = (dz @ P['w1b']).view(B, H, W, C)
         dt1 = torch.empty_like(dt2)
-        dlnw = torch.zeros_like(lnw) if pg else None
-        dlnb = torch.zeros_like(lnb) if pg else None
         _abi.ln_bwd(dt2, t1, lnw, lnb, mean, rstd, dt1, dlnw, dlnb, False)
         dx = torch.empty_like(dout)
         _abi.dwconv7_fwd(dt1, wtf, None, dx, add=dout)                  # + residual gradient
@@ -382,12 +400,9 @@ class _ConvNeXtBlock(Function):
             return (dx,) + (None,) * 9
         x, t2, a, w2, b2f = sv[7:]
         gf = P['gf']
-        ddw = torch.zeros(49, C, device=dout.device, dtype=torch.float32)
-        ddb = torch.zeros(C, device=dout.device, dtype=torch.float32)
         _abi.dwconv7_wgrad(x, dt1, ddw, ddb)
-        dw1 = (dz.t() @ t2.view(M, C)).float()
-        dw2g = (d2.t() @ a).float()                                     # gradient w.r.t. gamma-folded W2
-        col = torch.zeros(C, device=dout.device, dtype=torch.float32)
+        dw1 = _wgrad(dz, t2.view(M, C))
+        dw2g = _wgrad(d2, a)                                            # gradient w.r.t. gamma-folded W2
         _abi.colsum_bf16(d2, col)
         dw2 = gf[:, None] * dw2g
         db2 = col * gf
@@ -503,7 +518,7 @@ class _Downsample(Function):
         _abi.ln_bwd_patch2(dt, x, lnw, lnb, mean, rstd, dx, dlw, dlb)
         if not pg:
             return dx, None, None, None, None
-        dwk = (dy2.t() @ t).float()                                     # [Co, (kh, kw, Cin)]
+        dwk = _wgrad(dy2, t)                                            # [Co, (kh, kw, Cin)]
         dcw = dwk.view(Co, 2, 2, C).permute(0, 3, 1, 2)
         dcb = torch.zeros(Co, device=dy.device, dtype=torch.float32)
         _abi.colsum_bf16(dy2, dcb)
@@ -650,10 +665,10 @@ class _ViTBlock(Function):
             out = torch.zeros(m.shape[1], device=dev, dtype=torch.float32)
             _abi.colsum_bf16(m, out)
             return out
-        dwqkv = (dqkv.t() @ t).float()
-        dwproj = (dx1.t() @ o.view(M, D)).float()
-        dw1 = (dz.t() @ t2).float()
-        dw2 = (d2.t() @ a).float()
+        dwqkv = _wgrad(dqkv, t)
+        dwproj = _wgrad(dx1, o.view(M, D))
+        dw1 = _wgrad(dz, t2)
+        dw2 = _wgrad(d2, a)
         return (dx, dn1w, dn1b, dwqkv, colsum(dqkv), dwproj, colsum(dx1), dn2w, dn2b, dw1, db1, dw2, colsum(d2), None)
 
 
@@ -685,7 +700,7 @@ class _Linear1x1(Function):
         dx = _gemm(dy2, wt).view(*dy.shape[:-1], wt.shape[0])
         if not _wants(ctx, 1, 2):
             return dx, None, None
-        dw = (dy2.t() @ x.view(dy2.shape[0], -1)).float().view(ctx.wshape)
+        dw = _wgrad(dy2, x.view(dy2.shape[0], -1)).view(ctx.wshape)
         db = torch.zeros(dy2.shape[1], device=dy.device, dtype=torch.float32)
         _abi.colsum_bf16(dy2, db)
         return dx, dw, db
