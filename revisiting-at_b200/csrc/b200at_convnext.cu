@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "b200at_gelu.cuh"
 #include "b200at_tma.cuh"
@@ -404,6 +405,10 @@ struct DwTile {
   static constexpr int kTilePad = (kTileBytes + 127) / 128 * 128;        // TMA destination: 128-byte aligned
   static constexpr int kWBytes = 49 * (kDwCh / 2) * 8;                   // fp32x2 taps of the channel group
   static constexpr int kSmem = 2 * kTilePad + kWBytes + 64 + 128;        // + barriers + alignment slack
+  // resident CTAs per SM the register budget is cut for: the half-height tile keeps 7 instead of 14 accumulator rows
+  // per column, which buys a third CTA (21 instead of 14 warps per SM: the full-height form is latency-bound at 2.9
+  // active warps per scheduler, profiles/r01_ncu_dwconv_stem0_v11_summary.txt)
+  static constexpr int kMinCtas = (TH == 7 && TW == 28) ? 3 : 2;
 };
 
 struct DwParams {
@@ -417,7 +422,7 @@ struct DwParams {
 };
 
 template <int TH, int TW, int NB, bool BIAS, bool ADD>
-__global__ void __launch_bounds__(DwTile<TH, TW, NB>::kThreads, 2)
+__global__ void __launch_bounds__(DwTile<TH, TW, NB>::kThreads, DwTile<TH, TW, NB>::kMinCtas)
     dwconv7_kernel(const __grid_constant__ CUtensorMap map_x, const DwParams p) {
   typedef DwTile<TH, TW, NB> T;
   extern __shared__ __align__(128) uint8_t dw_smem_raw[];
@@ -713,7 +718,7 @@ int launch_dwconv(const void* x, const float* wt, const float* bias, const void*
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int per_sm = (228 * 1024) / (T::kSmem + 1024);      // resident CTAs per SM by shared memory (launch bounds: 2)
-  per_sm = per_sm < 1 ? 1 : (per_sm > 2 ? 2 : per_sm);
+  per_sm = per_sm < 1 ? 1 : (per_sm > T::kMinCtas ? T::kMinCtas : per_sm);
   const int64_t cap = (int64_t)sms * per_sm;
   const int grid = (int)(total < cap ? total : cap);
 #define B200AT_DW(BI, AD)                                                                                     \
@@ -843,7 +848,9 @@ int b200at_dwconv7_fwd(const void* x, const float* wt, const float* bias, const 
   cudaStream_t s = (cudaStream_t)stream;
   // tile shapes: wide maps 14 x 28; 14-wide maps two images side by side; the 7 x 7 maps of the last stage three
   // images of 7 x 8 (one masked column)
-  if (W > 14) return launch_dwconv<14, 28, 1>(x, wt, bias, add, y, B, H, W, C, s);
+  static const bool half_height = [] { const char* e = getenv("B200AT_DW_TH7"); return e == nullptr || e[0] != '0'; }();
+  if (W > 14) return half_height ? launch_dwconv<7, 28, 1>(x, wt, bias, add, y, B, H, W, C, s)
+                                 : launch_dwconv<14, 28, 1>(x, wt, bias, add, y, B, H, W, C, s);
   if (W > 8 || H > 7) return launch_dwconv<14, 14, 2>(x, wt, bias, add, y, B, H, W, C, s);
   return launch_dwconv<7, 8, 3>(x, wt, bias, add, y, B, H, W, C, s);
 }
