@@ -1,14 +1,17 @@
-"""Layer functions of the ConvNeXt-CvSt forward/backward (reference math: models/convnext.py:37-50,
+"""Layer functions of the ConvNeXt-CvSt / ViT-S-CvSt forward and backward (reference math: models/convnext.py:37-50,
 utils_architecture.py:57-81) on NHWC bf16 activations.
 
-The memory-bound ops -- depthwise 7x7 conv (fwd / input-grad / weight-grad), per-pixel LayerNorm
-(fwd [+GELU] / input-grad / gamma-beta grads), bias+GELU on the 4C hidden, layer-scale+residual -- are
-the hand-written sm_100a kernels of csrc/b200at_convnext.cu behind include/b200at_model.h, wrapped as
-autograd Functions that compute weight gradients only when autograd asks for them (the attack's backward
-is input-grad only: autopgd_train_clean.py:185).  The dense pwconv/MLP GEMMs and the strided stem /
-downsample convolutions are library calls (cuBLAS / cuDNN through torch) in this round; ncu of the
-round-1 baseline (profiles/r01_launches_summary_torch_model.txt) shows them at ~8 % of the step against
-~85 % for the memory-bound ops, which is why those were written first.
+Each layer group is one autograd Function over the C ABI of include/b200at_model.h:
+  * depthwise 7x7 conv (fwd / input-grad with the residual join / weight-grad), per-pixel LayerNorm (fwd [+GELU] /
+    input-grad / gamma-beta grads), bias+GELU: the hand-written kernels of csrc/b200at_convnext.cu;
+  * the block's MLP (pwconv1 -> GELU -> pwconv2 + layer scale + bias + residual) and its input gradient: ONE tcgen05
+    kernel per direction with the hidden activation kept on chip (csrc/b200at_mlp.cu) for C in {96, 128, 192}, the
+    tcgen05 GEMM (csrc/b200at_gemm.cu) + bias/GELU kernels for the wider stages;
+  * first stem stage fused (csrc/b200at_stem.cu), downsample = patch-layout LayerNorm + tcgen05 GEMM, attention
+    (csrc/b200at_attention.cu).
+The Functions compute weight gradients only when autograd will ask for them (the attack's backward is input-grad
+only: autopgd_train_clean.py:185).  Library calls that remain: cuBLAS for the weight-gradient GEMMs (contraction over
+the M rows), cuDNN for the strided 3x3 stem convolutions outside the fused first stage.
 """
 import os
 import weakref
