@@ -230,3 +230,34 @@ def test_interpolate_pos_encoding():
     if ref_loader.available():
         _, ua = ref_loader.convnext_t_cvst()
         assert torch.equal(out, ua.interpolate_pos_encoding(pe, new_img_size=320, patch_size=16))
+
+
+def _aa_eval():
+    spec = importlib.util.spec_from_file_location('_b200at_aa_eval', os.path.join(ROOT, 'AA_eval.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_aa_eval_accepts_the_runner_command_line(tmp_path):
+    """the argument string runner_aa_eval.py:13-16 builds (with its `--not-orig` abbreviation and `--a100` flag)"""
+    aa = _aa_eval()
+    job = '--model_in {} --mod {} --not-orig {} --a100 {} --full_aa {} --l_norms {} --batch_size {}'.format(
+        str(tmp_path), 'convnext_base', 1, 1, 0, 'Linf', 100)
+    a = aa.get_args_parser(shlex.split(job))
+    assert a.model_in == [str(tmp_path)] and a.mod == 'convnext_base' and a.not_original == 1 and a.a100 == 1
+    assert a.full_aa == 0 and a.l_norms == 'Linf' and a.batch_size == 100 and a.img_size == 224 and a.n_ex == 5000
+    assert aa.eps_dict['imagenet'] == {'Linf': 4. / 255., 'L2': 2., 'L1': 75.}
+    # run folder -> weights_20.pt when present (AA_eval.py:124), else the latest weights_N.pt; EMA files are not picked
+    for n in (2, 11, 7):
+        torch.save({}, tmp_path / f'weights_{n}.pt')
+    torch.save({}, tmp_path / 'weights_ema_30.pt')
+    assert aa.resolve_checkpoint(str(tmp_path)) == (str(tmp_path / 'weights_11.pt'), str(tmp_path))
+    torch.save({}, tmp_path / 'weights_20.pt')
+    assert aa.resolve_checkpoint(str(tmp_path))[0] == str(tmp_path / 'weights_20.pt')
+    assert aa.resolve_checkpoint(str(tmp_path / 'weights_7.pt')) == (str(tmp_path / 'weights_7.pt'), str(tmp_path))
+    assert aa.resolve_checkpoint('random') == (None, None)
+    x, y = aa.load_points('synthetic', 6, 32)
+    assert x.shape == (6, 3, 32, 32) and y.shape == (6,) and 0. <= float(x.min()) and float(x.max()) < 1.
+    x2, _ = aa.load_points('synthetic', 6, 32)
+    assert torch.equal(x, x2)                                              # the subset is fixed
