@@ -9,16 +9,26 @@
 // they move 2 B (z written once for the backward / z read once).
 //
 // Per 128-row tile, the hidden dimension is walked in chunks of 64 columns:
-//   GEMM-a  acc_a[128 x 64]  = A_tile[128 x C] . Wa_chunk[64 x C]^T          (TMEM, double buffered)
-//   f       16 epilogue warps: tcgen05.ld -> bias / GELU / GELU' (z chunk stored / loaded in bf16) -> bf16 ->
-//           shared memory in the K-major SWIZZLE_128B operand layout (double buffered)
-//   GEMM-b  acc_b[128 x C] += P_chunk[128 x 64] . Wb_chunk[C x 64]^T         (TMEM, lives for the whole tile)
-// then acc_b (+ bias2 + residual) -> bf16 -> global.  Persistent, one CTA per SM, warp-specialised:
-//   warp 0 TMA producer (A tile ring, weight-chunk ring), warp 1 MMA issuer (GEMM-a of chunk j+1 is issued before
-//   GEMM-b of chunk j, so the tensor pipe works under the GELU of the previous chunk), warp 2 TMEM allocator,
-//   warps 4-19 the elementwise stage + final epilogue.  mbarrier-only synchronisation.
-// The hidden values are rounded to bf16 exactly where the unfused path stores them (z, da), so both paths agree
-// to the accumulation order of the second GEMM.
+//   GEMM-a  acc_a[128 x 64]  = A_tile[128 x C] . Wa_chunk[64 x C]^T          (TMEM, double buffered by chunk parity)
+//   f       16 epilogue warps in two groups of 8 (group = chunk parity): tcgen05.ld -> round to bf16 where the unfused
+//           path stores (z / da) -> bias / GELU / GELU' -> bf16 -> st.shared in the K-major SWIZZLE_128B operand layout
+//           (P[2]); the z chunk travels through its own swizzled buffer (Z[2]): TMA store forward, TMA load backward
+//   GEMM-b  acc_b[128 x C] += P_chunk[128 x 64] . Wb_chunk[C x 64]^T          (TMEM, double buffered across tiles)
+// then acc_b (+ bias2 + residual) -> bf16 -> global, deferred to after the warp's first chunk of the next tile.
+// Persistent, one CTA per SM, 640 threads, mbarrier-only synchronisation:
+//   warp 0      three independent TMA producer lanes: A tile + GEMM-a weight ring / GEMM-b weight ring / saved z (backward)
+//   warp 1      MMA issuer: GEMM-a of chunk g+2 is issued as soon as acc_a of chunk g has been drained, before GEMM-b of g
+//   warps 2, 3  TMA store issuers, one per chunk parity (z forward; the optional a / dz output straight from P);
+//               warp 2 also allocates / frees TMEM
+//   warps 4-19  the elementwise stage + final epilogue
+// Two rules this kernel learnt the hard way: a buffer that an asynchronous writer (TMA) refills may only be
+// released after the loads from it have RETURNED (mbarrier.arrive does not wait for them: `consume_loads`), and every
+// shared-memory access goes through explicit ld/st.shared on 32-bit addresses (pointer arithmetic on the re-aligned
+// dynamic shared base degrades to generic LD/ST).
+// The hidden values are rounded to bf16 exactly where the unfused path stores them (z, da): forward z / a / out are
+// bit-identical to the three-kernel path, backward dz within one bf16 step (profiles/debug/mlp_determinism.py).
+// B200AT_MLP_DEBUG (race hunting only; bit 2 makes the optional output wrong on purpose): 1 = final epilogue at the tile
+// end instead of deferred, 2 = skip the TMA store of P, 4 = plain instead of backed-off waits in the store warps.
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
