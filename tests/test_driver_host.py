@@ -261,3 +261,16 @@ def test_aa_eval_accepts_the_runner_command_line(tmp_path):
     assert x.shape == (6, 3, 32, 32) and y.shape == (6,) and 0. <= float(x.min()) and float(x.max()) < 1.
     x2, _ = aa.load_points('synthetic', 6, 32)
     assert torch.equal(x, x2)                                              # the subset is fixed
+
+
+def test_vit_checkpoint_round_trip_keeps_timm_names():
+    """ViT keys (`pos_embed`, `norm.weight`, `head.weight`) must NOT be taken for vendored ConvNeXt spellings"""
+    src = WrappedModel(vit.build(normalize=True, seed=1), None)
+    sd = checkpoint.reference_state_dict(src)
+    assert 'module.base_model.model.pos_embed' in sd and 'module.base_model.model.norm.weight' in sd
+    tgt = vit.build(normalize=False, seed=2)
+    missing, unused = checkpoint.load_checkpoint(tgt, sd)
+    assert not missing and not unused
+    a = {checkpoint._core(k): v for k, v in src.state_dict().items() if 'normalize' not in k}
+    b = {checkpoint._core(k): v for k, v in tgt.state_dict().items()}
+    assert set(a) == set(b) and all(torch.equal(a[k], b[k]) for k in b)
