@@ -13,7 +13,7 @@ The adversarial train step itself is `revisiting_at_b200.train_step.AdvTrainStep
 
 Deliberately different: bf16 autocast without GradScaler (`training.precision` is accepted and ignored),
 EMA on the device, models restricted to the CvSt families the engine builds (ConvNeXt-T/S/B/L, ViT-S with
-`model.not_original 1`).  Outside the hot path and therefore minimal: the data pipeline (`synthetic[:N]` batches,
+`model.not_original 1`), `logging.save_freq` is honoured (the reference overwrites it with 1 before saving: main.py:733).  Outside the hot path and therefore minimal: the data pipeline (`synthetic[:N]` batches,
 or a torchvision ImageFolder with random-resized-crop + flip; timm's RandAugment / RandomErasing are not rebuilt)
 and validation (clean top-1 on the first batches, main.py:905-942).
 """
