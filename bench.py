@@ -15,8 +15,9 @@ GPU (3x224x224, l-inf 4/255, APGD n_iter=2, bf16 autocast): 4 forwards + 2 input
   roofline  the fused l-inf APGD update kernel (b200at_linf_step): 20 B/element x B x n_fts per launch
              / mean launch duration, measured live with CUDA events on the launching
             stream over the timed region; peak = MEASURED_PEAKS.json hbm_gbs
-  cpu_baseline  oracle port of the same step (oracle/train_step_oracle.py), fp32, on this box's host
-            cores, bounded sample, rank 0 at N=1 only
+  cpu_baseline  the reference's own apgd_train + model files (staged under oracle/_ref by build(); the oracle
+            port if absent) in the same step, fp32, on this box's host cores, bounded sample (steps of 32
+            images = BASELINE configs[0]), rank 0 at N=1 only
   --impl reference   times that CPU implementation instead (rank 0 only)
 """
 import argparse
@@ -162,44 +163,61 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------- CPU arm
+CPU_BATCH = 32            # BASELINE.json configs[0]: the reference's own CPU-runnable case
+
+
 def cpu_step_factory(arch=ARCH):
-    from oracle.train_step_oracle import OracleTrainStep
+    """(step, kind): the UNMODIFIED reference `apgd_train` + its own ConvNeXt-T-CvSt modules when staged
+    (oracle/_ref, kind "reference"); the oracle port otherwise (other archs: timm is un-vendored) -- kind "port"."""
+    from oracle import train_step_oracle
     torch.set_num_threads(os.cpu_count())
-    return OracleTrainStep(build_oracle(arch), 'Linf', EPS, N_ITER)
+    if arch == ARCH and RES % 32 == 0:
+        step = train_step_oracle.reference_train_step('Linf', EPS, N_ITER)
+        if step is not None:
+            return step, 'reference'
+    return train_step_oracle.OracleTrainStep(build_oracle(arch), 'Linf', EPS, N_ITER), 'port'
+
+
+_KIND_NOTE = {'reference': 'unmodified reference apgd_train + models/convnext.py + ConvBlock1 (oracle/_ref), train_loop body restated',
+              'port': 'oracle/train_step_oracle.py port'}
+
+
+def _cpu_batch(step, budget_s, n_steps):
+    """CPU_BATCH images per step unless n_steps of them would not fit the budget (probe: one step of 4 images)."""
+    x, y = synth_batch(4, 7)
+    t0 = time.time(); step(x, y); t4 = time.time() - t0
+    per_img = t4 / 4
+    fit = int(budget_s / max(n_steps, 1) / max(per_img, 1e-4))
+    return max(2, min(CPU_BATCH, fit))
 
 
 def cpu_baseline(seconds, arch=ARCH):
-    """Oracle port of the step on the host cores, bounded sample: one warm-up step at batch 4, then as many
-    images as fit in ~`seconds` (batch 8..32), timed with the wall clock."""
-    step = cpu_step_factory(arch)
-    x, y = synth_batch(4, 7)
-    t0 = time.time(); step(x, y); t_warm = time.time() - t0
-    ips_guess = 4 / max(t_warm, 1e-3)
-    batch = int(min(32, max(8, ips_guess * seconds / 2)))
+    """The reference's CPU implementation of the step on the host cores, bounded sample: one probe step of 4 images
+    (doubles as warm-up), then steps of CPU_BATCH images for ~`seconds`, timed with the wall clock."""
+    step, kind = cpu_step_factory(arch)
+    batch = _cpu_batch(step, seconds, 1)
     x, y = synth_batch(batch, 8)
     n, t0 = 0, time.time()
     while True:
         step(x, y); n += batch
-        if time.time() - t0 > seconds / 2 or n >= 64:
+        if time.time() - t0 > seconds * 0.6 or n >= 3 * CPU_BATCH:
             break
     dt = time.time() - t0
-    return {'value': n / dt, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
-            'sample': f'{n} images in steps of {batch} (fp32, oracle/train_step_oracle.py, same model/attack config), '
+    return {'value': n / dt, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': kind,
+            'sample': f'{n} images in steps of {batch} (fp32, {_KIND_NOTE[kind]}, same model/attack config), '
                       f'{dt:.1f} s wall after one warm-up step'}
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU implementation of the path (oracle port; the reference is pure
-    Python and /root/reference does not travel to the GPU box), all host threads, rank 0 only."""
+    """--impl reference: the reference's own CPU implementation of the path (kind "reference": its unmodified
+    apgd_train and model files staged under oracle/_ref at build time; "port" only if they are absent), all host
+    threads, rank 0 only, every step a bounded sample (CPU_BATCH images) of the 128/GPU workload."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    step = cpu_step_factory(args.arch)
+    step, kind = cpu_step_factory(args.arch)
     total = args.steps + args.warmup
-    x, y = synth_batch(2, 7)
-    t0 = time.time(); step(x, y); t2 = time.time() - t0
-    budget = 150.0                                          # whole run ends within a few minutes
-    batch = int(min(32, max(2, (budget / max(total, 1)) * (2 / max(t2, 1e-3)) * 0.6)))
+    batch = _cpu_batch(step, 200.0, total)                   # whole run ends within a few minutes
     x, y = synth_batch(batch, 8)
     for _ in range(args.warmup):
         step(x, y)
@@ -209,11 +227,12 @@ def run_reference(args):
     dt = time.time() - t0
     v = batch * args.steps / dt
     cores = torch.get_num_threads()
-    sample = f'{args.steps} steps of {batch} images (bounded sample of the {args.batch}/GPU step), fp32, {cores} threads'
+    sample = (f'{args.steps} steps of {batch} images (bounded sample of the {args.batch}/GPU step), fp32, {cores} threads, '
+              f'{_KIND_NOTE[kind]}')
     line = {'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(args.gpus, args.batch, args.arch, args.ema, args.label_smoothing),
-            'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
+            'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': cores, 'kind': kind, 'sample': sample},
             'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
     print(json.dumps(line), flush=True)

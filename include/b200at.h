@@ -46,7 +46,10 @@ int b200at_apgd_init(const float* x, float* x_adv, float* state, int64_t B, int6
  * model's backward for loss.sum()), prediction, acc &= pred, strict best-loss compare, loss_steps
  * history, check_oscillation (:116-121) + step halving at a checkpoint (ckpt_k > 0 = window k),
  * l1 sparsity adaptation.  Leaves the pending image ops in state[FLAGS].
- * Exactly one of y_hard ([B] int64) / y_soft ([B][C] fp32) is non-null. dlogits / loss_out may be null. */
+ * Exactly one of y_hard ([B] int64) / y_soft ([B][C] fp32) is non-null. dlogits / loss_out may be null.
+ * A hard label (or target class) outside [0, C) traps the kernel -- the launch fails at the next synchronisation,
+ * like the device-side assert of torch's CUDA cross_entropy that the reference would hit; there is no host check
+ * (it would be a synchronisation per forward). */
 int b200at_loss_bookkeep(const void* logits, int logits_dtype, const int64_t* y_hard, const float* y_soft,
                          void* dlogits, float* loss_out, float* state, float* loss_steps, int64_t B, int64_t C,
                          int iter, int n_iter, int ckpt_k, int norm_kind, int loss_kind, float step_full,

@@ -306,15 +306,17 @@ class ImageNetTrainer:
             model = vit.build(normalize=bool(add_normalization), seed=int(torch.initial_seed() % (2 ** 31)))
         else:
             raise SystemExit(f'model.arch {arch!r}: the engine builds {sorted(convnext.ARCHS)} and vit_s')
+        if ckpt_path:
+            # before the EMA shadow is cloned and before DDP wraps the model: the reference loads the checkpoint
+            # (main.py:856-872) ahead of ModelEmaV2 (:881-887), so a resumed EMA starts from the loaded weights
+            checkpoint.load_checkpoint(model, ckpt_path)
+            print('checkpoint loaded')
         perturb = make_attack(attack, norm, eps, n_iter, verbose == 1, self.mixup_fn, alpha, noise_level, skip_projection)
         step = AdvTrainStep(model, attack=attack, perturb=perturb, distributed=bool(distributed), device=self.device,
                             ema=bool(model_ema), channels_last=bool(use_channel_last), mixup_fn=None,
                             graph_attack=attack == 'apgd' and self.mixup_fn is None,
                             param_groups=lambda named: weight_decay_groups(named, arch, weight_decay),
                             optimizer=optimizer, momentum=momentum)
-        if ckpt_path:
-            checkpoint.load_checkpoint(step.raw, ckpt_path)
-            print('checkpoint loaded')
         return step
 
     def single_val(self):
@@ -366,6 +368,9 @@ class ImageNetTrainer:
         if log_level > 0 and self.gpu == 0:
             self.log({'Validation acc': acc, 'points': n})
         for epoch in range(epochs):
+            sampler = getattr(self.train_loader, 'sampler', None)
+            if hasattr(sampler, 'set_epoch'):
+                sampler.set_epoch(epoch)                               # a new permutation / rank shard per epoch
             train_loss = self.train_loop(epoch)
             if log_level > 0:
                 self.log({'train_loss': train_loss.item(), 'epoch': epoch, 'images_per_sec_rank0': self.images_per_sec})

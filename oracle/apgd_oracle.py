@@ -16,8 +16,8 @@ Pinning: `oracle/make_goldens.py` runs the *unmodified* reference function
 (imported from /root/reference in the build container) on scripted-model and
 small-CNN inputs and commits inputs+outputs under `tests/golden/`;
 `tests/test_oracle_golden.py` checks this oracle against those vectors on
-every CPU run, and `tests/test_oracle_vs_reference.py` compares directly when
-/root/reference is present.  Parity status: PINNED for the attack
+every CPU run, and its `test_live_*` cases compare with the reference side by
+side when /root/reference is mounted.  Parity status: PINNED for the attack
 (l-inf / l2 / l1, hard and soft labels, ce and dlr).
 
 Arithmetic contract (reference line numbers in brackets):

@@ -1,15 +1,21 @@
-"""Import the UNMODIFIED reference from /root/reference (build container only).
+"""Import the UNMODIFIED reference by file path -- TEST / BENCH INFRASTRUCTURE ONLY.
 
-Used by `oracle/make_goldens.py` and by the CPU tests that compare the oracle
-with the reference directly.  /root/reference does not exist on the GPU box:
-nothing reachable from `-m gpu` tests, `smoke()` or `bench.py` imports this.
+Source: `/root/reference` where it is mounted (the build container), else the copy `oracle/stage_ref.py` staged
+under `oracle/_ref/` at build time (git-ignored; it travels to the GPU box with the snapshot).  Used by
+`oracle/make_goldens.py`, by the CPU tests that compare the oracle with the reference directly, and by
+`bench.py`'s CPU arm (`--impl reference`, `cpu_baseline`: kind "reference").  The `-m gpu` tests and `smoke()`
+never need it; the product package never imports it.
 """
 import importlib.util
 import os
 import sys
 import types
 
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), '_ref')
 REF = os.environ.get('B200AT_REFERENCE', '/root/reference')
+if not os.path.isfile(os.path.join(REF, 'autopgd_train_clean.py')) and \
+        os.path.isfile(os.path.join(_STAGED, 'autopgd_train_clean.py')):
+    REF = _STAGED
 
 
 def available() -> bool:
@@ -61,3 +67,14 @@ def convnext_t_cvst():
     m = cn.ConvNeXt(depths=[3, 3, 9, 3], dims=[96, 192, 384, 768])
     m.downsample_layers[0] = ua.ConvBlock1(48, end_siz=8)
     return m.eval(), ua
+
+
+def convnext_t_cvst_normalized(state_dict=None):
+    """`normalize_model(ConvNeXt-T-CvSt)` exactly as main.py:826-828 wraps it (utils_architecture.py:86-117), the
+    reference's own modules end to end; optionally loaded with a timm-named state dict of the oracle / engine."""
+    m, ua = convnext_t_cvst()
+    if state_dict is not None:
+        from . import convnext_oracle
+        km = convnext_oracle.vendored_key_map()
+        m.load_state_dict({km[k]: v for k, v in state_dict.items() if k in km})
+    return ua.normalize_model(m, (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)).eval()

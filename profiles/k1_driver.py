@@ -80,6 +80,22 @@ def main():
     dl = torch.empty_like(z)
     ls = torch.zeros(2, B, device=dev)
     timeit('loss_bookkeep(bf16 logits)', lambda: _abi.loss_bookkeep(z, y, dl, None, st, ls, 0, 2, 1, 'Linf', 'ce', 2 * eps, 0., n), 4. * B * 1000)
+    # l2 / l1 moves (the same 20 B/element single-pass ideal is the denominator; the extra passes of the
+    # dependent per-sample reductions count against the kernel)
+    flags.zero_()
+    st[_abi.ST_STEP] = torch.tensor([2 * 0.5, 0.5, 0.25] * B, device=dev)[:B]
+    xn = torch.empty_like(x)
+    sc = {'l2': None, 'l1': None}
+
+    def l2():
+        sc['l2'] = _abi.l2_step(x, xa, xo, xn, gr, xb, gb, xba, st, 0.5, 0.75, sc['l2'])
+    timeit('l2_step_steady(20B/elt credited)', l2, 20. * B * n)
+    st[_abi.ST_STEP] = 12.0
+    st[_abi.ST_TOPK] = 0.05
+
+    def l1():
+        sc['l1'] = _abi.l1_step(x, xa, xn, gr, xb, gb, xba, st, 12.0, sc['l1'])
+    timeit('l1_step_steady(20B/elt credited)', l1, 20. * B * n)
     if a.json:
         print(json.dumps({'batch': B, 'res': a.res, 'results': res}))
     else:

@@ -538,7 +538,13 @@ __global__ void __launch_bounds__(128) loss_bookkeep_kernel(LossArgs p) {
   warp_argmax(m1, i1);
   int label;
   if (ys) { warp_argmax(ym, yi); ysum = warp_sum(ysum); label = yi; }
-  else label = (int)p.y_hard[b];
+  else {
+    const int64_t yb = p.y_hard[b];
+    // a class index outside [0, C) is a caller bug; torch's CUDA cross_entropy (the reference's :113) raises a
+    // device-side assert for it, and DLR below would index z[label] out of bounds: fail as loudly, no host sync
+    if (yb < 0 || yb >= (int64_t)p.C) __trap();
+    label = (int)yb;
+  }
   const int pred = (i1 == label);
 
   float loss;
@@ -580,7 +586,9 @@ __global__ void __launch_bounds__(128) loss_bookkeep_kernel(LossArgs p) {
         if (c != i1 && c != i2 && c != i3 && better(v, c, m4, i4)) { m4 = v; i4 = c; }
       }
       warp_argmax(m4, i4);
-      const int it = (int)p.y_target[b];
+      const int64_t tb = p.y_target[b];
+      if (tb < 0 || tb >= (int64_t)p.C) __trap();
+      const int it = (int)tb;
       const float num = zy - to_f32<T>(z[it]);
       const float den = (m1 - 0.5f * (m3 + m4)) + 1e-12f;
       loss = -num / den;

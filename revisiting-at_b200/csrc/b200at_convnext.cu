@@ -14,6 +14,7 @@
 #include <stdlib.h>
 
 #include "b200at_gelu.cuh"
+#include "b200at_launch.cuh"
 #include "b200at_tma.cuh"
 #include "../../include/b200at_model.h"
 
@@ -723,13 +724,9 @@ int launch_dwconv(const void* x, const float* wt, const float* bias, const void*
   const int grid = (int)(total < cap ? total : cap);
 #define B200AT_DW(BI, AD)                                                                                     \
   do {                                                                                                        \
-    static bool configured = false;                                                                           \
-    if (!configured) {                                                                                        \
-      cudaError_t e = cudaFuncSetAttribute(dwconv7_kernel<TH, TW, NB, BI, AD>,                                \
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, T::kSmem);           \
-      if (e != cudaSuccess) return (int)e;                                                                    \
-      configured = true;                                                                                      \
-    }                                                                                                         \
+    static std::atomic<uint64_t> configured{0};                                                               \
+    cudaError_t e = b200at::ensure_dynamic_smem(dwconv7_kernel<TH, TW, NB, BI, AD>, T::kSmem, configured);    \
+    if (e != cudaSuccess) return (int)e;                                                                      \
     dwconv7_kernel<TH, TW, NB, BI, AD><<<grid, T::kThreads, T::kSmem, s>>>(map, p);                            \
   } while (0)
   if (bias) { if (add) B200AT_DW(true, true); else B200AT_DW(true, false); }

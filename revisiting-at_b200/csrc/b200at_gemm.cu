@@ -19,6 +19,7 @@
 #include <stdint.h>
 
 #include "b200at_gelu.cuh"
+#include "b200at_launch.cuh"
 #include "../../include/b200at_model.h"
 
 namespace {
@@ -380,12 +381,9 @@ int pick_block_n(int64_t N) {
 
 template <int EPI>
 int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, size_t smem, int grid, cudaStream_t s) {
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e != cudaSuccess) return (int)e;
-    configured = true;
-  }
+  static std::atomic<uint64_t> configured{0};
+  cudaError_t e = b200at::ensure_dynamic_smem(gemm_kernel<EPI>, 227 * 1024, configured);
+  if (e != cudaSuccess) return (int)e;
   gemm_kernel<EPI><<<grid, kNumThreads, smem, s>>>(ma, mb, p);
   return (int)cudaGetLastError();
 }

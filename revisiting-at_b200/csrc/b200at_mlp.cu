@@ -36,6 +36,7 @@
 #include <stdlib.h>
 
 #include "b200at_gelu.cuh"
+#include "b200at_launch.cuh"
 #include "b200at_tcgen05.cuh"
 #include "../../include/b200at_model.h"
 
@@ -460,12 +461,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const __grid_constant_
 template <int C, int MODE>
 int launch(const CUtensorMap& ma, const CUtensorMap& mwa, const CUtensorMap& mwb, const CUtensorMap& mz,
            const CUtensorMap& mp, const MlpParams& p, int grid, cudaStream_t s) {
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(mlp_kernel<C, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, MlpCfg<C>::Smem);
-    if (e != cudaSuccess) return (int)e;
-    configured = true;
-  }
+  static std::atomic<uint64_t> configured{0};
+  cudaError_t e = b200at::ensure_dynamic_smem(mlp_kernel<C, MODE>, (int)MlpCfg<C>::Smem, configured);
+  if (e != cudaSuccess) return (int)e;
   mlp_kernel<C, MODE><<<grid, kThreads, MlpCfg<C>::Smem, s>>>(ma, mwa, mwb, mz, mp, p);
   return (int)cudaGetLastError();
 }
