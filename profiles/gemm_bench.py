@@ -39,4 +39,12 @@ for M, C in ((401408, 96), (100352, 192), (25088, 384), (6272, 768)):
             torch.matmul(a, w.t(), out=c)
             _abi.bias_gelu_fwd(c, bias, c2)
         t4 = t(unfused)
-        print(f'{M:8d} {N:6d} {K:6d} | {t1 * 1e3:10.1f} {fl / t1 / 1e9:7.1f} | {t2 * 1e3:10.1f} {fl / t2 / 1e9:7.1f} | {t3 * 1e3:13.1f} {t4 * 1e3:14.1f}')
+        # the backward's pair: dz = (dout W2g) * GELU'(z) fused in the epilogue vs tcgen05 GEMM + bias_gelu_bwd kernel
+        z0 = torch.zeros(N, device=dev)
+        t5 = t(lambda: _abi.gemm_bf16(a, w, c, _abi.EPI_GELU_GRAD, aux=c2))
+        def unfused_bwd():
+            _abi.gemm_bf16(a, w, c, _abi.EPI_NONE)
+            _abi.bias_gelu_bwd(c, c2, z0, c, None)
+        t6 = t(unfused_bwd) if N > K else float('nan')
+        print(f'{M:8d} {N:6d} {K:6d} | {t1 * 1e3:10.1f} {fl / t1 / 1e9:7.1f} | {t2 * 1e3:10.1f} {fl / t2 / 1e9:7.1f} | {t3 * 1e3:13.1f} {t4 * 1e3:14.1f}'
+              f' | gelu_grad fused {t5 * 1e3:7.1f} us, gemm + gelu_bwd {t6 * 1e3:7.1f} us')

@@ -241,8 +241,7 @@ def l2_step(x, x_adv, x_old, x_new, grad, x_best, grad_best, x_best_adv, state, 
             _img(grad, x, 'grad'), _img(x_best, x, 'x_best'), _img(grad_best, x, 'grad_best'),
             _img(x_best_adv, x, 'x_best_adv'), _p(state), _p(scratch), B, n, eps, a, _stream())
     with _Timed('l2_step'):
-        _check(lib().b200at_l2_step(*args), 'l2_step')
-    LAUNCHES['count'] += 3
+        _check(lib().b200at_l2_step(*args), 'l2_step')             # one cluster launch (four with B200AT_L2_PHASES=4)
     return scratch
 
 

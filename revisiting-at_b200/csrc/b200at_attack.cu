@@ -9,7 +9,9 @@
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+#include <cooperative_groups.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "b200at_bodies.cuh"
 #include "../../include/b200at.h"
@@ -123,8 +125,95 @@ __global__ void __launch_bounds__(kThreads) l2_phase_kernel(B200atImages p, floa
   }
 }
 
+// Single-launch form: a cluster of kL2Cluster CTAs owns one sample and runs the four phases back to back.  Each CTA
+// covers kChunks / kL2Cluster of the sample's chunks with the SAME thread -> element mapping and the same fixed-order
+// sums as the four-launch form above (bit-identical results); the per-sample norms cross the cluster through
+// distributed shared memory (one cluster barrier per norm) instead of through global scratch and a kernel boundary.
+// The operands of a sample (4 x 602 KB at 224 px) are read from HBM once: phases 0..2 load with the L2-resident policy
+// and the same CTA re-reads them microseconds later (~37 samples x 2.4 MB in flight, well inside the 126 MB L2); only
+// phase 3 streams.  HBM traffic 20 B/element instead of 52.
+constexpr int kL2Cluster = 8;
+constexpr int kL2PerCta = kChunks / kL2Cluster;
+
+template <int PHASE, int VEC>
+__device__ __forceinline__ void l2_cluster_phase(const B200atImages& p, int b, int rank, float eps, float a,
+                                                 float one_minus_a, const float* sums, float* red, float* part) {
+  const int64_t nvec_row = p.n / VEC;
+  const int64_t per = (nvec_row + kChunks - 1) / kChunks;
+  float acc[kL2PerCta];
+  int64_t v0[kL2PerCta], v1[kL2PerCta];
+#pragma unroll
+  for (int k = 0; k < kL2PerCta; ++k) {
+    acc[k] = 0.0f;
+    v0[k] = (int64_t)(rank * kL2PerCta + k) * per;
+    v1[k] = (v0[k] + per < nvec_row) ? v0[k] + per : nvec_row;
+  }
+  // the chunks of this CTA side by side (kL2PerCta independent loads in flight per thread); each accumulator still
+  // sees its chunk's elements in the order of the one-chunk-per-CTA kernel
+  for (int64_t off = threadIdx.x; off < per; off += kThreads) {
+#pragma unroll
+    for (int k = 0; k < kL2PerCta; ++k) {
+      const int64_t v = v0[k] + off;
+      if (v < v1[k])
+        acc[k] += b200at_l2_body<PHASE, VEC, (PHASE < 3)>(p, (int64_t)b * nvec_row + v, eps, a, one_minus_a, sums);
+    }
+  }
+  if (PHASE < 3) {
+#pragma unroll
+    for (int k = 0; k < kL2PerCta; ++k) {
+      const float t = cta_sum(acc[k], red);
+      if (threadIdx.x == 0) part[PHASE * kL2PerCta + k] = t;
+    }
+  }
+}
+
+// the 32 chunk partials of one phase, gathered from the cluster's CTAs and added in chunk_total's butterfly order
+__device__ __forceinline__ float l2_cluster_total(cooperative_groups::cluster_group& cluster, float* part, int phase) {
+  const int lane = threadIdx.x & 31;
+  const float* remote = cluster.map_shared_rank(part, lane / kL2PerCta);
+  float t = remote[phase * kL2PerCta + (lane % kL2PerCta)];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  return t;
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(kThreads) l2_cluster_kernel(B200atImages p, float eps, float a, float one_minus_a) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  __shared__ float red[kThreads / 32];
+  __shared__ float part[3 * kL2PerCta];
+  const int rank = (int)cluster.block_rank();
+  const int b = blockIdx.y;
+  float sums[3] = {0.f, 0.f, 0.f};
+  l2_cluster_phase<0, VEC>(p, b, rank, eps, a, one_minus_a, sums, red, part);
+  cluster.sync();
+  sums[0] = l2_cluster_total(cluster, part, 0);
+  l2_cluster_phase<1, VEC>(p, b, rank, eps, a, one_minus_a, sums, red, part);
+  cluster.sync();
+  sums[1] = l2_cluster_total(cluster, part, 1);
+  l2_cluster_phase<2, VEC>(p, b, rank, eps, a, one_minus_a, sums, red, part);
+  cluster.sync();
+  sums[2] = l2_cluster_total(cluster, part, 2);
+  l2_cluster_phase<3, VEC>(p, b, rank, eps, a, one_minus_a, sums, red, part);
+  cluster.sync();   // nobody leaves while a peer may still be reading its partials
+}
+
 template <int VEC>
 int launch_l2(const B200atImages& p, float* scratch, float eps, float a, float oma, cudaStream_t s) {
+  static const bool four_launches = [] { const char* e = getenv("B200AT_L2_PHASES"); return e != nullptr && e[0] == '4'; }();
+  if (!four_launches) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(kL2Cluster, (unsigned)p.B);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kL2Cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return (int)cudaLaunchKernelEx(&cfg, l2_cluster_kernel<VEC>, p, eps, a, oma);
+  }
   dim3 grid(kChunks, (unsigned)p.B);
   l2_phase_kernel<0, VEC><<<grid, kThreads, 0, s>>>(p, scratch, eps, a, oma);
   l2_phase_kernel<1, VEC><<<grid, kThreads, 0, s>>>(p, scratch, eps, a, oma);

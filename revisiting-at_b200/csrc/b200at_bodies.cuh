@@ -32,6 +32,20 @@ __device__ __forceinline__ void b200at_st_stream(float* p, const B200atVec<VEC>&
     for (int i = 0; i < VEC; ++i) __stcs(p + i, r.v[i]);
   }
 }
+// L2-resident (ld.global.cg: no L1 allocation, normal L2 eviction priority) 16-byte loads for operands that a later
+// phase of the SAME kernel reads again (the single-launch l2 move)
+template <int VEC>
+__device__ __forceinline__ B200atVec<VEC> b200at_ld_keep(const float* p) {
+  B200atVec<VEC> r;
+  if constexpr (VEC == 4) {
+    const float4 t = __ldcg(reinterpret_cast<const float4*>(p));
+    r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
+  } else {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) r.v[i] = __ldcg(p + i);
+  }
+  return r;
+}
 // default-policy store: the new iterate is read next by the model's first layer, keep it in L2
 template <int VEC>
 __device__ __forceinline__ void b200at_st_keep(float* p, const B200atVec<VEC>& r) {
@@ -49,6 +63,8 @@ B200AT_HD B200atVec<VEC> b200at_ld_stream(const float* p) {
   for (int i = 0; i < VEC; ++i) r.v[i] = p[i];
   return r;
 }
+template <int VEC>
+B200AT_HD B200atVec<VEC> b200at_ld_keep(const float* p) { return b200at_ld_stream<VEC>(p); }
 template <int VEC>
 B200AT_HD void b200at_st_stream(float* p, const B200atVec<VEC>& r) {
   for (int i = 0; i < VEC; ++i) p[i] = r.v[i];
@@ -175,7 +191,8 @@ B200AT_HD void b200at_fgsm_step_body(const float* x, const float* x_adv, const f
 // ---- K2: l2 update, one phase per call (autopgd_train_clean.py:228-237).  Phases 0..2 return the
 // partial sum of squares of this vector; phase 3 writes the new iterate and applies the pending ops
 // exactly like the l-inf body.  `sums` = {||g||^2, ||z-x||^2, ||w-x||^2} of this sample so far.
-template <int PHASE, int VEC>
+// KEEP: load with the L2-resident policy (phases 0..2 of the single-launch form: the next phase re-reads the operands).
+template <int PHASE, int VEC, bool KEEP = false>
 B200AT_HD float b200at_l2_body(const B200atImages& p, int64_t vi, float eps, float a, float one_minus_a,
                                const float* sums) {
   const int64_t e = vi * VEC;
@@ -190,12 +207,21 @@ B200AT_HD float b200at_l2_body(const B200atImages& p, int64_t vi, float eps, flo
   const float n2 = PHASE > 2 ? sqrtf(sums[2]) : 0.0f;
 
   B200atVec<VEC> x, xo, xc, g;
-  g = b200at_ld_stream<VEC>((restore ? p.grad_best : p.grad) + e);
-  if (PHASE > 0) {
-    x = b200at_ld_stream<VEC>(p.x + e);
-    xc = b200at_ld_stream<VEC>((restore ? p.x_best : p.x_adv) + e);
+  if (KEEP) {
+    g = b200at_ld_keep<VEC>((restore ? p.grad_best : p.grad) + e);
+    if (PHASE > 0) {
+      x = b200at_ld_keep<VEC>(p.x + e);
+      xc = b200at_ld_keep<VEC>((restore ? p.x_best : p.x_adv) + e);
+    }
+    if (PHASE > 1) xo = b200at_ld_keep<VEC>(p.x_old + e);
+  } else {
+    g = b200at_ld_stream<VEC>((restore ? p.grad_best : p.grad) + e);
+    if (PHASE > 0) {
+      x = b200at_ld_stream<VEC>(p.x + e);
+      xc = b200at_ld_stream<VEC>((restore ? p.x_best : p.x_adv) + e);
+    }
+    if (PHASE > 1) xo = b200at_ld_stream<VEC>(p.x_old + e);
   }
-  if (PHASE > 1) xo = b200at_ld_stream<VEC>(p.x_old + e);
   if (PHASE == 3) {
     if (!restore) {
       if (write_adv) b200at_st_stream<VEC>(p.x_best_adv + e, xc);

@@ -737,6 +737,10 @@ int launch_dwconv(const void* x, const float* wt, const float* bias, const void*
 
 }  // namespace
 
+// b200at_dwconv_mma.cu: -1 = shape not covered, else the launch's cudaError_t
+int b200at_dwconv7_mma_launch(const void* x, const float* wt, const float* bias, const void* add, void* y, int64_t B,
+                              int64_t H, int64_t W, int64_t C, void* stream);
+
 extern "C" {
 
 int b200at_ln_fwd(const void* x, const float* w, const float* b, void* y, float* mean, float* rstd, int64_t M,
@@ -841,6 +845,13 @@ int b200at_add_bf16(const void* a, const void* b, void* c, int64_t total, void* 
 int b200at_dwconv7_fwd(const void* x, const float* wt, const float* bias, const void* add, void* y, int64_t B,
                        int64_t H, int64_t W, int64_t C, void* stream) {
   if (B <= 0) return 0;
+  // tensor-core (banded Toeplitz) kernel for every shape it covers: b200at_dwconv_mma.cu; B200AT_DW_MMA=0 keeps the
+  // fp32-FMA kernel below (A/B measurements, and shapes wider than 80 columns)
+  static const bool use_mma = [] { const char* e = getenv("B200AT_DW_MMA"); return e == nullptr || e[0] != '0'; }();
+  if (use_mma) {
+    const int r = b200at_dwconv7_mma_launch(x, wt, bias, add, y, B, H, W, C, stream);
+    if (r >= 0) return r;
+  }
   if (C % kDwCh || (reinterpret_cast<uintptr_t>(x) & 15)) return (int)cudaErrorInvalidValue;
   cudaStream_t s = (cudaStream_t)stream;
   // tile shapes: wide maps 14 x 28; 14-wide maps two images side by side; the 7 x 7 maps of the last stage three

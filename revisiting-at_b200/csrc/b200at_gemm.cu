@@ -29,10 +29,11 @@ typedef __nv_bfloat16 bf16;
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;            // 64 bf16 = 128 B = one SWIZZLE_128B row
 constexpr int kUmmaK = 16;
-constexpr int kStages = 4;
 constexpr int kEpilogueWarp0 = 4;      // warps 0..3: TMA / MMA / TMEM-alloc / idle
-constexpr int kEpilogueWarps = 8;      // warps 4..11
-constexpr int kNumThreads = 32 * (kEpilogueWarp0 + kEpilogueWarps);
+// Epilogue warps EW (template parameter): 8 (warps 4..11, 4-stage operand ring) for the light epilogues; 16 (warps 4..19,
+// 3-stage ring) for the GELU / GELU' epilogues, whose ~30 instructions per element on 8 warps took twice the tile's MMA
+// time (profiles/r01_gemm_bench_v2.txt) -- with 16 warps (4 per TMEM lane quarter, one 64-column strip each at
+// BLOCK_N = 256) the epilogue of tile i hides under the MMAs of tile i+1 (double-buffered accumulator).
 constexpr int kStripCols = 64;         // columns per epilogue strip (128 B of bf16 per row)
 constexpr int kStageTileBytes = 32 * kStripCols * 2;   // per-warp staging tile: 32 rows x 128 B
 
@@ -157,8 +158,8 @@ struct GemmParams {
   int block_n, tiles_m, tiles_n;
 };
 
-template <int EPI>
-__global__ void __launch_bounds__(kNumThreads, 1) gemm_kernel(const __grid_constant__ CUtensorMap map_a,
+template <int EPI, int EW>
+__global__ void __launch_bounds__(32 * (kEpilogueWarp0 + EW), 1) gemm_kernel(const __grid_constant__ CUtensorMap map_a,
                                                               const __grid_constant__ CUtensorMap map_b,
                                                               const GemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -167,13 +168,14 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_kernel(const __grid_const
   const uint32_t a_bytes = kBlockM * kBlockK * 2;
   const uint32_t b_bytes = (uint32_t)p.block_n * kBlockK * 2;
   const uint32_t stage_bytes = a_bytes + b_bytes;
+  constexpr int kStages = EW > 8 ? 3 : 4;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * stage_bytes);
   uint64_t* full = bars;                   // [kStages]
   uint64_t* empty = bars + kStages;        // [kStages]
   uint64_t* tfull = bars + 2 * kStages;    // [2]
   uint64_t* tempty = bars + 2 * kStages + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
-  uint8_t* staging = smem + kStages * stage_bytes + 256;   // [kEpilogueWarps][kStageTileBytes]
+  uint8_t* staging = smem + kStages * stage_bytes + 256;   // [EW][kStageTileBytes]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_k = (p.K + kBlockK - 1) / kBlockK;
@@ -186,7 +188,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_kernel(const __grid_const
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], kEpilogueWarps); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], EW); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -250,7 +252,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_kernel(const __grid_const
   } else if (warp >= kEpilogueWarp0) {
     // ------------------------------------------------------------------ epilogue (TMEM -> regs -> smem -> global)
     const int q = warp & 3;                            // TMEM lane quarter this warp may access
-    const int half = (warp - kEpilogueWarp0) >> 2;     // which of the two warps of that quarter
+    const int half = (warp - kEpilogueWarp0) >> 2;     // which of the EW / 4 warps of that quarter
     uint8_t* tile = staging + (warp - kEpilogueWarp0) * kStageTileBytes;
     int it = 0;
     for (int tile_id = blockIdx.x; tile_id < num_tiles; tile_id += gridDim.x, ++it) {
@@ -264,7 +266,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) gemm_kernel(const __grid_const
       const bool row_ok = row < p.M;
       const int64_t row_off = (int64_t)row * p.N;
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.block_n);
-      for (int s0 = half * kStripCols; s0 < p.block_n; s0 += 2 * kStripCols) {
+      for (int s0 = half * kStripCols; s0 < p.block_n; s0 += (EW / 4) * kStripCols) {
         const int width = (p.block_n - s0) < kStripCols ? (p.block_n - s0) : kStripCols;   // multiple of 16
         const int col0 = tn * p.block_n + s0;
         float f[kStripCols];
@@ -380,11 +382,15 @@ int pick_block_n(int64_t N) {
 }
 
 template <int EPI>
-int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, size_t smem, int grid, cudaStream_t s) {
+int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, int grid, cudaStream_t s) {
+  constexpr int EW = (EPI == B200AT_EPI_BIAS_GELU || EPI == B200AT_EPI_GELU_GRAD) ? 16 : 8;
+  constexpr int kStages = EW > 8 ? 3 : 4;
+  const size_t smem = 1024 + (size_t)kStages * (kBlockM * kBlockK * 2 + (size_t)p.block_n * kBlockK * 2) + 256 +
+                      (size_t)EW * kStageTileBytes;
   static std::atomic<uint64_t> configured{0};
-  cudaError_t e = b200at::ensure_dynamic_smem(gemm_kernel<EPI>, 227 * 1024, configured);
+  cudaError_t e = b200at::ensure_dynamic_smem(gemm_kernel<EPI, EW>, 227 * 1024, configured);
   if (e != cudaSuccess) return (int)e;
-  gemm_kernel<EPI><<<grid, kNumThreads, smem, s>>>(ma, mb, p);
+  gemm_kernel<EPI, EW><<<grid, 32 * (kEpilogueWarp0 + EW), smem, s>>>(ma, mb, p);
   return (int)cudaGetLastError();
 }
 
@@ -409,15 +415,13 @@ extern "C" int b200at_gemm_bf16(const void* a, const void* b, void* c, void* c2,
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int tiles = p.tiles_m * p.tiles_n;
   const int grid = tiles < sms ? tiles : sms;
-  const size_t smem = 1024 + (size_t)kStages * (kBlockM * kBlockK * 2 + (size_t)p.block_n * kBlockK * 2) + 256 +
-                      (size_t)kEpilogueWarps * kStageTileBytes;
   cudaStream_t s = (cudaStream_t)stream;
   switch (epilogue) {
-    case B200AT_EPI_NONE: return launch<B200AT_EPI_NONE>(ma, mb, p, smem, grid, s);
-    case B200AT_EPI_BIAS: return launch<B200AT_EPI_BIAS>(ma, mb, p, smem, grid, s);
-    case B200AT_EPI_BIAS_GELU: return launch<B200AT_EPI_BIAS_GELU>(ma, mb, p, smem, grid, s);
-    case B200AT_EPI_RESIDUAL: return launch<B200AT_EPI_RESIDUAL>(ma, mb, p, smem, grid, s);
-    case B200AT_EPI_GELU_GRAD: return launch<B200AT_EPI_GELU_GRAD>(ma, mb, p, smem, grid, s);
+    case B200AT_EPI_NONE: return launch<B200AT_EPI_NONE>(ma, mb, p, grid, s);
+    case B200AT_EPI_BIAS: return launch<B200AT_EPI_BIAS>(ma, mb, p, grid, s);
+    case B200AT_EPI_BIAS_GELU: return launch<B200AT_EPI_BIAS_GELU>(ma, mb, p, grid, s);
+    case B200AT_EPI_RESIDUAL: return launch<B200AT_EPI_RESIDUAL>(ma, mb, p, grid, s);
+    case B200AT_EPI_GELU_GRAD: return launch<B200AT_EPI_GELU_GRAD>(ma, mb, p, grid, s);
     default: return (int)cudaErrorInvalidValue;
   }
 }

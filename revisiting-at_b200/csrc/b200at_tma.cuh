@@ -53,6 +53,21 @@ __device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* ba
       : "memory");
 }
 
+// 4-D tiled store shared -> global (bulk async-group completion); elements outside the tensor -- negative coordinates
+// included -- are not written
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all committed bulk stores have finished READING their shared-memory source (it may be overwritten)
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// ... and have completed (before the CTA exits)
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// generic-proxy shared-memory accesses before this fence are ordered with async-proxy (TMA) accesses after it
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -73,8 +88,10 @@ inline EncodeTiledFn encode_tiled_fn() {
 
 // NHWC bf16 activation [B][H][W][C] as a 4-D tensor (C, W, H, B), box (box_c, box_w, box_h, box_b), no swizzle:
 // the box lands in shared memory as dense [box_b][box_h][box_w][box_c]
+// swizzle32: CU_TENSOR_MAP_SWIZZLE_32B (box_c * 2 bytes must be 32): the 16-byte half of a pixel's 32 bytes is XORed with
+// bit 7 of its shared-memory offset, which makes 8 consecutive pixels of one half a conflict-free ldmatrix / stmatrix
 inline bool make_map_nhwc_bf16(CUtensorMap* map, const void* ptr, int64_t B, int64_t H, int64_t W, int64_t C, int box_c,
-                               int box_w, int box_h, int box_b) {
+                               int box_w, int box_h, int box_b, bool swizzle32 = false) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (!fn) return false;
   const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
@@ -82,8 +99,8 @@ inline bool make_map_nhwc_bf16(CUtensorMap* map, const void* ptr, int64_t B, int
   const cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)box_b};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+            CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 }  // namespace b200at

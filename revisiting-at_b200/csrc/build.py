@@ -17,6 +17,7 @@ UNITS = [
     # (source, extra flags)
     ('b200at_attack.cu', ['-fmad=false']),
     ('b200at_convnext.cu', []),
+    ('b200at_dwconv_mma.cu', []),
     ('b200at_gemm.cu', []),
     ('b200at_mlp.cu', []),
     ('b200at_stem.cu', []),

@@ -48,7 +48,9 @@ def test_layernorm_fwd_bwd(ops, cuda_dev, C, gelu):
     assert torch.equal(dx2, dx)
 
 
-@pytest.mark.parametrize('shape', [(2, 56, 56, 96), (3, 28, 28, 192), (2, 14, 14, 384), (5, 7, 7, 768), (1, 20, 23, 32)])
+@pytest.mark.parametrize('shape', [(2, 56, 56, 96), (3, 28, 28, 192), (2, 14, 14, 384), (5, 7, 7, 768), (1, 20, 23, 32),
+                                   (2, 80, 80, 32), (3, 40, 40, 64), (9, 10, 10, 48), (2, 33, 47, 16), (1, 5, 3, 16),
+                                   (2, 17, 96, 32)])
 def test_dwconv7_fwd_dgrad_wgrad(ops, cuda_dev, shape):
     B, H, W, C = shape
     g = torch.Generator(device='cuda').manual_seed(H * C)
@@ -62,10 +64,34 @@ def test_dwconv7_fwd_dgrad_wgrad(ops, cuda_dev, shape):
     xt = x.clone().requires_grad_()
     out = ops._DwConv7.apply(xt, w, b)
     _close(out, ref.permute(0, 2, 3, 1), atol=2e-2)
+    if C % 32:                                     # the weight-gradient kernel works on 32-channel groups
+        with ops.input_grad_only():
+            out = ops._DwConv7.apply(xt, w, b)
+        (dx,) = torch.autograd.grad(out, [xt], dy)
+        _close(dx, rdx.permute(0, 2, 3, 1), atol=2e-2)
+        return
     dx, dw, db = torch.autograd.grad(out, [xt, w, b], dy)
     _close(dx, rdx.permute(0, 2, 3, 1), atol=2e-2)
     _close(dw, rdw, atol=1e-2 * (B * H * W) ** 0.5, rtol=1e-2)
     _close(db, rdb, atol=1e-2 * (B * H * W) ** 0.5, rtol=1e-2)
+
+
+@pytest.mark.parametrize('shape', [(3, 56, 56, 96), (5, 14, 14, 64), (9, 7, 7, 32), (2, 80, 80, 16)])
+def test_dwconv7_input_gradient_with_the_residual_join(cuda_dev, shape):
+    """b200at_dwconv7_fwd(dy, flipped taps, add=dout): the block's backward join (models/convnext.py:49) in the same pass"""
+    import revisiting_at_b200  # noqa: F401
+    from revisiting_at_b200 import _abi
+    B, H, W, C = shape
+    g = torch.Generator(device='cuda').manual_seed(7 * H + C)
+    dy = torch.randn(B, H, W, C, generator=g, device=cuda_dev).to(BF16)
+    res = torch.randn(B, H, W, C, generator=g, device=cuda_dev).to(BF16)
+    w = torch.randn(C, 1, 7, 7, generator=g, device=cuda_dev) * 0.1
+    wtf = w.reshape(C, 49).t().flip(0).contiguous()
+    out = torch.full_like(dy, float('nan'))
+    _abi.dwconv7_fwd(dy, wtf, None, out, add=res)
+    ref = F.conv_transpose2d(dy.float().permute(0, 3, 1, 2), w, padding=3, groups=C).permute(0, 2, 3, 1) + res.float()
+    _close(out, ref, atol=3e-2)
+    assert bool(torch.isfinite(out.float()).all())
 
 
 def test_bias_gelu_and_scale_residual(ops, cuda_dev):
