@@ -125,55 +125,44 @@ __global__ void __launch_bounds__(kThreads) l2_phase_kernel(B200atImages p, floa
   }
 }
 
-// Single-launch form: a cluster of kL2Cluster CTAs owns one sample and runs the four phases back to back.  Each CTA
-// covers kChunks / kL2Cluster of the sample's chunks with the SAME thread -> element mapping and the same fixed-order
-// sums as the four-launch form above (bit-identical results); the per-sample norms cross the cluster through
-// distributed shared memory (one cluster barrier per norm) instead of through global scratch and a kernel boundary.
-// The operands of a sample (4 x 602 KB at 224 px) are read from HBM once: phases 0..2 load with the L2-resident policy
-// and the same CTA re-reads them microseconds later (~37 samples x 2.4 MB in flight, well inside the 126 MB L2); only
-// phase 3 streams.  HBM traffic 20 B/element instead of 52.
+// Single-launch form: a cluster of kL2Cluster CTAs owns one sample and runs the four phases back to back; the per-sample
+// norms cross the cluster through distributed shared memory (one cluster barrier per norm) instead of through global
+// scratch and a kernel boundary.  Each CTA sums a contiguous eighth of the sample (thread -> warp -> CTA, fixed order), the
+// 8 partials are added in rank order by every thread: deterministic, but a different association than the four-launch
+// form (the l2 path is tolerance-checked: 1e-6 on x).  The operands of a sample (4 x 602 KB at 224 px) are read from HBM
+// once: phases 0..2 load with the L2-resident policy and the same CTA re-reads them microseconds later; occupancy is
+// held at 2 CTAs per SM (37 samples x 2.4 MB in flight, inside the 126 MB L2) by the dynamic shared-memory request.
+// HBM traffic 20 B/element instead of 52.
 constexpr int kL2Cluster = 8;
-constexpr int kL2PerCta = kChunks / kL2Cluster;
+constexpr int kL2SmemCap = 100 * 1024;    // dynamic shared memory per CTA: unused, bounds residency to 2 CTAs / SM
 
 template <int PHASE, int VEC>
-__device__ __forceinline__ void l2_cluster_phase(const B200atImages& p, int b, int rank, float eps, float a,
-                                                 float one_minus_a, const float* sums, float* red, float* part) {
-  const int64_t nvec_row = p.n / VEC;
-  const int64_t per = (nvec_row + kChunks - 1) / kChunks;
-  float acc[kL2PerCta];
-  int64_t v0[kL2PerCta], v1[kL2PerCta];
-#pragma unroll
-  for (int k = 0; k < kL2PerCta; ++k) {
-    acc[k] = 0.0f;
-    v0[k] = (int64_t)(rank * kL2PerCta + k) * per;
-    v1[k] = (v0[k] + per < nvec_row) ? v0[k] + per : nvec_row;
+__device__ __forceinline__ float l2_cluster_phase(const B200atImages& p, int b, int rank, float eps, float a,
+                                                  float one_minus_a, const float* sums, float* red) {
+  const int nvec_row = (int)(p.n / VEC);                 // n < 2^31 (checked by the entry point)
+  const int per = (nvec_row + kL2Cluster - 1) / kL2Cluster;
+  const int v0 = rank * per, v1 = (v0 + per < nvec_row) ? v0 + per : nvec_row;
+  const B200atL2Ctx ctx = b200at_l2_ctx<PHASE>(p, b, sums);
+  const int64_t base = (int64_t)b * p.n;
+  float acc0 = 0.0f, acc1 = 0.0f, acc2 = 0.0f, acc3 = 0.0f;
+  int v = v0 + threadIdx.x;
+  for (; v + 3 * kThreads < v1; v += 4 * kThreads) {      // four independent vectors in flight per thread
+    acc0 += b200at_l2_body_ctx<PHASE, VEC, (PHASE < 3)>(p, base + (int64_t)v * VEC, ctx, eps, a, one_minus_a);
+    acc1 += b200at_l2_body_ctx<PHASE, VEC, (PHASE < 3)>(p, base + (int64_t)(v + kThreads) * VEC, ctx, eps, a, one_minus_a);
+    acc2 += b200at_l2_body_ctx<PHASE, VEC, (PHASE < 3)>(p, base + (int64_t)(v + 2 * kThreads) * VEC, ctx, eps, a, one_minus_a);
+    acc3 += b200at_l2_body_ctx<PHASE, VEC, (PHASE < 3)>(p, base + (int64_t)(v + 3 * kThreads) * VEC, ctx, eps, a, one_minus_a);
   }
-  // the chunks of this CTA side by side (kL2PerCta independent loads in flight per thread); each accumulator still
-  // sees its chunk's elements in the order of the one-chunk-per-CTA kernel
-  for (int64_t off = threadIdx.x; off < per; off += kThreads) {
-#pragma unroll
-    for (int k = 0; k < kL2PerCta; ++k) {
-      const int64_t v = v0[k] + off;
-      if (v < v1[k])
-        acc[k] += b200at_l2_body<PHASE, VEC, (PHASE < 3)>(p, (int64_t)b * nvec_row + v, eps, a, one_minus_a, sums);
-    }
-  }
-  if (PHASE < 3) {
-#pragma unroll
-    for (int k = 0; k < kL2PerCta; ++k) {
-      const float t = cta_sum(acc[k], red);
-      if (threadIdx.x == 0) part[PHASE * kL2PerCta + k] = t;
-    }
-  }
+  for (; v < v1; v += kThreads)
+    acc0 += b200at_l2_body_ctx<PHASE, VEC, (PHASE < 3)>(p, base + (int64_t)v * VEC, ctx, eps, a, one_minus_a);
+  if (PHASE == 3) return 0.0f;
+  return cta_sum((acc0 + acc1) + (acc2 + acc3), red);    // valid in warp 0
 }
 
-// the 32 chunk partials of one phase, gathered from the cluster's CTAs and added in chunk_total's butterfly order
+// the kL2Cluster partials of one phase, gathered from the cluster's CTAs and added in rank order
 __device__ __forceinline__ float l2_cluster_total(cooperative_groups::cluster_group& cluster, float* part, int phase) {
-  const int lane = threadIdx.x & 31;
-  const float* remote = cluster.map_shared_rank(part, lane / kL2PerCta);
-  float t = remote[phase * kL2PerCta + (lane % kL2PerCta)];
+  float t = 0.0f;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  for (int r = 0; r < kL2Cluster; ++r) t += cluster.map_shared_rank(part, r)[phase];
   return t;
 }
 
@@ -182,20 +171,23 @@ __global__ void __launch_bounds__(kThreads) l2_cluster_kernel(B200atImages p, fl
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
   __shared__ float red[kThreads / 32];
-  __shared__ float part[3 * kL2PerCta];
+  __shared__ float part[3];
   const int rank = (int)cluster.block_rank();
   const int b = blockIdx.y;
   float sums[3] = {0.f, 0.f, 0.f};
-  l2_cluster_phase<0, VEC>(p, b, rank, eps, a, one_minus_a, sums, red, part);
+  float t = l2_cluster_phase<0, VEC>(p, b, rank, eps, a, one_minus_a, sums, red);
+  if (threadIdx.x == 0) part[0] = t;
   cluster.sync();
   sums[0] = l2_cluster_total(cluster, part, 0);
-  l2_cluster_phase<1, VEC>(p, b, rank, eps, a, one_minus_a, sums, red, part);
+  t = l2_cluster_phase<1, VEC>(p, b, rank, eps, a, one_minus_a, sums, red);
+  if (threadIdx.x == 0) part[1] = t;
   cluster.sync();
   sums[1] = l2_cluster_total(cluster, part, 1);
-  l2_cluster_phase<2, VEC>(p, b, rank, eps, a, one_minus_a, sums, red, part);
+  t = l2_cluster_phase<2, VEC>(p, b, rank, eps, a, one_minus_a, sums, red);
+  if (threadIdx.x == 0) part[2] = t;
   cluster.sync();
   sums[2] = l2_cluster_total(cluster, part, 2);
-  l2_cluster_phase<3, VEC>(p, b, rank, eps, a, one_minus_a, sums, red, part);
+  l2_cluster_phase<3, VEC>(p, b, rank, eps, a, one_minus_a, sums, red);
   cluster.sync();   // nobody leaves while a peer may still be reading its partials
 }
 
@@ -206,8 +198,16 @@ int launch_l2(const B200atImages& p, float* scratch, float eps, float a, float o
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(kL2Cluster, (unsigned)p.B);
     cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = 0;
+    cfg.dynamicSmemBytes = kL2SmemCap;
     cfg.stream = s;
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!configured[dev & 63]) {
+      cudaError_t e = cudaFuncSetAttribute(l2_cluster_kernel<VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, kL2SmemCap);
+      if (e != cudaSuccess) return (int)e;
+      configured[dev & 63] = true;
+    }
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = kL2Cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
@@ -801,7 +801,7 @@ int b200at_l2_step(const float* x, float* x_adv, const float* x_old, float* x_ne
                    int64_t B, int64_t n, float eps, float a, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   if (B <= 0 || n <= 0) return (int)cudaSuccess;
-  if (B > 65535) return (int)cudaErrorInvalidValue;
+  if (B > 65535 || n >= (int64_t)1 << 31) return (int)cudaErrorInvalidValue;
   B200atImages p{x, x_adv, x_old, x_new, grad, x_best, grad_best, x_best_adv, state, B, n};
   const float oma = (float)(1.0 - (double)a);
   const bool v4 = (n % 4 == 0) && aligned16(x) && aligned16(x_adv) && aligned16(x_old) && aligned16(x_new) &&

@@ -191,21 +191,31 @@ B200AT_HD void b200at_fgsm_step_body(const float* x, const float* x_adv, const f
 // ---- K2: l2 update, one phase per call (autopgd_train_clean.py:228-237).  Phases 0..2 return the
 // partial sum of squares of this vector; phase 3 writes the new iterate and applies the pending ops
 // exactly like the l-inf body.  `sums` = {||g||^2, ||z-x||^2, ||w-x||^2} of this sample so far.
-// KEEP: load with the L2-resident policy (phases 0..2 of the single-launch form: the next phase re-reads the operands).
-template <int PHASE, int VEC, bool KEEP = false>
-B200AT_HD float b200at_l2_body(const B200atImages& p, int64_t vi, float eps, float a, float one_minus_a,
-                               const float* sums) {
-  const int64_t e = vi * VEC;
-  const int b = (int)(e / p.n);
+// Per-sample constants of one l2 phase: read / derived once per sample by the single-launch kernel (the per-vector form
+// below rebuilds them for every vector: a 64-bit division for the sample index, three square roots, two state loads).
+struct B200atL2Ctx {
+  float step;
+  B200atL2Norms nm;
+  bool improved, write_adv, restore;
+};
+template <int PHASE>
+B200AT_HD B200atL2Ctx b200at_l2_ctx(const B200atImages& p, int b, const float* sums) {
+  B200atL2Ctx c;
   const int32_t fl = b200at_f2i(p.st[(int64_t)B200AT_ST_FLAGS * p.B + b]);
-  const float step = p.st[(int64_t)B200AT_ST_STEP * p.B + b];
-  const bool improved = fl & B200AT_F_IMPROVED;
-  const bool write_adv = fl & B200AT_F_WRITE_ADV;
-  const bool restore = (fl & B200AT_F_RESTORE) && !improved;
-  const float gnorm = PHASE > 0 ? sqrtf(sums[0]) : 0.0f;
-  const float n1 = PHASE > 1 ? sqrtf(sums[1]) : 0.0f;
-  const float n2 = PHASE > 2 ? sqrtf(sums[2]) : 0.0f;
+  c.step = p.st[(int64_t)B200AT_ST_STEP * p.B + b];
+  c.improved = fl & B200AT_F_IMPROVED;
+  c.write_adv = fl & B200AT_F_WRITE_ADV;
+  c.restore = (fl & B200AT_F_RESTORE) && !c.improved;
+  c.nm = b200at_l2_norms<PHASE>(sums);
+  return c;
+}
 
+// KEEP: load with the L2-resident policy (phases 0..2 of the single-launch form: the next phase re-reads the operands).
+// `e` = first element of the vector (of sample b, whose constants are in c).
+template <int PHASE, int VEC, bool KEEP>
+B200AT_HD float b200at_l2_body_ctx(const B200atImages& p, int64_t e, const B200atL2Ctx& c, float eps, float a,
+                                   float one_minus_a) {
+  const bool improved = c.improved, write_adv = c.write_adv, restore = c.restore;
   B200atVec<VEC> x, xo, xc, g;
   if (KEEP) {
     g = b200at_ld_keep<VEC>((restore ? p.grad_best : p.grad) + e);
@@ -239,11 +249,20 @@ B200AT_HD float b200at_l2_body(const B200atImages& p, int64_t vi, float eps, flo
 #pragma unroll
   for (int i = 0; i < VEC; ++i) {
     o.v[i] = b200at_l2_elem<PHASE>(PHASE > 0 ? x.v[i] : 0.0f, PHASE > 0 ? xc.v[i] : 0.0f, PHASE > 1 ? xo.v[i] : 0.0f,
-                                   g.v[i], step, eps, a, one_minus_a, gnorm, n1, n2);
+                                   g.v[i], c.step, eps, a, one_minus_a, c.nm);
     acc = B200AT_ADD(acc, B200AT_MUL(o.v[i], o.v[i]));
   }
   if (PHASE == 3) b200at_st_keep<VEC>(p.x_new + e, o);
   return acc;
+}
+
+// per-vector form (four-launch kernels, tests/hostcheck): vi = vector index over the whole batch
+template <int PHASE, int VEC>
+B200AT_HD float b200at_l2_body(const B200atImages& p, int64_t vi, float eps, float a, float one_minus_a,
+                               const float* sums) {
+  const int64_t e = vi * VEC;
+  const int b = (int)(e / p.n);
+  return b200at_l2_body_ctx<PHASE, VEC, false>(p, e, b200at_l2_ctx<PHASE>(p, b, sums), eps, a, one_minus_a);
 }
 
 // ---- iterate-log variants (n_iter + 1 <= B200AT_LOG_MAX_SLOTS): no image copies at all -------------

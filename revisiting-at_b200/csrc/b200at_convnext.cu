@@ -32,6 +32,24 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
   return *reinterpret_cast<float2*>(&rd);
 }
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b), rd;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  return *reinterpret_cast<float2*>(&rd);
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+  unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b), rd;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  return *reinterpret_cast<float2*>(&rd);
+}
+// bf16x2 word -> two fp32 (exact): low half << 16, high half masked -- two ALU-pipe instructions, none on the FMA pipe
+__device__ __forceinline__ float2 bf2_to_f2(uint32_t u) {
+  return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+}
+__device__ __forceinline__ uint32_t f2_to_bf2(float2 v) {
+  const bf162 t = __floats2bfloat162_rn(v.x, v.y);
+  return *reinterpret_cast<const uint32_t*>(&t);
+}
 __device__ __forceinline__ void unpack4(const uint2& u, float* f) {
   const float2 a = __bfloat1622float2(*reinterpret_cast<const bf162*>(&u.x));
   const float2 b = __bfloat1622float2(*reinterpret_cast<const bf162*>(&u.y));
@@ -220,6 +238,269 @@ __global__ void __launch_bounds__(kLnThreads) ln_bwd_kernel(const bf16* __restri
     }
     __syncthreads();
     for (int c = threadIdx.x; c < C; c += kLnThreads) {
+      atomicAdd(dw + c, red[c]);
+      atomicAdd(db + c, red[C + c]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ K8, pipelined form
+// The kernels above keep one row per lane group in flight (3 x 8-byte loads per lane): 3.7-4.0 TB/s of the 6.5 TB/s copy
+// rate (profiles/r01_ncu_dwconv_stem0_v11_summary.txt) -- not enough bytes in flight per SM.  Rows of [M][C] are
+// contiguous, so a tile of rows is ONE cp.async.bulk (global -> shared, mbarrier completion): persistent CTAs run a
+// kRingStages-deep ring of input tiles (>= 100 KB in flight per SM), the same lane-group arithmetic reads its rows from
+// shared memory, results leave through a double-buffered output tile and one cp.async.bulk store per tile.  The
+// per-row statistics ride in the ring as two more (small) bulk copies in the backward.
+constexpr int kRingThreads = 512;
+constexpr int kRingStages = 3;
+
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   b200at::smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(b200at::smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_store(void* dst, const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(b200at::smem_u32(src)),
+               "r"(bytes)
+               : "memory");
+}
+
+// C == 4 * G * VPL exactly (no lane predicates); arithmetic on packed fp32 pairs (add / mul / fma .f32x2): the scalar form
+// of this loop issued 25 instructions per element and was ISSUE-bound at 0.52 of the HBM rate
+// (profiles/r02_ln_ring_ncu_v1.txt), this one ~6.
+template <int G, int VPL, bool GELU>
+__global__ void __launch_bounds__(kRingThreads) ln_fwd_ring_kernel(const bf16* __restrict__ x, const float* __restrict__ w,
+                                                                  const float* __restrict__ b, bf16* __restrict__ y,
+                                                                  float* __restrict__ mean, float* __restrict__ rstd,
+                                                                  int64_t M, float eps, int tile_rows) {
+  constexpr int C = 4 * G * VPL;
+  constexpr int kRowBytes = 2 * C;
+  extern __shared__ __align__(128) uint8_t ring_smem[];
+  const int tile_bytes = tile_rows * kRowBytes;            // multiple of 16
+  const int tile_pad = (tile_bytes + 127) & ~127;
+  uint8_t* in0 = ring_smem;
+  uint8_t* out0 = ring_smem + kRingStages * tile_pad;
+  uint64_t* full = reinterpret_cast<uint64_t*>(ring_smem + (kRingStages + 2) * tile_pad);
+  const int tid = threadIdx.x, gl = tid % G;
+  constexpr int kRows = kRingThreads / G;
+  float2 wr[VPL][2], br[VPL][2];
+#pragma unroll
+  for (int j = 0; j < VPL; ++j) {
+    const int c = (gl + G * j) * 4;
+    wr[j][0] = make_float2(w[c], w[c + 1]); wr[j][1] = make_float2(w[c + 2], w[c + 3]);
+    br[j][0] = make_float2(b[c], b[c + 1]); br[j][1] = make_float2(b[c + 2], b[c + 3]);
+  }
+  constexpr float inv_c = 1.0f / (float)C;
+  const int64_t tiles = (M + tile_rows - 1) / tile_rows;
+  auto rows_of = [&](int64_t t) { const int64_t left = M - t * tile_rows; return (int)(left < tile_rows ? left : tile_rows); };
+  if (tid == 0) {
+    for (int s = 0; s < kRingStages; ++s) b200at::mbar_init(&full[s], 1);
+    b200at::mbar_fence_init();
+    for (int s = 0; s < kRingStages; ++s) {
+      const int64_t t = (int64_t)blockIdx.x + (int64_t)s * gridDim.x;
+      if (t < tiles) {
+        const uint32_t bytes = (uint32_t)rows_of(t) * kRowBytes;
+        b200at::mbar_expect_tx(&full[s], bytes);
+        bulk_load(in0 + s * tile_pad, x + t * tile_rows * C, bytes, &full[s]);
+      }
+    }
+  }
+  __syncthreads();
+  int k = 0;
+  for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x, ++k) {
+    const int s = k % kRingStages, ob = k & 1;
+    const int rows = rows_of(t);
+    b200at::mbar_wait(&full[s], (uint32_t)((k / kRingStages) & 1));
+    const uint8_t* in = in0 + s * tile_pad;
+    uint8_t* out = out0 + ob * tile_pad;
+    float* mean_t = mean + t * tile_rows;
+    float* rstd_t = rstd + t * tile_rows;
+    const int rows_pad = (rows + kRows - 1) / kRows * kRows;     // whole warps stay in the loop (shuffles)
+    for (int r = tid / G; r < rows_pad; r += kRows) {
+      const bool live = r < rows;
+      const uint2* xr = reinterpret_cast<const uint2*>(in + (live ? r : 0) * kRowBytes) + gl;
+      float2 f[VPL][2];
+      float2 sum2 = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < VPL; ++j) {
+        const uint2 u = xr[G * j];
+        f[j][0] = bf2_to_f2(u.x); f[j][1] = bf2_to_f2(u.y);
+        sum2 = fadd2(sum2, fadd2(f[j][0], f[j][1]));
+      }
+      const float mu = group_sum<G>(sum2.x + sum2.y) * inv_c;
+      const float2 nmu = make_float2(-mu, -mu);
+      float2 q2 = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < VPL; ++j) {
+        f[j][0] = fadd2(f[j][0], nmu); f[j][1] = fadd2(f[j][1], nmu);
+        q2 = ffma2(f[j][0], f[j][0], q2);
+        q2 = ffma2(f[j][1], f[j][1], q2);
+      }
+      const float rs = rsqrtf(group_sum<G>(q2.x + q2.y) * inv_c + eps);
+      if (!live) continue;
+      const float2 rs2 = make_float2(rs, rs);
+      uint2* yr = reinterpret_cast<uint2*>(out + r * kRowBytes) + gl;
+#pragma unroll
+      for (int j = 0; j < VPL; ++j) {
+        float2 o0 = ffma2(f[j][0], fmul2(rs2, wr[j][0]), br[j][0]);
+        float2 o1 = ffma2(f[j][1], fmul2(rs2, wr[j][1]), br[j][1]);
+        if (GELU) {
+          o0.x = gelu_f(o0.x); o0.y = gelu_f(o0.y); o1.x = gelu_f(o1.x); o1.y = gelu_f(o1.y);
+        }
+        yr[G * j] = make_uint2(f2_to_bf2(o0), f2_to_bf2(o1));
+      }
+      if (gl == 0) { mean_t[r] = mu; rstd_t[r] = rs; }
+    }
+    b200at::fence_proxy_async();
+    if (tid == 0) b200at::tma_store_wait_read();      // the store of tile k-1 has drained the OTHER output buffer
+    __syncthreads();
+    if (tid == 0) {
+      bulk_store(y + t * tile_rows * C, out, (uint32_t)rows * kRowBytes);
+      b200at::tma_store_commit();
+      const int64_t tn = t + (int64_t)kRingStages * gridDim.x;
+      if (tn < tiles) {
+        const uint32_t bytes = (uint32_t)rows_of(tn) * kRowBytes;
+        b200at::mbar_expect_tx(&full[s], bytes);
+        bulk_load(in0 + s * tile_pad, x + tn * tile_rows * C, bytes, &full[s]);
+      }
+    }
+  }
+  if (tid == 0) b200at::tma_store_wait_all();
+}
+
+template <int G, int VPL, bool GELU, bool PGRAD>
+__global__ void __launch_bounds__(kRingThreads) ln_bwd_ring_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
+                                                                  const float* __restrict__ w, const float* __restrict__ b,
+                                                                  const float* __restrict__ mean,
+                                                                  const float* __restrict__ rstd, bf16* __restrict__ dx,
+                                                                  float* __restrict__ dw, float* __restrict__ db,
+                                                                  int64_t M, int tile_rows) {
+  constexpr int C = 4 * G * VPL;
+  constexpr int kRowBytes = 2 * C;
+  extern __shared__ __align__(128) uint8_t ring_smem[];
+  const int tile_bytes = tile_rows * kRowBytes;
+  const int stat_bytes = tile_rows * 4;                    // tile_rows % 4 == 0
+  const int stage_pad = ((2 * tile_bytes + 2 * stat_bytes) + 127) & ~127;   // [dy tile][x tile][mean][rstd]
+  const int out_pad = (tile_bytes + 127) & ~127;
+  uint8_t* in0 = ring_smem;
+  uint8_t* out0 = ring_smem + kRingStages * stage_pad;
+  uint64_t* full = reinterpret_cast<uint64_t*>(ring_smem + kRingStages * stage_pad + 2 * out_pad);
+  float* red = reinterpret_cast<float*>(full + kRingStages);   // PGRAD: [2][C]
+  const int tid = threadIdx.x, gl = tid % G;
+  constexpr int kRows = kRingThreads / G;
+  float2 wr[VPL][2], br[VPL][2], aw[VPL][2], ab[VPL][2];
+#pragma unroll
+  for (int j = 0; j < VPL; ++j) {
+    const int c = (gl + G * j) * 4;
+    wr[j][0] = make_float2(w[c], w[c + 1]); wr[j][1] = make_float2(w[c + 2], w[c + 3]);
+    br[j][0] = GELU ? make_float2(b[c], b[c + 1]) : make_float2(0.f, 0.f);
+    br[j][1] = GELU ? make_float2(b[c + 2], b[c + 3]) : make_float2(0.f, 0.f);
+    aw[j][0] = aw[j][1] = ab[j][0] = ab[j][1] = make_float2(0.f, 0.f);
+  }
+  if (PGRAD)
+    for (int c = tid; c < 2 * C; c += kRingThreads) red[c] = 0.f;
+  constexpr float inv_c = 1.0f / (float)C;
+  const int64_t tiles = (M + tile_rows - 1) / tile_rows;
+  auto rows_of = [&](int64_t t) { const int64_t left = M - t * tile_rows; return (int)(left < tile_rows ? left : tile_rows); };
+  auto issue = [&](int s, int64_t t) {                      // thread 0 only
+    const int rows = rows_of(t);
+    const uint32_t bytes = (uint32_t)rows * kRowBytes, sb = (uint32_t)(rows & ~3) * 4;   // statistics: whole 16-byte pieces
+    uint8_t* st = in0 + s * stage_pad;
+    float* mu_s = reinterpret_cast<float*>(st + 2 * tile_bytes);
+    float* rs_s = reinterpret_cast<float*>(st + 2 * tile_bytes + stat_bytes);
+    for (int r = rows & ~3; r < rows; ++r) {                // the last tile's 1-3 odd rows: plain copies (every reader
+      mu_s[r] = mean[t * tile_rows + r];                    // passes a __syncthreads before it uses this stage)
+      rs_s[r] = rstd[t * tile_rows + r];
+    }
+    b200at::mbar_expect_tx(&full[s], 2 * bytes + 2 * sb);
+    bulk_load(st, dy + t * tile_rows * C, bytes, &full[s]);
+    bulk_load(st + tile_bytes, x + t * tile_rows * C, bytes, &full[s]);
+    if (sb) {
+      bulk_load(mu_s, mean + t * tile_rows, sb, &full[s]);
+      bulk_load(rs_s, rstd + t * tile_rows, sb, &full[s]);
+    }
+  };
+  if (tid == 0) {
+    for (int s = 0; s < kRingStages; ++s) b200at::mbar_init(&full[s], 1);
+    b200at::mbar_fence_init();
+    for (int s = 0; s < kRingStages; ++s) {
+      const int64_t t = (int64_t)blockIdx.x + (int64_t)s * gridDim.x;
+      if (t < tiles) issue(s, t);
+    }
+  }
+  __syncthreads();
+  int k = 0;
+  for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x, ++k) {
+    const int s = k % kRingStages, ob = k & 1;
+    const int rows = rows_of(t);
+    b200at::mbar_wait(&full[s], (uint32_t)((k / kRingStages) & 1));
+    const uint8_t* st = in0 + s * stage_pad;
+    const float* mu_t = reinterpret_cast<const float*>(st + 2 * tile_bytes);
+    const float* rs_t = reinterpret_cast<const float*>(st + 2 * tile_bytes + stat_bytes);
+    uint8_t* out = out0 + ob * out_pad;
+    const int rows_pad = (rows + kRows - 1) / kRows * kRows;
+    for (int r = tid / G; r < rows_pad; r += kRows) {
+      const bool live = r < rows;
+      const int rr = live ? r : 0;
+      const uint2* gr = reinterpret_cast<const uint2*>(st + rr * kRowBytes) + gl;
+      const uint2* xr = reinterpret_cast<const uint2*>(st + tile_bytes + rr * kRowBytes) + gl;
+      const float mu = mu_t[rr], rs = live ? rs_t[rr] : 0.f;
+      const float2 rs2 = make_float2(rs, rs), nmr = make_float2(-mu * rs, -mu * rs);
+      float2 xh[VPL][2], g[VPL][2];
+      float2 s1 = make_float2(0.f, 0.f), s2 = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < VPL; ++j) {
+        const uint2 ux = xr[G * j], ud = gr[G * j];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          xh[j][h] = ffma2(bf2_to_f2(h ? ux.y : ux.x), rs2, nmr);          // (x - mean) * rstd
+          float2 d = bf2_to_f2(h ? ud.y : ud.x);
+          if (!live) d = make_float2(0.f, 0.f);
+          if (GELU) {
+            const float2 pre = ffma2(xh[j][h], wr[j][h], br[j][h]);
+            d.x *= gelu_grad_f(pre.x); d.y *= gelu_grad_f(pre.y);
+          }
+          if (PGRAD) { aw[j][h] = ffma2(d, xh[j][h], aw[j][h]); ab[j][h] = fadd2(ab[j][h], d); }
+          g[j][h] = fmul2(d, wr[j][h]);
+          s1 = fadd2(s1, g[j][h]);
+          s2 = ffma2(g[j][h], xh[j][h], s2);
+        }
+      }
+      const float m1 = group_sum<G>(s1.x + s1.y) * inv_c, m2 = group_sum<G>(s2.x + s2.y) * inv_c;
+      if (!live) continue;
+      const float2 nm2 = make_float2(-m2, -m2), nm1 = make_float2(-m1, -m1);
+      uint2* dr = reinterpret_cast<uint2*>(out + r * kRowBytes) + gl;
+#pragma unroll
+      for (int j = 0; j < VPL; ++j) {
+        // rstd * (g - mean(g) - xhat * mean(g * xhat))
+        const float2 o0 = fmul2(rs2, fadd2(ffma2(xh[j][0], nm2, g[j][0]), nm1));
+        const float2 o1 = fmul2(rs2, fadd2(ffma2(xh[j][1], nm2, g[j][1]), nm1));
+        dr[G * j] = make_uint2(f2_to_bf2(o0), f2_to_bf2(o1));
+      }
+    }
+    b200at::fence_proxy_async();
+    if (tid == 0) b200at::tma_store_wait_read();
+    __syncthreads();
+    if (tid == 0) {
+      bulk_store(dx + t * tile_rows * C, out, (uint32_t)rows * kRowBytes);
+      b200at::tma_store_commit();
+      const int64_t tn = t + (int64_t)kRingStages * gridDim.x;
+      if (tn < tiles) issue(s, tn);
+    }
+  }
+  if (tid == 0) b200at::tma_store_wait_all();
+  if (PGRAD) {
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+      const int c = (gl + G * j) * 4;
+      atomicAdd(&red[c], aw[j][0].x); atomicAdd(&red[c + 1], aw[j][0].y);
+      atomicAdd(&red[c + 2], aw[j][1].x); atomicAdd(&red[c + 3], aw[j][1].y);
+      atomicAdd(&red[C + c], ab[j][0].x); atomicAdd(&red[C + c + 1], ab[j][0].y);
+      atomicAdd(&red[C + c + 2], ab[j][1].x); atomicAdd(&red[C + c + 3], ab[j][1].y);
+    }
+    __syncthreads();
+    for (int c = tid; c < C; c += kRingThreads) {
       atomicAdd(dw + c, red[c]);
       atomicAdd(db + c, red[C + c]);
     }
@@ -675,11 +956,53 @@ inline int ln_grid(int64_t M, int G) {
 #define B200AT_LN_FOR_VPL(G, X) X(G, 1) X(G, 2) X(G, 3) X(G, 4) X(G, 5) X(G, 6) X(G, 7) X(G, 8) X(G, 9) X(G, 10) X(G, 11) X(G, 12)
 #define B200AT_LN_FOR_ALL(X) B200AT_LN_FOR_VPL(32, X) B200AT_LN_FOR_VPL(16, X) B200AT_LN_FOR_VPL(8, X) B200AT_LN_FOR_VPL(4, X)
 
+// (G, VPL) pairs the pipelined kernels are built for: every ConvNeXt-T/S/B/L and ViT-S width (C = 48 ... 1536)
+#define B200AT_RING_FOR_VPL(G, X) X(G, 1) X(G, 2) X(G, 3) X(G, 4) X(G, 6)
+#define B200AT_RING_FOR_ALL(X) B200AT_RING_FOR_VPL(32, X) B200AT_RING_FOR_VPL(16, X) B200AT_RING_FOR_VPL(8, X) B200AT_RING_FOR_VPL(4, X)
+inline bool ring_shape_ok(int G, int VPL, int C) { return (VPL == 1 || VPL == 2 || VPL == 3 || VPL == 4 || VPL == 6) && C == 4 * G * VPL; }
+inline bool use_ring(int64_t M, int C) {
+  static const bool on = [] { const char* e = getenv("B200AT_LN_RING"); return e == nullptr || e[0] != '0'; }();
+  return on && C % 8 == 0 && M * C >= (int64_t)1 << 19;   // >= 1 MB of rows: enough tiles for every SM
+}
+// rows per tile: whole passes of the CTA (kRingThreads / G rows each), ~12 KB, a multiple of 4 rows
+inline int ring_tile_rows(int G, int C) {
+  const int pass = kRingThreads / G;
+  int passes = 12288 / (pass * C * 2);
+  if (passes < 1) passes = 1;
+  return pass * passes;
+}
+inline int ring_grid(int64_t M, int tile_rows, size_t smem) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int per_sm = (int)((size_t)(227 * 1024) / (smem + 1024));
+  per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);     // 4 x 512 threads = the SM's 2048
+  const int64_t tiles = (M + tile_rows - 1) / tile_rows, cap = (int64_t)sms * per_sm;
+  return (int)(tiles < cap ? tiles : cap);
+}
+
 template <bool GELU>
 int launch_ln_fwd(const bf16* x, const float* w, const float* b, bf16* y, float* mean, float* rstd, int64_t M, int C,
                   float eps, cudaStream_t s, int pH = 0, int pW = 0) {
   int G, VPL;
   ln_shape(C / 4, G, VPL);
+  if (pW == 0 && use_ring(M, C) && ring_shape_ok(G, VPL, C)) {
+    const int tr = ring_tile_rows(G, C);
+    const size_t smem = (size_t)(kRingStages + 2) * (((size_t)tr * C * 2 + 127) & ~(size_t)127) + 64;
+    if (smem <= 200 * 1024) {
+      const int grid = ring_grid(M, tr, smem);
+#define B200AT_CASE(GG, V)                                                                                               \
+      if (G == GG && VPL == V) {                                                                                         \
+        static b200at::SmemConfig conf;                                                                            \
+        cudaError_t e = b200at::ensure_dynamic_smem(ln_fwd_ring_kernel<GG, V, GELU>, (int)smem, conf);                   \
+        if (e != cudaSuccess) return (int)e;                                                                             \
+        ln_fwd_ring_kernel<GG, V, GELU><<<grid, kRingThreads, smem, s>>>(x, w, b, y, mean, rstd, M, eps, tr);             \
+        return (int)cudaGetLastError();                                                                                  \
+      }
+      B200AT_RING_FOR_ALL(B200AT_CASE)
+#undef B200AT_CASE
+    }
+  }
   const int g = ln_grid(M, G);
 #define B200AT_CASE(GG, V) \
   if (G == GG && VPL == V) { ln_fwd_kernel<GG, V, GELU><<<g, kLnThreads, 0, s>>>(x, w, b, y, mean, rstd, M, C, eps, pH, pW); return (int)cudaGetLastError(); }
@@ -693,6 +1016,26 @@ int launch_ln_bwd(const bf16* dy, const bf16* x, const float* w, const float* b,
                   bf16* dx, float* dw, float* db, int64_t M, int C, cudaStream_t s, int pH = 0, int pW = 0) {
   int G, VPL;
   ln_shape(C / 4, G, VPL);
+  if (pW == 0 && use_ring(M, C) && ring_shape_ok(G, VPL, C) && (reinterpret_cast<uintptr_t>(mean) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(rstd) & 15) == 0) {
+    const int tr = ring_tile_rows(G, C);
+    const size_t tb = (size_t)tr * C * 2;
+    const size_t smem = (size_t)kRingStages * ((2 * tb + 8 * (size_t)tr + 127) & ~(size_t)127) + 2 * ((tb + 127) & ~(size_t)127) +
+                        64 + (PGRAD ? sizeof(float) * 2 * C : 0);
+    if (smem <= 200 * 1024) {
+      const int grid = ring_grid(M, tr, smem);
+#define B200AT_CASE(GG, V)                                                                                               \
+      if (G == GG && VPL == V) {                                                                                         \
+        static b200at::SmemConfig conf;                                                                            \
+        cudaError_t e = b200at::ensure_dynamic_smem(ln_bwd_ring_kernel<GG, V, GELU, PGRAD>, (int)smem, conf);            \
+        if (e != cudaSuccess) return (int)e;                                                                             \
+        ln_bwd_ring_kernel<GG, V, GELU, PGRAD><<<grid, kRingThreads, smem, s>>>(dy, x, w, b, mean, rstd, dx, dw, db, M, tr); \
+        return (int)cudaGetLastError();                                                                                  \
+      }
+      B200AT_RING_FOR_ALL(B200AT_CASE)
+#undef B200AT_CASE
+    }
+  }
   const int g = ln_grid(M, G);
   const size_t sm = PGRAD ? sizeof(float) * 2 * C : 0;
 #define B200AT_CASE(GG, V) \
@@ -724,7 +1067,7 @@ int launch_dwconv(const void* x, const float* wt, const float* bias, const void*
   const int grid = (int)(total < cap ? total : cap);
 #define B200AT_DW(BI, AD)                                                                                     \
   do {                                                                                                        \
-    static std::atomic<uint64_t> configured{0};                                                               \
+    static b200at::SmemConfig configured;                                                               \
     cudaError_t e = b200at::ensure_dynamic_smem(dwconv7_kernel<TH, TW, NB, BI, AD>, T::kSmem, configured);    \
     if (e != cudaSuccess) return (int)e;                                                                      \
     dwconv7_kernel<TH, TW, NB, BI, AD><<<grid, T::kThreads, T::kSmem, s>>>(map, p);                            \

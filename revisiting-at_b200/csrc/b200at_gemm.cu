@@ -387,7 +387,7 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, in
   constexpr int kStages = EW > 8 ? 3 : 4;
   const size_t smem = 1024 + (size_t)kStages * (kBlockM * kBlockK * 2 + (size_t)p.block_n * kBlockK * 2) + 256 +
                       (size_t)EW * kStageTileBytes;
-  static std::atomic<uint64_t> configured{0};
+  static b200at::SmemConfig configured;
   cudaError_t e = b200at::ensure_dynamic_smem(gemm_kernel<EPI, EW>, 227 * 1024, configured);
   if (e != cudaSuccess) return (int)e;
   gemm_kernel<EPI, EW><<<grid, 32 * (kEpilogueWarp0 + EW), smem, s>>>(ma, mb, p);

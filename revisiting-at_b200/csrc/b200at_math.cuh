@@ -180,29 +180,58 @@ B200AT_HD void b200at_bookkeep_sample(float* st, float* loss_steps, int B, int b
 // ------------------------------------------------------------------------------------------------
 // l2 move (autopgd_train_clean.py:228-237).  Three dependent per-sample norms:
 // ||g||, ||z - x||, ||w - x||; each phase recomputes the elementwise chain up to its reduction.
-B200AT_HD float b200at_l2_z(float xc, float g, float step, float gnorm) {
-  return B200AT_ADD(xc, B200AT_DIV(B200AT_MUL(step, g), B200AT_ADD(gnorm, 1e-12f)));
+// Division by a per-sample constant c = norm + 1e-12 whose correctly rounded reciprocal rc is computed once per sample:
+// q0 = RN(d rc), e = d - c q0 (exact, one FMA), q = RN(q0 + e rc) -- Markstein's sequence, equal to the IEEE quotient
+// except for a last-place difference in rare cases (the l2 path is tolerance-checked at 1e-6: the norms themselves depend
+// on the summation order).  3 instructions instead of the ~20 of __fdiv_rn, 6 divisions per element and iteration.
+#if defined(__CUDA_ARCH__)
+B200AT_HD float b200at_div_by(float d, float c, float rc) {
+  const float q0 = __fmul_rn(d, rc);
+  const float e = __fmaf_rn(-c, q0, d);
+  return __fmaf_rn(e, rc, q0);
 }
-// clamp(x + d / (||d|| + 1e-12) * min(eps, ||d||), 0, 1)
-B200AT_HD float b200at_l2_ball(float x, float d, float nrm, float eps) {
-  const float q = B200AT_DIV(d, B200AT_ADD(nrm, 1e-12f));
+B200AT_HD float b200at_rcp(float c) { return __frcp_rn(c); }
+#else
+B200AT_HD float b200at_div_by(float d, float c, float rc) { (void)rc; return d / c; }
+B200AT_HD float b200at_rcp(float c) { return 1.0f / c; }
+#endif
+B200AT_HD float b200at_l2_z(float xc, float g, float step, float gden, float grcp) {
+  return B200AT_ADD(xc, b200at_div_by(B200AT_MUL(step, g), gden, grcp));
+}
+// clamp(x + d / (||d|| + 1e-12) * min(eps, ||d||), 0, 1);  den = ||d|| + 1e-12, rcp = 1 / den
+B200AT_HD float b200at_l2_ball(float x, float d, float nrm, float den, float rcp, float eps) {
+  const float q = b200at_div_by(d, den, rcp);
   return b200at_clamp01(B200AT_ADD(x, B200AT_MUL(q, b200at_min(eps, nrm))));
 }
 B200AT_HD float b200at_momentum(float xc, float z, float xo, float a, float one_minus_a) {
   const float w = B200AT_ADD(xc, B200AT_MUL(B200AT_SUB(z, xc), a));
   return B200AT_ADD(w, B200AT_MUL(B200AT_SUB(xc, xo), one_minus_a));
 }
+// the three norms of a sample with their denominators (norm + 1e-12) and reciprocals
+struct B200atL2Norms {
+  float n[3], den[3], rcp[3];
+};
+template <int PHASE>
+B200AT_HD B200atL2Norms b200at_l2_norms(const float* sums) {
+  B200atL2Norms r;
+  for (int i = 0; i < 3; ++i) {
+    r.n[i] = i < PHASE ? sqrtf(sums[i]) : 0.0f;
+    r.den[i] = B200AT_ADD(r.n[i], 1e-12f);
+    r.rcp[i] = i < PHASE ? b200at_rcp(r.den[i]) : 0.0f;
+  }
+  return r;
+}
 // value whose square is accumulated in phase 0/1/2, or the new iterate in phase 3
 template <int PHASE>
 B200AT_HD float b200at_l2_elem(float x, float xc, float xo, float g, float step, float eps, float a,
-                               float one_minus_a, float gnorm, float n1, float n2) {
+                               float one_minus_a, const B200atL2Norms& nm) {
   if (PHASE == 0) return g;
-  const float d1 = B200AT_SUB(b200at_l2_z(xc, g, step, gnorm), x);
+  const float d1 = B200AT_SUB(b200at_l2_z(xc, g, step, nm.den[0], nm.rcp[0]), x);
   if (PHASE == 1) return d1;
-  const float z1 = b200at_l2_ball(x, d1, n1, eps);
+  const float z1 = b200at_l2_ball(x, d1, nm.n[1], nm.den[1], nm.rcp[1], eps);
   const float d2 = B200AT_SUB(b200at_momentum(xc, z1, xo, a, one_minus_a), x);
   if (PHASE == 2) return d2;
-  return b200at_l2_ball(x, d2, n2, eps);
+  return b200at_l2_ball(x, d2, nm.n[2], nm.den[2], nm.rcp[2], eps);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -461,7 +461,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const __grid_constant_
 template <int C, int MODE>
 int launch(const CUtensorMap& ma, const CUtensorMap& mwa, const CUtensorMap& mwb, const CUtensorMap& mz,
            const CUtensorMap& mp, const MlpParams& p, int grid, cudaStream_t s) {
-  static std::atomic<uint64_t> configured{0};
+  static b200at::SmemConfig configured;
   cudaError_t e = b200at::ensure_dynamic_smem(mlp_kernel<C, MODE>, (int)MlpCfg<C>::Smem, configured);
   if (e != cudaSuccess) return (int)e;
   mlp_kernel<C, MODE><<<grid, kThreads, MlpCfg<C>::Smem, s>>>(ma, mwa, mwb, mz, mp, p);

@@ -49,7 +49,7 @@ def test_layernorm_fwd_bwd(ops, cuda_dev, C, gelu):
 
 
 @pytest.mark.parametrize('shape', [(2, 56, 56, 96), (3, 28, 28, 192), (2, 14, 14, 384), (5, 7, 7, 768), (1, 20, 23, 32),
-                                   (2, 80, 80, 32), (3, 40, 40, 64), (9, 10, 10, 48), (2, 33, 47, 16), (1, 5, 3, 16),
+                                   (2, 80, 80, 32), (3, 40, 40, 64), (9, 10, 10, 64), (2, 33, 47, 16), (1, 5, 3, 32),
                                    (2, 17, 96, 32)])
 def test_dwconv7_fwd_dgrad_wgrad(ops, cuda_dev, shape):
     B, H, W, C = shape
@@ -92,6 +92,19 @@ def test_dwconv7_input_gradient_with_the_residual_join(cuda_dev, shape):
     ref = F.conv_transpose2d(dy.float().permute(0, 3, 1, 2), w, padding=3, groups=C).permute(0, 2, 3, 1) + res.float()
     _close(out, ref, atol=3e-2)
     assert bool(torch.isfinite(out.float()).all())
+
+
+@pytest.mark.parametrize('shape', ['2 14 14 64', '5 7 7 32 add', '9 10 10 48 add', '1 5 3 16', '4 14 14 384 add'])
+def test_tensor_core_dwconv_on_the_narrow_maps_it_does_not_serve_by_default(cuda_dev, shape):
+    """Maps narrower than 20 columns are dispatched to the FMA kernel (faster there); the tensor-core kernel still covers
+    them (NB > 1 tiles, image masks) -- forced here through B200AT_DWM_MINW=1 in a fresh process (the switch is read once)."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, B200AT_DWM_MINW='1')
+    out = subprocess.run([sys.executable, os.path.join(root, 'profiles', 'debug', 'dwm_probe.py')] + shape.split(),
+                         env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert 'bad count 0 ' in out.stdout and "nan 0" in out.stdout, out.stdout
 
 
 def test_bias_gelu_and_scale_residual(ops, cuda_dev):
