@@ -25,6 +25,17 @@ int b200at_ln_fwd(const void* x, const float* w, const float* b, void* y, float*
 int b200at_ln_bwd(const void* dy, const void* x, const float* w, const float* b, const float* mean, const float* rstd,
                   void* dx, float* dw, float* db, int64_t M, int64_t C, int fuse_gelu, void* stream);
 
+/* The same two with a per-channel bias added to x first: y = LN(x + pre_bias) [-> GELU].  This is how the CvSt stem's
+ * `Conv2d(..., bias=True)` -> LayerNorm (utils_architecture.py:205-211) runs when the convolution is a library call
+ * without its bias: the bias add (a full extra pass over the stem's activation, the largest of the network) rides in the
+ * LayerNorm kernel; the convolution's bias gradient is the column sum of dx (b200at_colsum_bf16).  pre_bias: fp32 [C] or
+ * null. */
+int b200at_ln_fwd_bias(const void* x, const float* pre_bias, const float* w, const float* b, void* y, float* mean,
+                       float* rstd, int64_t M, int64_t C, float eps, int fuse_gelu, void* stream);
+int b200at_ln_bwd_bias(const void* dy, const void* x, const float* pre_bias, const float* w, const float* b,
+                       const float* mean, const float* rstd, void* dx, float* dw, float* db, int64_t M, int64_t C,
+                       int fuse_gelu, void* stream);
+
 /* The LayerNorm in front of a downsample layer (models/convnext.py:79-82: LayerNorm(channels_first) -> Conv2d(k=2, s=2)),
  * writing its result in the "2x2 patch" layout [B][H/2][W/2][2][2][C] (pixel (b,h,w) -> row 4*((b*H/2+h/2)*W/2+w/2) +
  * 2*(h&1) + (w&1)), so that the stride-2 2x2 convolution becomes b200at_gemm_bf16 over [B*H/2*W/2][4C] rows with the
@@ -100,6 +111,18 @@ int b200at_stem0_bwd_input(const void* dy, const float* x, const float* mean3, c
 #define B200AT_EPI_GELU_GRAD 4
 int b200at_gemm_bf16(const void* a, const void* b, void* c, void* c2, const void* aux, const float* bias,
                      int64_t M, int64_t N, int64_t K, int epilogue, void* stream);
+
+/* Kernel-side copies of one ConvNeXt block's MLP weights, rebuilt once per optimiser step (models/convnext.py:42-49 with
+ * the layer scale `gamma` folded into pwconv2): w1b = bf16(W1) [4C][C], w1t = w1b^T [C][4C], w2g = bf16(gamma[:,None] W2)
+ * [C][4C], w2gt = w2g^T [4C][C] (the four operands b200at_mlp_fused / b200at_gemm_bf16 take in the two directions) and
+ * b2g = gamma * b2.  fp32 parameters in, one launch.  C % 32 == 0. */
+int b200at_prepare_mlp_weights(const float* w1, const float* w2, const float* b2, const float* gamma, void* w1b, void* w1t,
+                               void* w2g, void* w2gt, float* b2g, int64_t C, void* stream);
+/* Tail of the block's parameter gradients: given dW2g (gradient w.r.t. the folded gamma[:,None] W2, fp32 [C][4C]) and
+ * col = column sum of the upstream gradient:  dW2 = gamma[:,None] dW2g,  db2 = col gamma,  dgamma = rowsum(dW2g W2) + col b2
+ * (the chain rule of models/convnext.py:45-47 `x = self.gamma * x`). */
+int b200at_finish_mlp_grads(const float* dw2g, const float* w2, const float* col, const float* b2, const float* gamma,
+                            float* dw2, float* db2, float* dgamma, int64_t C, void* stream);
 
 /* The ImageNormalizer (utils_architecture.py:86-98) in front of the TRAINING forward's first (library) convolution, with
  * the cast and the layout change: y[B][H][W][3] bf16 = (x[B][3][H][W] - mean) / std, fp32 arithmetic rounded once.

@@ -92,6 +92,8 @@ def _declare(L):
     sig.update({
         'b200at_ln_fwd': [P, P, P, P, P, P, I64, I64, F, I, P],
         'b200at_ln_bwd': [P, P, P, P, P, P, P, P, P, I64, I64, I, P],
+        'b200at_ln_fwd_bias': [P, P, P, P, P, P, P, I64, I64, F, I, P],
+        'b200at_ln_bwd_bias': [P, P, P, P, P, P, P, P, P, P, I64, I64, I, P],
         'b200at_ln_fwd_patch2': [P, P, P, P, P, P, I64, I64, I64, I64, F, P],
         'b200at_ln_bwd_patch2': [P, P, P, P, P, P, P, P, P, I64, I64, I64, I64, P],
         'b200at_bias_gelu_fwd': [P, P, P, I64, I64, P],
@@ -106,6 +108,8 @@ def _declare(L):
         'b200at_mlp_fused_supported': [I64],
         'b200at_mlp_fused': [P, P, P, P, P, P, P, P, P, I64, I64, I, P],
         'b200at_normalize_nhwc_bf16': [P, P, P, P, I64, I64, I64, P],
+        'b200at_prepare_mlp_weights': [P, P, P, P, P, P, P, P, P, I64, P],
+        'b200at_finish_mlp_grads': [P, P, P, P, P, P, P, P, I64, P],
         'b200at_stem0_fwd': [P, P, P, P, P, P, P, P, I64, I64, I64, I64, F, P],
         'b200at_stem0_bwd_input': [P, P, P, P, P, P, P, P, P, I64, I64, I64, I64, F, P],
         'b200at_attn_fwd': [P, P, P, I64, I64, I64, F, P],
@@ -280,21 +284,34 @@ def _par(t, name, n=None):
     return c_void_p(t.data_ptr())
 
 
-def ln_fwd(x, w, b, y, mean, rstd, eps, gelu):
+def ln_fwd(x, w, b, y, mean, rstd, eps, gelu, pre_bias=None):
+    """y = LN(x [+ pre_bias]) [-> GELU]; pre_bias: the bias of a library convolution in front (fp32 [C])"""
     C = x.shape[-1]
     M = x.numel() // C
     with _Timed('ln_fwd'):
-        _check(lib().b200at_ln_fwd(_act(x, 'x'), _par(w, 'w', C), _par(b, 'b', C), _act(y, 'y'), _par(mean, 'mean', M),
-                                   _par(rstd, 'rstd', M), M, C, eps, int(gelu), _stream()), 'ln_fwd')
+        if pre_bias is None:
+            _check(lib().b200at_ln_fwd(_act(x, 'x'), _par(w, 'w', C), _par(b, 'b', C), _act(y, 'y'),
+                                       _par(mean, 'mean', M), _par(rstd, 'rstd', M), M, C, eps, int(gelu), _stream()),
+                   'ln_fwd')
+        else:
+            _check(lib().b200at_ln_fwd_bias(_act(x, 'x'), _par(pre_bias, 'pre_bias', C), _par(w, 'w', C), _par(b, 'b', C),
+                                            _act(y, 'y'), _par(mean, 'mean', M), _par(rstd, 'rstd', M), M, C, eps,
+                                            int(gelu), _stream()), 'ln_fwd_bias')
 
 
-def ln_bwd(dy, x, w, b, mean, rstd, dx, dw, db, gelu):
+def ln_bwd(dy, x, w, b, mean, rstd, dx, dw, db, gelu, pre_bias=None):
     C = x.shape[-1]
     M = x.numel() // C
     with _Timed('ln_bwd'):
-        _check(lib().b200at_ln_bwd(_act(dy, 'dy'), _act(x, 'x'), _par(w, 'w', C), _par(b, 'b', C), _par(mean, 'mean', M),
-                                   _par(rstd, 'rstd', M), _act(dx, 'dx'), _par(dw, 'dw', C), _par(db, 'db', C), M, C,
-                                   int(gelu), _stream()), 'ln_bwd')
+        if pre_bias is None:
+            _check(lib().b200at_ln_bwd(_act(dy, 'dy'), _act(x, 'x'), _par(w, 'w', C), _par(b, 'b', C),
+                                       _par(mean, 'mean', M), _par(rstd, 'rstd', M), _act(dx, 'dx'), _par(dw, 'dw', C),
+                                       _par(db, 'db', C), M, C, int(gelu), _stream()), 'ln_bwd')
+        else:
+            _check(lib().b200at_ln_bwd_bias(_act(dy, 'dy'), _act(x, 'x'), _par(pre_bias, 'pre_bias', C), _par(w, 'w', C),
+                                            _par(b, 'b', C), _par(mean, 'mean', M), _par(rstd, 'rstd', M), _act(dx, 'dx'),
+                                            _par(dw, 'dw', C), _par(db, 'db', C), M, C, int(gelu), _stream()),
+                   'ln_bwd_bias')
 
 
 def ln_fwd_patch2(x, w, b, y, mean, rstd, eps):
@@ -332,6 +349,35 @@ def bias_gelu_bwd(dh, z, bias, dz, dbias=None):
     with _Timed('bias_gelu_bwd'):
         _check(lib().b200at_bias_gelu_bwd(_act(dh, 'dh'), _act(z, 'z'), _par(bias, 'bias', N), _act(dz, 'dz'),
                                           _par(dbias, 'dbias', N), M, N, _stream()), 'bias_gelu_bwd')
+
+
+def prepare_mlp_weights(w1, w2, b2, gamma):
+    """One launch: {w1b, w1t, w2g, w2gt (bf16), b2g, gf (fp32)} of a ConvNeXt block (ops._prepared)."""
+    C = gamma.numel()
+    dev = w1.device
+    w1, w2, b2, gamma = (t.detach().float().contiguous() for t in (w1, w2, b2, gamma))
+    out = dict(w1b=torch.empty(4 * C, C, device=dev, dtype=torch.bfloat16), w1t=torch.empty(C, 4 * C, device=dev, dtype=torch.bfloat16),
+               w2g=torch.empty(C, 4 * C, device=dev, dtype=torch.bfloat16), w2gt=torch.empty(4 * C, C, device=dev, dtype=torch.bfloat16),
+               b2g=torch.empty(C, device=dev, dtype=torch.float32), gf=gamma)
+    with _Timed('prepare_mlp_weights'):
+        _check(lib().b200at_prepare_mlp_weights(_par(w1, 'w1', 4 * C * C), _par(w2, 'w2', 4 * C * C), _par(b2, 'b2', C),
+                                                _par(gamma, 'gamma', C), _act(out['w1b'], 'w1b'), _act(out['w1t'], 'w1t'),
+                                                _act(out['w2g'], 'w2g'), _act(out['w2gt'], 'w2gt'), _par(out['b2g'], 'b2g', C),
+                                                C, _stream()), 'prepare_mlp_weights')
+    return out
+
+
+def finish_mlp_grads(dw2g, w2, col, b2, gamma):
+    """(dW2, db2, dgamma) from the gradient w.r.t. the layer-scale-folded pwconv2 weight, one launch."""
+    C = gamma.numel()
+    dw2 = torch.empty_like(dw2g)
+    db2 = torch.empty(C, device=dw2g.device, dtype=torch.float32)
+    dgamma = torch.empty_like(db2)
+    with _Timed('finish_mlp_grads'):
+        _check(lib().b200at_finish_mlp_grads(_par(dw2g, 'dw2g', 4 * C * C), _par(w2, 'w2', 4 * C * C), _par(col, 'col', C),
+                                             _par(b2, 'b2', C), _par(gamma, 'gamma', C), _par(dw2, 'dw2', 4 * C * C),
+                                             _par(db2, 'db2', C), _par(dgamma, 'dgamma', C), C, _stream()), 'finish_mlp_grads')
+    return dw2, db2, dgamma
 
 
 def colsum_bf16(a, out):

@@ -82,6 +82,7 @@ __global__ void __launch_bounds__(kThreads) fgsm_step_kernel(const float* __rest
 // partial in scratch[phase][b][chunk]; the next phase adds the kChunks partials with a warp butterfly.
 constexpr int kChunks = 32;
 
+template <int THREADS = kThreads>
 __device__ __forceinline__ float cta_sum(float v, float* smem) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -89,7 +90,7 @@ __device__ __forceinline__ float cta_sum(float v, float* smem) {
   __syncthreads();
   float t = 0.0f;
   if (threadIdx.x < 32) {
-    t = threadIdx.x < (kThreads / 32) ? smem[threadIdx.x] : 0.0f;
+    t = threadIdx.x < (THREADS / 32) ? smem[threadIdx.x] : 0.0f;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
   }
@@ -134,6 +135,7 @@ __global__ void __launch_bounds__(kThreads) l2_phase_kernel(B200atImages p, floa
 // held at 2 CTAs per SM (37 samples x 2.4 MB in flight, inside the 126 MB L2) by the dynamic shared-memory request.
 // HBM traffic 20 B/element instead of 52.
 constexpr int kL2Cluster = 8;
+constexpr int kL2Threads = 512;           // 2 CTAs x 16 warps per SM: the loads in flight that the HBM phase needs
 constexpr int kL2SmemCap = 100 * 1024;    // dynamic shared memory per CTA: unused, bounds residency to 2 CTAs / SM
 
 template <int PHASE, int VEC>
@@ -146,16 +148,16 @@ __device__ __forceinline__ float l2_cluster_phase(const B200atImages& p, int b, 
   const int64_t base = (int64_t)b * p.n;
   float acc0 = 0.0f, acc1 = 0.0f, acc2 = 0.0f, acc3 = 0.0f;
   int v = v0 + threadIdx.x;
-  for (; v + 3 * kThreads < v1; v += 4 * kThreads) {      // four independent vectors in flight per thread
+  for (; v + 3 * kL2Threads < v1; v += 4 * kL2Threads) {      // four independent vectors in flight per thread
     acc0 += b200at_l2_body_ctx<PHASE, VEC, (PHASE < 3)>(p, base + (int64_t)v * VEC, ctx, eps, a, one_minus_a);
-    acc1 += b200at_l2_body_ctx<PHASE, VEC, (PHASE < 3)>(p, base + (int64_t)(v + kThreads) * VEC, ctx, eps, a, one_minus_a);
-    acc2 += b200at_l2_body_ctx<PHASE, VEC, (PHASE < 3)>(p, base + (int64_t)(v + 2 * kThreads) * VEC, ctx, eps, a, one_minus_a);
-    acc3 += b200at_l2_body_ctx<PHASE, VEC, (PHASE < 3)>(p, base + (int64_t)(v + 3 * kThreads) * VEC, ctx, eps, a, one_minus_a);
+    acc1 += b200at_l2_body_ctx<PHASE, VEC, (PHASE < 3)>(p, base + (int64_t)(v + kL2Threads) * VEC, ctx, eps, a, one_minus_a);
+    acc2 += b200at_l2_body_ctx<PHASE, VEC, (PHASE < 3)>(p, base + (int64_t)(v + 2 * kL2Threads) * VEC, ctx, eps, a, one_minus_a);
+    acc3 += b200at_l2_body_ctx<PHASE, VEC, (PHASE < 3)>(p, base + (int64_t)(v + 3 * kL2Threads) * VEC, ctx, eps, a, one_minus_a);
   }
-  for (; v < v1; v += kThreads)
+  for (; v < v1; v += kL2Threads)
     acc0 += b200at_l2_body_ctx<PHASE, VEC, (PHASE < 3)>(p, base + (int64_t)v * VEC, ctx, eps, a, one_minus_a);
   if (PHASE == 3) return 0.0f;
-  return cta_sum((acc0 + acc1) + (acc2 + acc3), red);    // valid in warp 0
+  return cta_sum<kL2Threads>((acc0 + acc1) + (acc2 + acc3), red);    // valid in warp 0
 }
 
 // the kL2Cluster partials of one phase, gathered from the cluster's CTAs and added in rank order
@@ -167,10 +169,10 @@ __device__ __forceinline__ float l2_cluster_total(cooperative_groups::cluster_gr
 }
 
 template <int VEC>
-__global__ void __launch_bounds__(kThreads) l2_cluster_kernel(B200atImages p, float eps, float a, float one_minus_a) {
+__global__ void __launch_bounds__(kL2Threads) l2_cluster_kernel(B200atImages p, float eps, float a, float one_minus_a) {
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
-  __shared__ float red[kThreads / 32];
+  __shared__ float red[kL2Threads / 32];
   __shared__ float part[3];
   const int rank = (int)cluster.block_rank();
   const int b = blockIdx.y;
@@ -197,7 +199,7 @@ int launch_l2(const B200atImages& p, float* scratch, float eps, float a, float o
   if (!four_launches) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(kL2Cluster, (unsigned)p.B);
-    cfg.blockDim = dim3(kThreads);
+    cfg.blockDim = dim3(kL2Threads);
     cfg.dynamicSmemBytes = kL2SmemCap;
     cfg.stream = s;
     static bool configured[64] = {};

@@ -91,11 +91,12 @@ template <int G, int VPL, bool GELU>
 __global__ void __launch_bounds__(kLnThreads) ln_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ w,
                                                             const float* __restrict__ b, bf16* __restrict__ y,
                                                             float* __restrict__ mean, float* __restrict__ rstd,
-                                                            int64_t M, int C, float eps, int pH, int pW) {
+                                                            int64_t M, int C, float eps, int pH, int pW,
+                                                            const float* __restrict__ pre_bias) {
   const int gl = threadIdx.x % G;                       // lane within the row group
   const int nv = C >> 2;
   constexpr int kRows = kLnThreads / G;                 // rows per CTA iteration
-  float wr[VPL][4], br[VPL][4];
+  float wr[VPL][4], br[VPL][4], pbr[VPL][4];
 #pragma unroll
   for (int j = 0; j < VPL; ++j) {
     const int v = gl + G * j;
@@ -103,6 +104,7 @@ __global__ void __launch_bounds__(kLnThreads) ln_fwd_kernel(const bf16* __restri
     for (int k = 0; k < 4; ++k) {
       wr[j][k] = v < nv ? w[v * 4 + k] : 0.f;
       br[j][k] = v < nv ? b[v * 4 + k] : 0.f;
+      pbr[j][k] = (pre_bias && v < nv) ? pre_bias[v * 4 + k] : 0.f;
     }
   }
   const float inv_c = 1.0f / (float)C;
@@ -117,6 +119,8 @@ __global__ void __launch_bounds__(kLnThreads) ln_fwd_kernel(const bf16* __restri
       const int v = gl + G * j;
       if (live && v < nv) {
         unpack4(__ldcs(xr + v), f[j]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) f[j][k] += pbr[j][k];
         s += (f[j][0] + f[j][1]) + (f[j][2] + f[j][3]);
       } else {
         f[j][0] = f[j][1] = f[j][2] = f[j][3] = 0.f;
@@ -159,12 +163,13 @@ __global__ void __launch_bounds__(kLnThreads) ln_bwd_kernel(const bf16* __restri
                                                             const float* __restrict__ mean,
                                                             const float* __restrict__ rstd, bf16* __restrict__ dx,
                                                             float* __restrict__ dw, float* __restrict__ db,
-                                                            int64_t M, int C, int pH, int pW) {
+                                                            int64_t M, int C, int pH, int pW,
+                                                            const float* __restrict__ pre_bias) {
   extern __shared__ float red[];  // PGRAD: [2][C] accumulated with shared-memory atomics
   const int gl = threadIdx.x % G;
   const int nv = C >> 2;
   constexpr int kRows = kLnThreads / G;
-  float wr[VPL][4], br[VPL][4], aw[VPL][4], ab[VPL][4];
+  float wr[VPL][4], br[VPL][4], aw[VPL][4], ab[VPL][4], pbr[VPL][4];
 #pragma unroll
   for (int j = 0; j < VPL; ++j) {
     const int v = gl + G * j;
@@ -172,6 +177,7 @@ __global__ void __launch_bounds__(kLnThreads) ln_bwd_kernel(const bf16* __restri
     for (int k = 0; k < 4; ++k) {
       wr[j][k] = v < nv ? w[v * 4 + k] : 0.f;
       br[j][k] = (GELU && v < nv) ? b[v * 4 + k] : 0.f;
+      pbr[j][k] = (pre_bias && v < nv) ? pre_bias[v * 4 + k] : 0.f;
       aw[j][k] = 0.f; ab[j][k] = 0.f;
     }
   }
@@ -197,7 +203,7 @@ __global__ void __launch_bounds__(kLnThreads) ln_bwd_kernel(const bf16* __restri
         unpack4(__ldcs(gr + v), dv);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          xh[j][k] = (xv[k] - mu) * rs;
+          xh[j][k] = ((xv[k] + pbr[j][k]) - mu) * rs;
           float d = dv[k];
           if (GELU) d *= gelu_grad_f(xh[j][k] * wr[j][k] + br[j][k]);
           if (PGRAD) { aw[j][k] += d * xh[j][k]; ab[j][k] += d; }
@@ -273,7 +279,8 @@ template <int G, int VPL, bool GELU>
 __global__ void __launch_bounds__(kRingThreads) ln_fwd_ring_kernel(const bf16* __restrict__ x, const float* __restrict__ w,
                                                                   const float* __restrict__ b, bf16* __restrict__ y,
                                                                   float* __restrict__ mean, float* __restrict__ rstd,
-                                                                  int64_t M, float eps, int tile_rows) {
+                                                                  int64_t M, float eps, int tile_rows,
+                                                                  const float* __restrict__ pre_bias) {
   constexpr int C = 4 * G * VPL;
   constexpr int kRowBytes = 2 * C;
   extern __shared__ __align__(128) uint8_t ring_smem[];
@@ -284,12 +291,14 @@ __global__ void __launch_bounds__(kRingThreads) ln_fwd_ring_kernel(const bf16* _
   uint64_t* full = reinterpret_cast<uint64_t*>(ring_smem + (kRingStages + 2) * tile_pad);
   const int tid = threadIdx.x, gl = tid % G;
   constexpr int kRows = kRingThreads / G;
-  float2 wr[VPL][2], br[VPL][2];
+  float2 wr[VPL][2], br[VPL][2], pbr[VPL][2];
 #pragma unroll
   for (int j = 0; j < VPL; ++j) {
     const int c = (gl + G * j) * 4;
     wr[j][0] = make_float2(w[c], w[c + 1]); wr[j][1] = make_float2(w[c + 2], w[c + 3]);
     br[j][0] = make_float2(b[c], b[c + 1]); br[j][1] = make_float2(b[c + 2], b[c + 3]);
+    pbr[j][0] = pre_bias ? make_float2(pre_bias[c], pre_bias[c + 1]) : make_float2(0.f, 0.f);
+    pbr[j][1] = pre_bias ? make_float2(pre_bias[c + 2], pre_bias[c + 3]) : make_float2(0.f, 0.f);
   }
   constexpr float inv_c = 1.0f / (float)C;
   const int64_t tiles = (M + tile_rows - 1) / tile_rows;
@@ -325,7 +334,7 @@ __global__ void __launch_bounds__(kRingThreads) ln_fwd_ring_kernel(const bf16* _
 #pragma unroll
       for (int j = 0; j < VPL; ++j) {
         const uint2 u = xr[G * j];
-        f[j][0] = bf2_to_f2(u.x); f[j][1] = bf2_to_f2(u.y);
+        f[j][0] = fadd2(bf2_to_f2(u.x), pbr[j][0]); f[j][1] = fadd2(bf2_to_f2(u.y), pbr[j][1]);
         sum2 = fadd2(sum2, fadd2(f[j][0], f[j][1]));
       }
       const float mu = group_sum<G>(sum2.x + sum2.y) * inv_c;
@@ -375,7 +384,8 @@ __global__ void __launch_bounds__(kRingThreads) ln_bwd_ring_kernel(const bf16* _
                                                                   const float* __restrict__ mean,
                                                                   const float* __restrict__ rstd, bf16* __restrict__ dx,
                                                                   float* __restrict__ dw, float* __restrict__ db,
-                                                                  int64_t M, int tile_rows) {
+                                                                  int64_t M, int tile_rows,
+                                                                  const float* __restrict__ pre_bias) {
   constexpr int C = 4 * G * VPL;
   constexpr int kRowBytes = 2 * C;
   extern __shared__ __align__(128) uint8_t ring_smem[];
@@ -389,10 +399,12 @@ __global__ void __launch_bounds__(kRingThreads) ln_bwd_ring_kernel(const bf16* _
   float* red = reinterpret_cast<float*>(full + kRingStages);   // PGRAD: [2][C]
   const int tid = threadIdx.x, gl = tid % G;
   constexpr int kRows = kRingThreads / G;
-  float2 wr[VPL][2], br[VPL][2], aw[VPL][2], ab[VPL][2];
+  float2 wr[VPL][2], br[VPL][2], aw[VPL][2], ab[VPL][2], pbr[VPL][2];
 #pragma unroll
   for (int j = 0; j < VPL; ++j) {
     const int c = (gl + G * j) * 4;
+    pbr[j][0] = pre_bias ? make_float2(pre_bias[c], pre_bias[c + 1]) : make_float2(0.f, 0.f);
+    pbr[j][1] = pre_bias ? make_float2(pre_bias[c + 2], pre_bias[c + 3]) : make_float2(0.f, 0.f);
     wr[j][0] = make_float2(w[c], w[c + 1]); wr[j][1] = make_float2(w[c + 2], w[c + 3]);
     br[j][0] = GELU ? make_float2(b[c], b[c + 1]) : make_float2(0.f, 0.f);
     br[j][1] = GELU ? make_float2(b[c + 2], b[c + 3]) : make_float2(0.f, 0.f);
@@ -454,7 +466,7 @@ __global__ void __launch_bounds__(kRingThreads) ln_bwd_ring_kernel(const bf16* _
         const uint2 ux = xr[G * j], ud = gr[G * j];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          xh[j][h] = ffma2(bf2_to_f2(h ? ux.y : ux.x), rs2, nmr);          // (x - mean) * rstd
+          xh[j][h] = ffma2(fadd2(bf2_to_f2(h ? ux.y : ux.x), pbr[j][h]), rs2, nmr);   // (x + pre_bias - mean) * rstd
           float2 d = bf2_to_f2(h ? ud.y : ud.x);
           if (!live) d = make_float2(0.f, 0.f);
           if (GELU) {
@@ -917,6 +929,77 @@ __global__ void __launch_bounds__(256) dwconv7_wgrad_kernel(const bf16* __restri
   }
 }
 
+// ------------------------------------------------------------------------------------------------ K9b
+// Per-optimiser-step weight preparation of one block's MLP (ops._prepared) in ONE launch instead of seven torch ops:
+//   w1b = bf16(W1) [4C][C],  w1t = w1b^T [C][4C],  w2g = bf16(gamma[:,None] * W2) [C][4C],  w2gt = w2g^T [4C][C],
+//   b2g = gamma * b2.  32 x 32 tiles through a padded shared-memory tile (coalesced reads and transposed writes).
+__global__ void __launch_bounds__(256) prepare_mlp_weights_kernel(const float* __restrict__ w1, const float* __restrict__ w2,
+                                                                  const float* __restrict__ b2, const float* __restrict__ gamma,
+                                                                  bf16* __restrict__ w1b, bf16* __restrict__ w1t,
+                                                                  bf16* __restrict__ w2g, bf16* __restrict__ w2gt,
+                                                                  float* __restrict__ b2g, int C) {
+  __shared__ float tile[32][33];
+  const int H = 4 * C;
+  const int tiles_r1 = H / 32, tiles_c1 = C / 32;          // W1 is [H][C], W2 is [C][H]
+  const int n1 = tiles_r1 * tiles_c1;
+  int t = blockIdx.x;
+  const bool second = t >= n1;
+  if (second) t -= n1;
+  const int rows = second ? C : H, cols = second ? H : C;
+  const int tr = t / (cols / 32), tc = t % (cols / 32);
+  const float* src = second ? w2 : w1;
+  bf16* dst = second ? w2g : w1b;
+  bf16* dst_t = second ? w2gt : w1t;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = tr * 32 + ty + 8 * i, c = tc * 32 + tx;
+    float v = src[(int64_t)r * cols + c];
+    if (second) v *= gamma[r];
+    const bf16 h = __float2bfloat16_rn(v);
+    dst[(int64_t)r * cols + c] = h;
+    tile[ty + 8 * i][tx] = __bfloat162float(h);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = tc * 32 + ty + 8 * i, c = tr * 32 + tx;  // transposed matrix is [cols][rows]
+    dst_t[(int64_t)r * rows + c] = __float2bfloat16_rn(tile[tx][ty + 8 * i]);
+  }
+  if (blockIdx.x == 0)
+    for (int c = threadIdx.x; c < C; c += 256) b2g[c] = gamma[c] * b2[c];
+}
+
+// Tail of one block's parameter gradients (ops._ConvNeXtBlock.backward) in ONE launch instead of eight torch ops.  The
+// weight-gradient GEMM yields dW2g, the gradient w.r.t. the layer-scale-folded matrix gamma[:,None] * W2; `col` is the column
+// sum of the block's upstream gradient:
+//   dW2 = gamma[:,None] * dW2g,   db2 = col * gamma,   dgamma = rowsum(dW2g * W2) + col * b2.      One warp per row.
+__global__ void __launch_bounds__(256) finish_mlp_grads_kernel(const float* __restrict__ dw2g, const float* __restrict__ w2,
+                                                               const float* __restrict__ col, const float* __restrict__ b2,
+                                                               const float* __restrict__ gamma, float* __restrict__ dw2,
+                                                               float* __restrict__ db2, float* __restrict__ dgamma, int C) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= C) return;
+  const int H = 4 * C;
+  const float gm = gamma[row];
+  const float4* a = reinterpret_cast<const float4*>(dw2g + (int64_t)row * H);
+  const float4* w = reinterpret_cast<const float4*>(w2 + (int64_t)row * H);
+  float4* o = reinterpret_cast<float4*>(dw2 + (int64_t)row * H);
+  float acc = 0.f;
+  for (int k = lane; k < H / 4; k += 32) {
+    const float4 g4 = a[k], w4 = w[k];
+    acc += (g4.x * w4.x + g4.y * w4.y) + (g4.z * w4.z + g4.w * w4.w);
+    o[k] = make_float4(gm * g4.x, gm * g4.y, gm * g4.z, gm * g4.w);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if (lane == 0) {
+    const float cl = col[row];
+    dgamma[row] = acc + cl * b2[row];
+    db2[row] = cl * gm;
+  }
+}
+
 inline int flat_grid(int64_t total8) {
   int64_t g = (total8 + 255) / 256;
   const int64_t cap = 148 * 16;
@@ -962,7 +1045,8 @@ inline int ln_grid(int64_t M, int G) {
 inline bool ring_shape_ok(int G, int VPL, int C) { return (VPL == 1 || VPL == 2 || VPL == 3 || VPL == 4 || VPL == 6) && C == 4 * G * VPL; }
 inline bool use_ring(int64_t M, int C) {
   static const bool on = [] { const char* e = getenv("B200AT_LN_RING"); return e == nullptr || e[0] != '0'; }();
-  return on && C % 8 == 0 && M * C >= (int64_t)1 << 19;   // >= 1 MB of rows: enough tiles for every SM
+  return on && C % 8 == 0 && M * C >= (int64_t)1 << 24;   // >= 32 MB of rows (stages 0-1, stems): below that the
+                                                           // launch is latency-bound and the plain kernels are as fast
 }
 // rows per tile: whole passes of the CTA (kRingThreads / G rows each), ~12 KB, a multiple of 4 rows
 inline int ring_tile_rows(int G, int C) {
@@ -983,7 +1067,7 @@ inline int ring_grid(int64_t M, int tile_rows, size_t smem) {
 
 template <bool GELU>
 int launch_ln_fwd(const bf16* x, const float* w, const float* b, bf16* y, float* mean, float* rstd, int64_t M, int C,
-                  float eps, cudaStream_t s, int pH = 0, int pW = 0) {
+                  float eps, cudaStream_t s, int pH = 0, int pW = 0, const float* pre_bias = nullptr) {
   int G, VPL;
   ln_shape(C / 4, G, VPL);
   if (pW == 0 && use_ring(M, C) && ring_shape_ok(G, VPL, C)) {
@@ -996,7 +1080,7 @@ int launch_ln_fwd(const bf16* x, const float* w, const float* b, bf16* y, float*
         static b200at::SmemConfig conf;                                                                            \
         cudaError_t e = b200at::ensure_dynamic_smem(ln_fwd_ring_kernel<GG, V, GELU>, (int)smem, conf);                   \
         if (e != cudaSuccess) return (int)e;                                                                             \
-        ln_fwd_ring_kernel<GG, V, GELU><<<grid, kRingThreads, smem, s>>>(x, w, b, y, mean, rstd, M, eps, tr);             \
+        ln_fwd_ring_kernel<GG, V, GELU><<<grid, kRingThreads, smem, s>>>(x, w, b, y, mean, rstd, M, eps, tr, pre_bias);        \
         return (int)cudaGetLastError();                                                                                  \
       }
       B200AT_RING_FOR_ALL(B200AT_CASE)
@@ -1005,7 +1089,7 @@ int launch_ln_fwd(const bf16* x, const float* w, const float* b, bf16* y, float*
   }
   const int g = ln_grid(M, G);
 #define B200AT_CASE(GG, V) \
-  if (G == GG && VPL == V) { ln_fwd_kernel<GG, V, GELU><<<g, kLnThreads, 0, s>>>(x, w, b, y, mean, rstd, M, C, eps, pH, pW); return (int)cudaGetLastError(); }
+  if (G == GG && VPL == V) { ln_fwd_kernel<GG, V, GELU><<<g, kLnThreads, 0, s>>>(x, w, b, y, mean, rstd, M, C, eps, pH, pW, pre_bias); return (int)cudaGetLastError(); }
   B200AT_LN_FOR_ALL(B200AT_CASE)
 #undef B200AT_CASE
   return (int)cudaErrorInvalidValue;
@@ -1013,7 +1097,8 @@ int launch_ln_fwd(const bf16* x, const float* w, const float* b, bf16* y, float*
 
 template <bool GELU, bool PGRAD>
 int launch_ln_bwd(const bf16* dy, const bf16* x, const float* w, const float* b, const float* mean, const float* rstd,
-                  bf16* dx, float* dw, float* db, int64_t M, int C, cudaStream_t s, int pH = 0, int pW = 0) {
+                  bf16* dx, float* dw, float* db, int64_t M, int C, cudaStream_t s, int pH = 0, int pW = 0,
+                  const float* pre_bias = nullptr) {
   int G, VPL;
   ln_shape(C / 4, G, VPL);
   if (pW == 0 && use_ring(M, C) && ring_shape_ok(G, VPL, C) && (reinterpret_cast<uintptr_t>(mean) & 15) == 0 &&
@@ -1029,7 +1114,7 @@ int launch_ln_bwd(const bf16* dy, const bf16* x, const float* w, const float* b,
         static b200at::SmemConfig conf;                                                                            \
         cudaError_t e = b200at::ensure_dynamic_smem(ln_bwd_ring_kernel<GG, V, GELU, PGRAD>, (int)smem, conf);            \
         if (e != cudaSuccess) return (int)e;                                                                             \
-        ln_bwd_ring_kernel<GG, V, GELU, PGRAD><<<grid, kRingThreads, smem, s>>>(dy, x, w, b, mean, rstd, dx, dw, db, M, tr); \
+        ln_bwd_ring_kernel<GG, V, GELU, PGRAD><<<grid, kRingThreads, smem, s>>>(dy, x, w, b, mean, rstd, dx, dw, db, M, tr, pre_bias); \
         return (int)cudaGetLastError();                                                                                  \
       }
       B200AT_RING_FOR_ALL(B200AT_CASE)
@@ -1039,7 +1124,7 @@ int launch_ln_bwd(const bf16* dy, const bf16* x, const float* w, const float* b,
   const int g = ln_grid(M, G);
   const size_t sm = PGRAD ? sizeof(float) * 2 * C : 0;
 #define B200AT_CASE(GG, V) \
-  if (G == GG && VPL == V) { ln_bwd_kernel<GG, V, GELU, PGRAD><<<g, kLnThreads, sm, s>>>(dy, x, w, b, mean, rstd, dx, dw, db, M, C, pH, pW); return (int)cudaGetLastError(); }
+  if (G == GG && VPL == V) { ln_bwd_kernel<GG, V, GELU, PGRAD><<<g, kLnThreads, sm, s>>>(dy, x, w, b, mean, rstd, dx, dw, db, M, C, pH, pW, pre_bias); return (int)cudaGetLastError(); }
   B200AT_LN_FOR_ALL(B200AT_CASE)
 #undef B200AT_CASE
   return (int)cudaErrorInvalidValue;
@@ -1103,6 +1188,29 @@ int b200at_ln_bwd(const void* dy, const void* x, const float* w, const float* b,
   const bool pg = dw != nullptr;
   if (pg != (db != nullptr)) return (int)cudaErrorInvalidValue;
 #define B200AT_GO(G, P) launch_ln_bwd<G, P>((const bf16*)dy, (const bf16*)x, w, b, mean, rstd, (bf16*)dx, dw, db, M, (int)C, s)
+  if (fuse_gelu) return pg ? B200AT_GO(true, true) : B200AT_GO(true, false);
+  return pg ? B200AT_GO(false, true) : B200AT_GO(false, false);
+#undef B200AT_GO
+}
+
+int b200at_ln_fwd_bias(const void* x, const float* pre_bias, const float* w, const float* b, void* y, float* mean,
+                       float* rstd, int64_t M, int64_t C, float eps, int fuse_gelu, void* stream) {
+  if (M <= 0) return 0;
+  if (C % 4 || C > 1536) return (int)cudaErrorInvalidValue;
+  cudaStream_t s = (cudaStream_t)stream;
+  return fuse_gelu ? launch_ln_fwd<true>((const bf16*)x, w, b, (bf16*)y, mean, rstd, M, (int)C, eps, s, 0, 0, pre_bias)
+                   : launch_ln_fwd<false>((const bf16*)x, w, b, (bf16*)y, mean, rstd, M, (int)C, eps, s, 0, 0, pre_bias);
+}
+
+int b200at_ln_bwd_bias(const void* dy, const void* x, const float* pre_bias, const float* w, const float* b,
+                       const float* mean, const float* rstd, void* dx, float* dw, float* db, int64_t M, int64_t C,
+                       int fuse_gelu, void* stream) {
+  if (M <= 0) return 0;
+  if (C % 4 || C > 1536) return (int)cudaErrorInvalidValue;
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool pg = dw != nullptr;
+  if (pg != (db != nullptr)) return (int)cudaErrorInvalidValue;
+#define B200AT_GO(G, P) launch_ln_bwd<G, P>((const bf16*)dy, (const bf16*)x, w, b, mean, rstd, (bf16*)dx, dw, db, M, (int)C, s, 0, 0, pre_bias)
   if (fuse_gelu) return pg ? B200AT_GO(true, true) : B200AT_GO(true, false);
   return pg ? B200AT_GO(false, true) : B200AT_GO(false, false);
 #undef B200AT_GO
@@ -1182,6 +1290,22 @@ int b200at_add_bf16(const void* a, const void* b, void* c, int64_t total, void* 
   if (total <= 0) return 0;
   if (total % 8) return (int)cudaErrorInvalidValue;
   add_kernel<<<flat_grid(total / 8), 256, 0, (cudaStream_t)stream>>>((const bf16*)a, (const bf16*)b, (bf16*)c, total / 8);
+  return (int)cudaGetLastError();
+}
+
+int b200at_prepare_mlp_weights(const float* w1, const float* w2, const float* b2, const float* gamma, void* w1b, void* w1t,
+                               void* w2g, void* w2gt, float* b2g, int64_t C, void* stream) {
+  if (C <= 0 || C % 32) return (int)cudaErrorInvalidValue;
+  const int tiles = 2 * (int)((4 * C / 32) * (C / 32));
+  prepare_mlp_weights_kernel<<<tiles, 256, 0, (cudaStream_t)stream>>>(w1, w2, b2, gamma, (bf16*)w1b, (bf16*)w1t, (bf16*)w2g,
+                                                                      (bf16*)w2gt, b2g, (int)C);
+  return (int)cudaGetLastError();
+}
+
+int b200at_finish_mlp_grads(const float* dw2g, const float* w2, const float* col, const float* b2, const float* gamma,
+                            float* dw2, float* db2, float* dgamma, int64_t C, void* stream) {
+  if (C <= 0 || C % 4) return (int)cudaErrorInvalidValue;
+  finish_mlp_grads_kernel<<<(unsigned)((C + 7) / 8), 256, 0, (cudaStream_t)stream>>>(dw2g, w2, col, b2, gamma, dw2, db2, dgamma, (int)C);
   return (int)cudaGetLastError();
 }
 

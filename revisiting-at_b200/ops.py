@@ -51,35 +51,43 @@ def _need_cuda(x):
 
 
 class _LayerNorm(Function):
+    """y = LN(x [+ pre_bias]) [-> GELU].  `pre_bias` is the bias of a library convolution in front of the LayerNorm (the
+    CvSt stems, utils_architecture.py:205-211): added inside the LayerNorm kernels instead of by a separate full pass, its
+    gradient is the column sum of dx."""
     @staticmethod
-    def forward(ctx, x, w, b, eps, gelu):
+    def forward(ctx, x, w, b, eps, gelu, pre_bias=None):
         x = x.contiguous()
         y = torch.empty_like(x)
         M = x.numel() // x.shape[-1]
         mean = torch.empty(M, device=x.device, dtype=torch.float32)
         rstd = torch.empty_like(mean)
         wf, bf = w.detach().float().contiguous(), b.detach().float().contiguous()
-        _abi.ln_fwd(x, wf, bf, y, mean, rstd, eps, gelu)
-        ctx.save_for_backward(x, wf, bf, mean, rstd)
+        pbf = None if pre_bias is None else pre_bias.detach().float().contiguous()
+        _abi.ln_fwd(x, wf, bf, y, mean, rstd, eps, gelu, pre_bias=pbf)
+        ctx.save_for_backward(x, wf, bf, mean, rstd, pbf)
         ctx.gelu = gelu
         ctx.param_grads = not _INPUT_GRAD_ONLY[0]
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, wf, bf, mean, rstd = ctx.saved_tensors
+        x, wf, bf, mean, rstd, pbf = ctx.saved_tensors
         dy = dy.contiguous()
         dx = torch.empty_like(x)
         pg = _wants(ctx, 1, 2)
         dw = torch.zeros_like(wf) if pg else None
         db = torch.zeros_like(bf) if pg else None
-        _abi.ln_bwd(dy, x, wf, bf, mean, rstd, dx, dw, db, ctx.gelu)
-        return dx, dw, db, None, None
+        _abi.ln_bwd(dy, x, wf, bf, mean, rstd, dx, dw, db, ctx.gelu, pre_bias=pbf)
+        dpb = None
+        if pbf is not None and ctx.param_grads and ctx.needs_input_grad[5]:
+            dpb = torch.zeros_like(pbf)
+            _abi.colsum_bf16(dx.view(-1, dx.shape[-1]), dpb)
+        return dx, dw, db, None, None, dpb
 
 
-def layer_norm(x, w, b, eps=1e-6, gelu=False):
+def layer_norm(x, w, b, eps=1e-6, gelu=False, pre_bias=None):
     """x: [..., C] bf16 NHWC."""
-    return _LayerNorm.apply(x, w, b, eps, gelu)
+    return _LayerNorm.apply(x, w, b, eps, gelu, pre_bias)
 
 
 class _DwConv7(Function):
@@ -264,6 +272,8 @@ def _bf16(p):
 def _prepared(w1, w2, b2, gamma):
     """bf16 / transposed / layer-scale-folded copies of the block's MLP weights."""
     def build(w1, w2, b2, gamma):
+        if w1.is_cuda and gamma.numel() % 32 == 0:
+            return _abi.prepare_mlp_weights(w1, w2, b2, gamma)      # one launch instead of seven
         gf = gamma.float()
         w1b = w1.to(BF16).contiguous()                                  # [4C, C]   pwconv1: t2 @ w1b^T
         w1t = w1b.t().contiguous()                                      # [C, 4C]   dt2 = dz @ w1b  == dz @ w1t^T
@@ -407,9 +417,7 @@ class _ConvNeXtBlock(Function):
         dw1 = _wgrad(dz, t2.view(M, C))
         dw2g = _wgrad(d2, a)                                            # gradient w.r.t. gamma-folded W2
         _abi.colsum_bf16(d2, col)
-        dw2 = gf[:, None] * dw2g
-        db2 = col * gf
-        dgamma = (dw2g * w2.float()).sum(1) + col * b2f
+        dw2, db2, dgamma = _abi.finish_mlp_grads(dw2g, w2.float().contiguous(), col, b2f, gf)
         return dx, ddw.t().reshape(C, 1, 7, 7), ddb, dlnw, dlnb, dw1, db1, dw2, db2, dgamma
 
 
@@ -478,9 +486,13 @@ def stem_layer(x, cw, cb, lw, lb, stride, first, mean=None, std=None):
         x = x.to(BF16).contiguous(memory_format=torch.channels_last)
     else:
         x = x.permute(0, 3, 1, 2)                        # NHWC storage viewed as NCHW channels_last
-    y = F.conv2d(x, _cast(cw), _cast(cb), stride=stride, padding=1)
+    # the library convolution runs WITHOUT its bias: torch adds a conv bias as a separate full pass over the output (the
+    # largest activations of the network: 0.5 ms per step) and reduces its gradient in another; both ride in the
+    # LayerNorm kernels instead (`pre_bias`), which need C % 8 == 0
+    fold = cw.shape[0] % 8 == 0
+    y = F.conv2d(x, _cast(cw), None if fold else _cast(cb), stride=stride, padding=1)
     y = y.permute(0, 2, 3, 1)                            # -> NHWC view of the channels_last result
-    return layer_norm(y, lw, lb, 1e-6, gelu=True)
+    return layer_norm(y, lw, lb, 1e-6, gelu=True, pre_bias=cb if fold else None)
 
 
 class _Downsample(Function):

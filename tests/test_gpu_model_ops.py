@@ -48,6 +48,30 @@ def test_layernorm_fwd_bwd(ops, cuda_dev, C, gelu):
     assert torch.equal(dx2, dx)
 
 
+@pytest.mark.parametrize('M,C', [(1031, 48), (200000, 96), (4100, 144)])
+def test_layernorm_with_the_convolution_bias_folded_in(ops, cuda_dev, M, C):
+    """y = GELU(LN(x + pre_bias)): the CvSt stem's conv bias rides in the LayerNorm kernels (plain and pipelined forms);
+    its gradient is the column sum of dx (utils_architecture.py:205-211)."""
+    g = torch.Generator(device='cuda').manual_seed(C + 1)
+    x = (torch.randn(M, C, generator=g, device=cuda_dev) * 2 + 0.5).to(BF16)
+    pb = torch.randn(C, generator=g, device=cuda_dev).requires_grad_()
+    w = torch.randn(C, generator=g, device=cuda_dev).requires_grad_()
+    b = torch.randn(C, generator=g, device=cuda_dev).requires_grad_()
+    dy = torch.randn(M, C, generator=g, device=cuda_dev).to(BF16)
+    xr = x.float().requires_grad_()
+    ref = F.gelu(F.layer_norm(xr + pb, (C,), w, b, 1e-6))
+    rdx, rdw, rdb, rdp = torch.autograd.grad(ref, [xr, w, b, pb], dy.float())
+    xt = x.clone().requires_grad_()
+    out = ops.layer_norm(xt, w, b, 1e-6, True, pre_bias=pb)
+    _close(out, ref, atol=2e-2)
+    dx, dw, db, dp = torch.autograd.grad(out, [xt, w, b, pb], dy)
+    _close(dx, rdx, atol=3e-2)
+    scale = M ** 0.5
+    _close(dw, rdw, atol=2e-2 * scale, rtol=1e-2)
+    _close(db, rdb, atol=2e-2 * scale, rtol=1e-2)
+    _close(dp, rdp, atol=3e-2 * scale, rtol=2e-2)       # column sum of the bf16-rounded dx
+
+
 @pytest.mark.parametrize('shape', [(2, 56, 56, 96), (3, 28, 28, 192), (2, 14, 14, 384), (5, 7, 7, 768), (1, 20, 23, 32),
                                    (2, 80, 80, 32), (3, 40, 40, 64), (9, 10, 10, 64), (2, 33, 47, 16), (1, 5, 3, 32),
                                    (2, 17, 96, 32)])
