@@ -59,6 +59,7 @@ def parse():
     ap.add_argument('--ema', type=int, default=None, help='on-device EMA of the parameters (default: on for convnext_base = config 4)')
     ap.add_argument('--label-smoothing', type=float, default=None, help='default 0.1 for convnext_base (config 4), else 0')
     ap.add_argument('--no-graph', action='store_true', help='launch the attack kernel by kernel instead of replaying its CUDA graph')
+    ap.add_argument('--graph-step', type=int, default=int(os.environ.get('B200AT_GRAPH_STEP', '0')), help='1: replay the WHOLE step (attack + training forward/backward + all-reduce + AdamW) from one CUDA graph')
     ap.add_argument('--cpu-seconds', type=float, default=20.0, help='budget of the cpu_baseline sample')
     ap.add_argument('--res', type=int, default=RES, help='image side (224 = the metric line; 320 = the secondary resolution of north_star)')
     return ap.parse_args()
@@ -259,7 +260,8 @@ def run_b200(args):
     batch = args.batch
     model = build_engine(args.arch)
     step = AdvTrainStep(model, 'apgd', 'Linf', EPS, N_ITER, distributed=distributed, device=dev,
-                        graph_attack=not args.no_graph, ema=bool(args.ema), label_smoothing=args.label_smoothing)
+                        graph_attack=not args.no_graph, ema=bool(args.ema), label_smoothing=args.label_smoothing,
+                        graph_step=bool(args.graph_step) and not args.no_graph)
 
     pool = 2
     host = [synth_batch(batch, 1234 + 17 * rank + i) for i in range(pool)]
@@ -304,7 +306,7 @@ def run_b200(args):
         loss = step(x, y)
         sink.copy_(loss.reshape(1), non_blocking=False)     # D2H read of the step's result
 
-    n_warm = max(args.warmup, 3) + (0 if args.no_graph else 2)   # graph mode: 2 eager calls, 1 capture, >= 2 replays
+    n_warm = max(args.warmup, 3) + (0 if args.no_graph else 2) + (1 if args.graph_step else 0)   # graph mode: 2 eager calls, 1 capture, >= 2 replays
     for i in range(n_warm):
         resident_step(i)
     sampler = ClockSampler(local)
@@ -321,6 +323,7 @@ def run_b200(args):
     # roofline of the fused l-inf update: the same K steps once more with the attack launched kernel by kernel
     # (a kernel inside a replayed CUDA graph cannot carry events), CUDA events on the launching stream around
     # every K1 launch.
+    step.graphed = None                                     # (whole-step graph off for this part as well)
     step.use_graph(False)
     resident_step(0)
     # algorithmic bytes per element of each timed K1 launch (20 B = read x, x_adv, x_adv_old, grad +
@@ -374,7 +377,7 @@ def run_b200(args):
                      'peak_source': peak_src, 'frac_of_nominal_8TBps': achieved / 8000.0,
                      'timed_region': f'{args.steps} more steps with the attack launched kernel by kernel '
                                      f'({ms_eager / args.steps:.2f} ms/step)'},
-        'attack_launch': 'eager' if args.no_graph else 'cuda_graph (one graph per apgd_train call: 3 forwards + 2 input-grad backwards + update/bookkeeping kernels)',
+        'attack_launch': 'eager' if args.no_graph else ('cuda_graph of the WHOLE step (attack + training forward/backward + all-reduce + AdamW)' if args.graph_step else 'cuda_graph (one graph per apgd_train call: 3 forwards + 2 input-grad backwards + update/bookkeeping kernels)'),
         'clocks': clocks,
         'model_engine': ENGINE_NOTE[args.arch == 'vit_small'],
     }

@@ -97,8 +97,10 @@ int b200at_l2_step(const float* x, float* x_adv, const float* x_old, float* x_ne
 /* autopgd_train_clean.py:239-250 with L1_projection (:24-91) (+ the pending image ops): sparse sign step on
  * the top-k |grad| coordinates (exact order statistic by radix select), then projection of x+delta onto the
  * l1 ball of radius eps intersected with [0,1]^n.  No momentum, x_old is not read; x_new must NOT alias
- * x_adv.  Writes nnz(x_new - x) to state[SP_ADV].  scratch: >= B200AT_L1_SCRATCH_WORDS(B) 4-byte words. */
-#define B200AT_L1_SCRATCH_WORDS(B) ((3 * 2048 + 16 + 32 * 2 + 32 * 32) * (B))
+ * x_adv.  Writes nnz(x_new - x) to state[SP_ADV].  scratch: >= B200AT_L1_SCRATCH_WORDS(B) 4-byte words.
+ * 12 kernel launches + 1 memset: the per-sample decisions between the image passes are made in the prologue of the
+ * next pass, not by helper launches. */
+#define B200AT_L1_SCRATCH_WORDS(B) ((3 * 2048 + 32 + 32 * 2 + 2 * 32 * 32) * (B))
 int b200at_l1_step(const float* x, float* x_adv, float* x_new, const float* grad, float* x_best, float* grad_best,
                    float* x_best_adv, float* state, void* scratch, int64_t B, int64_t n, float eps, void* stream);
 

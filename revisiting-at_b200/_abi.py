@@ -249,7 +249,7 @@ def l2_step(x, x_adv, x_old, x_new, grad, x_best, grad_best, x_best_adv, state, 
     return scratch
 
 
-L1_LAUNCHES = 3 * 2 + 2 + 2 * 7 + 1
+L1_LAUNCHES = 3 + 1 + 7 + 1    # histogram x3, sums, sectioning x7, final (+ one memset)
 
 
 def l1_step(x, x_adv, x_new, grad, x_best, grad_best, x_best_adv, state, eps, scratch=None):
@@ -257,7 +257,7 @@ def l1_step(x, x_adv, x_new, grad, x_best, grad_best, x_best_adv, state, eps, sc
     if x_new.data_ptr() == x_adv.data_ptr():
         raise B200atError('l1_step: x_new must not alias x_adv')
     if scratch is None:
-        scratch = torch.empty((3 * 2048 + 16 + 64 + 1024) * max(B, 1), device=x.device, dtype=torch.int32)
+        scratch = torch.empty((3 * 2048 + 32 + 64 + 2048) * max(B, 1), device=x.device, dtype=torch.int32)
     args = (_img(x, name='x'), _img(x_adv, x, 'x_adv'), _img(x_new, x, 'x_new'), _img(grad, x, 'grad'),
             _img(x_best, x, 'x_best'), _img(grad_best, x, 'grad_best'), _img(x_best_adv, x, 'x_best_adv'),
             _p(state), _p(scratch), B, n, eps, _stream())

@@ -136,26 +136,39 @@ __global__ void __launch_bounds__(kThreads) l2_phase_kernel(B200atImages p, floa
 // HBM traffic 20 B/element instead of 52.
 constexpr int kL2Cluster = 8;
 constexpr int kL2Threads = 512;           // 2 CTAs x 16 warps per SM: the loads in flight that the HBM phase needs
-constexpr int kL2SmemCap = 100 * 1024;    // dynamic shared memory per CTA: unused, bounds residency to 2 CTAs / SM
+constexpr int kL2SmemCap = 100 * 1024;    // dynamic shared memory per CTA: the gradient slice; also bounds residency to 2 CTAs / SM
 
+// `gbuf`: this CTA's slice of the gradient in shared memory (filled in phase 0, read by phases 1..3: 12 of the 52 B/element
+// the four phases read come from there instead of from L2), or null when the slice does not fit (n / 8 floats > the buffer).
 template <int PHASE, int VEC>
 __device__ __forceinline__ float l2_cluster_phase(const B200atImages& p, int b, int rank, float eps, float a,
-                                                  float one_minus_a, const float* sums, float* red) {
+                                                  float one_minus_a, const float* sums, float* red, float* gbuf) {
   const int nvec_row = (int)(p.n / VEC);                 // n < 2^31 (checked by the entry point)
   const int per = (nvec_row + kL2Cluster - 1) / kL2Cluster;
   const int v0 = rank * per, v1 = (v0 + per < nvec_row) ? v0 + per : nvec_row;
   const B200atL2Ctx ctx = b200at_l2_ctx<PHASE>(p, b, sums);
   const int64_t base = (int64_t)b * p.n;
   float acc0 = 0.0f, acc1 = 0.0f, acc2 = 0.0f, acc3 = 0.0f;
+  B200atVec<VEC>* gv = reinterpret_cast<B200atVec<VEC>*>(gbuf);
+  auto one = [&](int v) -> float {
+    const int64_t e = base + (int64_t)v * VEC;
+    if (gbuf == nullptr) return b200at_l2_body_ctx<PHASE, VEC, (PHASE < 3)>(p, e, ctx, eps, a, one_minus_a);
+    if (PHASE == 0) {                                    // the gradient is read from HBM exactly once: stream it, park it
+      const B200atVec<VEC> g = b200at_ld_stream<VEC>((ctx.restore ? p.grad_best : p.grad) + e);
+      gv[v - v0] = g;
+      return b200at_l2_body_ctx<0, VEC, false>(p, e, ctx, eps, a, one_minus_a, &g);
+    }
+    const B200atVec<VEC> g = gv[v - v0];
+    return b200at_l2_body_ctx<PHASE, VEC, (PHASE < 3)>(p, e, ctx, eps, a, one_minus_a, &g);
+  };
   int v = v0 + threadIdx.x;
   for (; v + 3 * kL2Threads < v1; v += 4 * kL2Threads) {      // four independent vectors in flight per thread
-    acc0 += b200at_l2_body_ctx<PHASE, VEC, (PHASE < 3)>(p, base + (int64_t)v * VEC, ctx, eps, a, one_minus_a);
-    acc1 += b200at_l2_body_ctx<PHASE, VEC, (PHASE < 3)>(p, base + (int64_t)(v + kL2Threads) * VEC, ctx, eps, a, one_minus_a);
-    acc2 += b200at_l2_body_ctx<PHASE, VEC, (PHASE < 3)>(p, base + (int64_t)(v + 2 * kL2Threads) * VEC, ctx, eps, a, one_minus_a);
-    acc3 += b200at_l2_body_ctx<PHASE, VEC, (PHASE < 3)>(p, base + (int64_t)(v + 3 * kL2Threads) * VEC, ctx, eps, a, one_minus_a);
+    acc0 += one(v);
+    acc1 += one(v + kL2Threads);
+    acc2 += one(v + 2 * kL2Threads);
+    acc3 += one(v + 3 * kL2Threads);
   }
-  for (; v < v1; v += kL2Threads)
-    acc0 += b200at_l2_body_ctx<PHASE, VEC, (PHASE < 3)>(p, base + (int64_t)v * VEC, ctx, eps, a, one_minus_a);
+  for (; v < v1; v += kL2Threads) acc0 += one(v);
   if (PHASE == 3) return 0.0f;
   return cta_sum<kL2Threads>((acc0 + acc1) + (acc2 + acc3), red);    // valid in warp 0
 }
@@ -172,24 +185,27 @@ template <int VEC>
 __global__ void __launch_bounds__(kL2Threads) l2_cluster_kernel(B200atImages p, float eps, float a, float one_minus_a) {
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
+  extern __shared__ __align__(16) float l2_gbuf[];         // kL2SmemCap bytes
   __shared__ float red[kL2Threads / 32];
   __shared__ float part[3];
   const int rank = (int)cluster.block_rank();
   const int b = blockIdx.y;
+  const int64_t slice = ((p.n / VEC + kL2Cluster - 1) / kL2Cluster) * VEC;
+  float* gbuf = (slice * 4 <= kL2SmemCap) ? l2_gbuf : nullptr;
   float sums[3] = {0.f, 0.f, 0.f};
-  float t = l2_cluster_phase<0, VEC>(p, b, rank, eps, a, one_minus_a, sums, red);
+  float t = l2_cluster_phase<0, VEC>(p, b, rank, eps, a, one_minus_a, sums, red, gbuf);
   if (threadIdx.x == 0) part[0] = t;
   cluster.sync();
   sums[0] = l2_cluster_total(cluster, part, 0);
-  t = l2_cluster_phase<1, VEC>(p, b, rank, eps, a, one_minus_a, sums, red);
+  t = l2_cluster_phase<1, VEC>(p, b, rank, eps, a, one_minus_a, sums, red, gbuf);
   if (threadIdx.x == 0) part[1] = t;
   cluster.sync();
   sums[1] = l2_cluster_total(cluster, part, 1);
-  t = l2_cluster_phase<2, VEC>(p, b, rank, eps, a, one_minus_a, sums, red);
+  t = l2_cluster_phase<2, VEC>(p, b, rank, eps, a, one_minus_a, sums, red, gbuf);
   if (threadIdx.x == 0) part[2] = t;
   cluster.sync();
   sums[2] = l2_cluster_total(cluster, part, 2);
-  l2_cluster_phase<3, VEC>(p, b, rank, eps, a, one_minus_a, sums, red);
+  l2_cluster_phase<3, VEC>(p, b, rank, eps, a, one_minus_a, sums, red, gbuf);
   cluster.sync();   // nobody leaves while a peer may still be reading its partials
 }
 
@@ -231,15 +247,19 @@ int launch_l2(const B200atImages& p, float* scratch, float eps, float a, float o
 // then the final write.  grid = (kChunks, B) for the image passes; tiny per-sample kernels in between.
 // Scratch words per sample: see B200AT_L1_SCRATCH_WORDS in include/b200at.h.
 constexpr int kHistBins = 2048;
-constexpr int kMetaWords = 16;
-enum { M_PREFIX = 0, M_RANK = 1, M_COUNT_LT = 2, M_NAN = 3, M_ZERO = 4, M_THR = 5, M_NNZ = 6, M_C = 7, M_NEED = 8,
-       M_ALPHA = 9 };
+constexpr int kMetaWords = 32;
+// per-sample meta words.  The scan of radix level L and the decision of sectioning pass P are made in the PROLOGUE of the
+// next image pass by every CTA of the sample (redundantly: 8 KB of histogram / 4 KB of partial sums from L2) instead of by
+// 1-warp helper launches in between; CTA 0 of the sample publishes the result for the launches after that.  Every result
+// has its own slot, so a CTA publishing slot L never races with a slower CTA of the same launch still reading slot L - 1.
+enum { M_PREFIX = 0 /*..2*/, M_RANK = 3 /*..5*/, M_COUNT_LT = 6 /*..8*/, M_NAN = 9, M_ZERO = 10, M_THR = 11, M_NNZ = 12,
+       M_C = 13, M_NEED = 14, M_ALPHA = 16 /*..22: water-level prefix after pass 0..6*/ };
 
 struct L1Scratch {
   int* hist;      // [3][B][kHistBins]
   int* meta;      // [B][kMetaWords]
   float* sums;    // [B][kChunks][2]
-  float* sect;    // [B][kChunks][32]
+  float* sect;    // [2][B][kChunks][32]   (double-buffered by pass parity: pass p+1's prologue reads what pass p wrote)
 };
 __host__ __device__ inline L1Scratch l1_scratch(void* base, int64_t B) {
   L1Scratch s;
@@ -265,15 +285,77 @@ __device__ __forceinline__ L1Sel l1_select(const B200atImages& p, int b) {
   return s;
 }
 
+struct L1Scan { uint32_t prefix; int rank, count_lt; };
+
+// Locate the bin of radix level LEVEL that holds the wanted rank (whole CTA, kThreads threads; every thread returns the
+// same result).  Level 0 starts from the rank the top-k fraction asks for, levels 1-2 from the published level below.
+template <int LEVEL>
+__device__ __forceinline__ L1Scan l1_scan_dev(const float* __restrict__ st, const L1Scratch& S, int64_t B, int64_t n, int b,
+                                              int* sm /* >= kThreads/32 + 2 ints */) {
+  const int* meta = S.meta + b * kMetaWords;
+  const int* gh = S.hist + ((int64_t)LEVEL * B + b) * kHistBins;
+  int rank, prev_clt = 0;
+  uint32_t prev = 0u;
+  if (LEVEL == 0) rank = (int)b200at_l1_rank(st[(int64_t)B200AT_ST_TOPK * B + b], n);
+  else { rank = meta[M_RANK + LEVEL - 1]; prev = (uint32_t)meta[M_PREFIX + LEVEL - 1]; prev_clt = meta[M_COUNT_LT + LEVEL - 1]; }
+  constexpr int per = kHistBins / kThreads;  // 8 consecutive bins per thread
+  int loc[per], tot = 0;
+#pragma unroll
+  for (int i = 0; i < per; ++i) { loc[i] = gh[threadIdx.x * per + i]; tot += loc[i]; }
+  int incl = tot;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if ((threadIdx.x & 31) >= o) incl += t;
+  }
+  int* warp_tot = sm;
+  int* found = sm + kThreads / 32;           // [0] bin, [1] exclusive count
+  if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = incl;
+  if (threadIdx.x == 0) { found[0] = -1; found[1] = 0; }
+  __syncthreads();
+  int base = 0;
+  for (int w = 0; w < (threadIdx.x >> 5); ++w) base += warp_tot[w];
+  int excl = base + incl - tot;
+  if (rank >= excl && rank < excl + tot) {
+#pragma unroll
+    for (int i = 0; i < per; ++i) {
+      if (rank < excl + loc[i]) { found[0] = threadIdx.x * per + i; found[1] = excl; break; }
+      excl += loc[i];
+    }
+  }
+  __syncthreads();
+  const int bin = found[0] < 0 ? 0 : found[0];
+  const int ex = found[0] < 0 ? 0 : found[1];
+  __syncthreads();                           // `sm` is reused by the caller
+  L1Scan r;
+  r.prefix = LEVEL == 0 ? (uint32_t)bin : (LEVEL == 1 ? ((prev << 11) | bin) : ((prev << 9) | bin));
+  r.rank = rank - ex;
+  r.count_lt = prev_clt + ex;
+  return r;
+}
+__device__ __forceinline__ void l1_publish_scan(int* meta, int level, const L1Scan& r) {
+  meta[M_PREFIX + level] = (int)r.prefix;
+  meta[M_RANK + level] = r.rank;
+  meta[M_COUNT_LT + level] = r.count_lt;
+}
+
 template <int LEVEL, int VEC>
-__global__ void __launch_bounds__(kThreads) l1_hist_kernel(B200atImages p, void* scratch) {
+__global__ void __launch_bounds__(kThreads) l1_hist_kernel(B200atImages p, void* scratch, float* st_rw) {
   __shared__ int h[kHistBins];
+  __shared__ int scan_sm[kThreads / 32 + 2];
   const int b = blockIdx.y, c = blockIdx.x;
   const L1Scratch S = l1_scratch(scratch, p.B);
   const L1Sel sel = l1_select(p, b);
+  uint32_t prefix = 0u;
+  if (LEVEL == 0) {
+    if (c == 0 && threadIdx.x == 0) *reinterpret_cast<int*>(st_rw + (int64_t)B200AT_ST_SP_ADV * p.B + b) = 0;
+  } else {
+    const L1Scan r = l1_scan_dev<LEVEL - 1>(p.st, S, p.B, p.n, b, scan_sm);
+    prefix = r.prefix;
+    if (c == 0 && threadIdx.x == 0) l1_publish_scan(S.meta + b * kMetaWords, LEVEL - 1, r);
+  }
   for (int i = threadIdx.x; i < kHistBins; i += kThreads) h[i] = 0;
   __syncthreads();
-  const uint32_t prefix = (uint32_t)S.meta[b * kMetaWords + M_PREFIX];
   const int64_t nvec_row = p.n / VEC;
   const int64_t per = (nvec_row + kChunks - 1) / kChunks;
   const int64_t v0 = c * per, v1 = (v0 + per < nvec_row) ? v0 + per : nvec_row;
@@ -311,70 +393,37 @@ __global__ void __launch_bounds__(kThreads) l1_hist_kernel(B200atImages p, void*
   }
 }
 
-// one CTA per sample: locate the bin holding the wanted rank; after the last level derive thr and nnz
-template <int LEVEL>
-__global__ void __launch_bounds__(kThreads) l1_scan_kernel(const float* __restrict__ st, void* scratch, int64_t B,
-                                                            int64_t n) {
-  __shared__ int warp_tot[kThreads / 32];
-  __shared__ int found_bin, found_excl;
-  const int b = blockIdx.x;
-  const L1Scratch S = l1_scratch(scratch, B);
-  int* meta = S.meta + b * kMetaWords;
-  const int* gh = S.hist + ((int64_t)LEVEL * B + b) * kHistBins;
-  int rank;
-  if (LEVEL == 0) rank = (int)b200at_l1_rank(st[(int64_t)B200AT_ST_TOPK * B + b], n);
-  else rank = meta[M_RANK];
-  constexpr int per = kHistBins / kThreads;  // 8 consecutive bins per thread
-  int loc[per], tot = 0;
-#pragma unroll
-  for (int i = 0; i < per; ++i) { loc[i] = gh[threadIdx.x * per + i]; tot += loc[i]; }
-  int incl = tot;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int t = __shfl_up_sync(0xffffffffu, incl, o);
-    if ((threadIdx.x & 31) >= o) incl += t;
-  }
-  if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = incl;
-  if (threadIdx.x == 0) found_bin = -1;
-  __syncthreads();
-  int base = 0;
-  for (int w = 0; w < (threadIdx.x >> 5); ++w) base += warp_tot[w];
-  int excl = base + incl - tot;
-  if (rank >= excl && rank < excl + tot) {
-#pragma unroll
-    for (int i = 0; i < per; ++i) {
-      if (rank < excl + loc[i]) { found_bin = threadIdx.x * per + i; found_excl = excl; break; }
-      excl += loc[i];
-    }
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const int bin = found_bin < 0 ? 0 : found_bin;
-    const int ex = found_bin < 0 ? 0 : found_excl;
-    const uint32_t prev = LEVEL == 0 ? 0u : (uint32_t)meta[M_PREFIX];
-    const uint32_t prefix = LEVEL == 0 ? (uint32_t)bin : (LEVEL == 1 ? ((prev << 11) | bin) : ((prev << 9) | bin));
-    meta[M_PREFIX] = (int)prefix;
-    meta[M_RANK] = rank - ex;
-    meta[M_COUNT_LT] = (LEVEL == 0 ? 0 : meta[M_COUNT_LT]) + ex;
-    if (LEVEL == 2) {
-      const float thr = b200at_i2f((int32_t)prefix);
-      float nnz = 0.0f;
-      if (prefix <= 0x7f800000u)
-        nnz = (float)((int)n - meta[M_COUNT_LT] - meta[M_NAN] - (prefix == 0u ? meta[M_ZERO] : 0));
-      meta[M_THR] = b200at_f2i(thr);
-      meta[M_NNZ] = b200at_f2i(nnz);
-    }
-  }
+// water-level prefix after sectioning pass `pass` (:71-88): keep the candidates still below the level.  Every warp of every
+// CTA of the sample evaluates it from the 32 chunk partials of that pass (lane k = candidate k + 1, fixed chunk order).
+__device__ __forceinline__ uint32_t l1_decide_dev(const L1Scratch& S, int64_t B, int b, int pass, float cc) {
+  const int k = threadIdx.x & 31;
+  const int* meta = S.meta + b * kMetaWords;
+  const uint32_t prev = pass == 0 ? 0u : (uint32_t)meta[M_ALPHA + pass - 1];
+  const int ncand = b200at_l1_ncand(pass);
+  const float* sect = S.sect + ((int64_t)(pass & 1) * B + b) * kChunks * 32;
+  float gk = 0.0f;
+  if (k < ncand)
+    for (int c = 0; c < kChunks; ++c) gk += sect[c * 32 + k];
+  const bool below = (k < ncand) && (gk + cc < 0.0f);
+  const unsigned m = __ballot_sync(0xffffffffu, below);
+  const int kstar = __ffs(~m) - 1;  // number of leading candidates still below the level
+  return prev | ((uint32_t)kstar << b200at_l1_shift(pass));
 }
 
-// sum|y| and sum(a) partials
+// sum|y| and sum(a) partials (prologue: the scan of the last radix level -> threshold and nnz, published by CTA 0)
 template <int VEC>
 __global__ void __launch_bounds__(kThreads) l1_sums_kernel(B200atImages p, void* scratch) {
   __shared__ float red[kThreads / 32];
+  __shared__ int scan_sm[kThreads / 32 + 2];
   const int b = blockIdx.y, c = blockIdx.x;
   const L1Scratch S = l1_scratch(scratch, p.B);
+  int* meta = S.meta + b * kMetaWords;
+  const L1Scan r = l1_scan_dev<2>(p.st, S, p.B, p.n, b, scan_sm);
+  const float thr = b200at_i2f((int32_t)r.prefix);
+  float nnz = 0.0f;
+  if (r.prefix <= 0x7f800000u) nnz = (float)((int)p.n - r.count_lt - meta[M_NAN] - (r.prefix == 0u ? meta[M_ZERO] : 0));
+  if (c == 0 && threadIdx.x == 0) { l1_publish_scan(meta, 2, r); meta[M_THR] = b200at_f2i(thr); meta[M_NNZ] = b200at_f2i(nnz); }
   const L1Sel sel = l1_select(p, b);
-  const float thr = b200at_i2f(S.meta[b * kMetaWords + M_THR]), nnz = b200at_i2f(S.meta[b * kMetaWords + M_NNZ]);
   const int64_t nvec_row = p.n / VEC;
   const int64_t per = (nvec_row + kChunks - 1) / kChunks;
   const int64_t v0 = c * per, v1 = (v0 + per < nvec_row) ? v0 + per : nvec_row;
@@ -398,35 +447,36 @@ __global__ void __launch_bounds__(kThreads) l1_sums_kernel(B200atImages p, void*
   }
 }
 
-// per sample: c = eps - sum|y|, need = (sum(a) + c < 0)  (:49-52);  one warp per sample
-__global__ void l1_need_kernel(void* scratch, int64_t B, float eps) {
-  const int b = blockIdx.x;
-  const L1Scratch S = l1_scratch(scratch, B);
-  float tb = S.sums[((int64_t)b * kChunks + threadIdx.x) * 2 + 0];
-  float ta = S.sums[((int64_t)b * kChunks + threadIdx.x) * 2 + 1];
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    tb += __shfl_xor_sync(0xffffffffu, tb, o);
-    ta += __shfl_xor_sync(0xffffffffu, ta, o);
-  }
-  if (threadIdx.x == 0) {
-    const float c = eps - tb;
-    S.meta[b * kMetaWords + M_C] = b200at_f2i(c);
-    S.meta[b * kMetaWords + M_NEED] = (ta + c < 0.0f) ? 1 : 0;
-    S.meta[b * kMetaWords + M_ALPHA] = 0;
-  }
-}
-
-// g(alpha_k) = sum_i clamp(alpha_k, a_i, b_i) for the 31 candidates of this pass
+// Sectioning pass `pass`: g(alpha_k) = sum_i clamp(alpha_k, a_i, b_i) for the 31 candidates of this pass; samples that need
+// no l1 shrink are skipped.  Prologue: pass 0 derives c = eps - sum|y| and need = (sum(a) + c < 0) (:49-52) from the partial
+// sums, later passes the water-level prefix from the previous pass's partial sums.
 template <int VEC>
-__global__ void __launch_bounds__(kThreads) l1_section_kernel(B200atImages p, void* scratch, int pass) {
+__global__ void __launch_bounds__(kThreads) l1_section_kernel(B200atImages p, void* scratch, int pass, float eps) {
   __shared__ float red[kThreads / 32];
   const int b = blockIdx.y, c = blockIdx.x;
   const L1Scratch S = l1_scratch(scratch, p.B);
-  if (!S.meta[b * kMetaWords + M_NEED]) return;
+  int* meta = S.meta + b * kMetaWords;
+  const bool pub = c == 0 && threadIdx.x == 0;
+  const float thr = b200at_i2f(meta[M_THR]), nnz = b200at_i2f(meta[M_NNZ]);
+  uint32_t prefix = 0u;
+  if (pass == 0) {
+    float tb = S.sums[((int64_t)b * kChunks + (threadIdx.x & 31)) * 2 + 0];
+    float ta = S.sums[((int64_t)b * kChunks + (threadIdx.x & 31)) * 2 + 1];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      tb += __shfl_xor_sync(0xffffffffu, tb, o);
+      ta += __shfl_xor_sync(0xffffffffu, ta, o);
+    }
+    const float cc = eps - tb;
+    const int need = (ta + cc < 0.0f) ? 1 : 0;
+    if (pub) { meta[M_C] = b200at_f2i(cc); meta[M_NEED] = need; }
+    if (!need) return;
+  } else {
+    if (!meta[M_NEED]) return;
+    prefix = l1_decide_dev(S, p.B, b, pass - 1, b200at_i2f(meta[M_C]));
+    if (pub) meta[M_ALPHA + pass - 1] = (int)prefix;
+  }
   const L1Sel sel = l1_select(p, b);
-  const float thr = b200at_i2f(S.meta[b * kMetaWords + M_THR]), nnz = b200at_i2f(S.meta[b * kMetaWords + M_NNZ]);
-  const uint32_t prefix = (uint32_t)S.meta[b * kMetaWords + M_ALPHA];
   const int ncand = b200at_l1_ncand(pass);
   float cand[31], acc[31];
 #pragma unroll
@@ -446,7 +496,7 @@ __global__ void __launch_bounds__(kThreads) l1_section_kernel(B200atImages p, vo
       for (int k = 0; k < 31; ++k) acc[k] += b200at_l1_level(cand[k], a, bb);
     }
   }
-  float* out = S.sect + ((int64_t)b * kChunks + c) * 32;
+  float* out = S.sect + (((int64_t)(pass & 1) * p.B + b) * kChunks + c) * 32;
 #pragma unroll
   for (int k = 0; k < 31; ++k) {
     if (k < ncand) {
@@ -456,30 +506,16 @@ __global__ void __launch_bounds__(kThreads) l1_section_kernel(B200atImages p, vo
   }
 }
 
-// per sample (one warp, lane k = candidate k+1): keep the candidates below the water level (:71-88)
-__global__ void l1_decide_kernel(void* scratch, int64_t B, int pass) {
-  const int b = blockIdx.x, k = threadIdx.x;
-  const L1Scratch S = l1_scratch(scratch, B);
-  if (!S.meta[b * kMetaWords + M_NEED]) return;
-  const int ncand = b200at_l1_ncand(pass);
-  float gk = 0.0f;
-  if (k < ncand)
-    for (int c = 0; c < kChunks; ++c) gk += S.sect[((int64_t)b * kChunks + c) * 32 + k];
-  const float cc = b200at_i2f(S.meta[b * kMetaWords + M_C]);
-  const bool below = (k < ncand) && (gk + cc < 0.0f);
-  const unsigned m = __ballot_sync(0xffffffffu, below);
-  const int kstar = __ffs(~m) - 1;  // number of leading candidates still below the level
-  if (k == 0) S.meta[b * kMetaWords + M_ALPHA] |= (int)((uint32_t)kstar << b200at_l1_shift(pass));
-}
-
 template <int VEC>
 __global__ void __launch_bounds__(kThreads) l1_final_kernel(B200atImages p, void* scratch, float* st_rw) {
   const int b = blockIdx.y, c = blockIdx.x;
   const L1Scratch S = l1_scratch(scratch, p.B);
   const L1Sel sel = l1_select(p, b);
-  const float thr = b200at_i2f(S.meta[b * kMetaWords + M_THR]), nnz = b200at_i2f(S.meta[b * kMetaWords + M_NNZ]);
-  const int need = S.meta[b * kMetaWords + M_NEED];
-  const float alpha = b200at_i2f(S.meta[b * kMetaWords + M_ALPHA]);
+  const int* meta = S.meta + b * kMetaWords;
+  const float thr = b200at_i2f(meta[M_THR]), nnz = b200at_i2f(meta[M_NNZ]);
+  const int need = meta[M_NEED];
+  float alpha = 0.0f;
+  if (need) alpha = b200at_i2f((int32_t)l1_decide_dev(S, p.B, b, B200AT_L1_PASSES - 1, b200at_i2f(meta[M_C])));
   const int64_t nvec_row = p.n / VEC;
   const int64_t per = (nvec_row + kChunks - 1) / kChunks;
   const int64_t v0 = c * per, v1 = (v0 + per < nvec_row) ? v0 + per : nvec_row;
@@ -512,26 +548,20 @@ __global__ void __launch_bounds__(kThreads) l1_final_kernel(B200atImages p, void
     atomicAdd(reinterpret_cast<int*>(st_rw + (int64_t)B200AT_ST_SP_ADV * p.B + b), moved);
 }
 
+// 12 kernel launches (+ one memset) per move: three histogram passes, the sums pass, seven sectioning passes, the final
+// pass.  It was 23 launches + 2 memsets: three scan, one need and seven decide launches of one CTA / one warp per
+// sample sat in between.
 template <int VEC>
 int launch_l1(const B200atImages& p, void* scratch, float* st_rw, float eps, cudaStream_t s) {
   const L1Scratch S = l1_scratch(scratch, p.B);
   cudaError_t e = cudaMemsetAsync(S.hist, 0, sizeof(int) * (3 * kHistBins + kMetaWords) * p.B, s);
   if (e != cudaSuccess) return (int)e;
-  e = cudaMemsetAsync(st_rw + (int64_t)B200AT_ST_SP_ADV * p.B, 0, sizeof(int) * p.B, s);
-  if (e != cudaSuccess) return (int)e;
   dim3 grid(kChunks, (unsigned)p.B);
-  l1_hist_kernel<0, VEC><<<grid, kThreads, 0, s>>>(p, scratch);
-  l1_scan_kernel<0><<<(unsigned)p.B, kThreads, 0, s>>>(p.st, scratch, p.B, p.n);
-  l1_hist_kernel<1, VEC><<<grid, kThreads, 0, s>>>(p, scratch);
-  l1_scan_kernel<1><<<(unsigned)p.B, kThreads, 0, s>>>(p.st, scratch, p.B, p.n);
-  l1_hist_kernel<2, VEC><<<grid, kThreads, 0, s>>>(p, scratch);
-  l1_scan_kernel<2><<<(unsigned)p.B, kThreads, 0, s>>>(p.st, scratch, p.B, p.n);
+  l1_hist_kernel<0, VEC><<<grid, kThreads, 0, s>>>(p, scratch, st_rw);
+  l1_hist_kernel<1, VEC><<<grid, kThreads, 0, s>>>(p, scratch, st_rw);
+  l1_hist_kernel<2, VEC><<<grid, kThreads, 0, s>>>(p, scratch, st_rw);
   l1_sums_kernel<VEC><<<grid, kThreads, 0, s>>>(p, scratch);
-  l1_need_kernel<<<(unsigned)p.B, 32, 0, s>>>(scratch, p.B, eps);
-  for (int pass = 0; pass < B200AT_L1_PASSES; ++pass) {
-    l1_section_kernel<VEC><<<grid, kThreads, 0, s>>>(p, scratch, pass);
-    l1_decide_kernel<<<(unsigned)p.B, 32, 0, s>>>(scratch, p.B, pass);
-  }
+  for (int pass = 0; pass < B200AT_L1_PASSES; ++pass) l1_section_kernel<VEC><<<grid, kThreads, 0, s>>>(p, scratch, pass, eps);
   l1_final_kernel<VEC><<<grid, kThreads, 0, s>>>(p, scratch, st_rw);
   return (int)cudaGetLastError();
 }

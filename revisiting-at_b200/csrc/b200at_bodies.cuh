@@ -212,12 +212,20 @@ B200AT_HD B200atL2Ctx b200at_l2_ctx(const B200atImages& p, int b, const float* s
 
 // KEEP: load with the L2-resident policy (phases 0..2 of the single-launch form: the next phase re-reads the operands).
 // `e` = first element of the vector (of sample b, whose constants are in c).
+// `gpre`: the gradient vector if the caller already holds it (shared-memory copy made in phase 0), else null.
 template <int PHASE, int VEC, bool KEEP>
 B200AT_HD float b200at_l2_body_ctx(const B200atImages& p, int64_t e, const B200atL2Ctx& c, float eps, float a,
-                                   float one_minus_a) {
+                                   float one_minus_a, const B200atVec<VEC>* gpre = nullptr) {
   const bool improved = c.improved, write_adv = c.write_adv, restore = c.restore;
   B200atVec<VEC> x, xo, xc, g;
-  if (KEEP) {
+  if (gpre) {
+    g = *gpre;
+    if (PHASE > 0) {
+      x = KEEP ? b200at_ld_keep<VEC>(p.x + e) : b200at_ld_stream<VEC>(p.x + e);
+      xc = KEEP ? b200at_ld_keep<VEC>((restore ? p.x_best : p.x_adv) + e) : b200at_ld_stream<VEC>((restore ? p.x_best : p.x_adv) + e);
+    }
+    if (PHASE > 1) xo = KEEP ? b200at_ld_keep<VEC>(p.x_old + e) : b200at_ld_stream<VEC>(p.x_old + e);
+  } else if (KEEP) {
     g = b200at_ld_keep<VEC>((restore ? p.grad_best : p.grad) + e);
     if (PHASE > 0) {
       x = b200at_ld_keep<VEC>(p.x + e);

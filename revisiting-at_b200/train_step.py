@@ -109,6 +109,46 @@ class GraphedAttack:
         return out
 
 
+class GraphedStep:
+    """The WHOLE training step -- attack, training forward, backward, gradient all-reduce, fused AdamW, EMA -- replayed from
+    one CUDA graph (torch's whole-network capture recipe: static input buffers, `zero_grad(set_to_none=True)`, capturable
+    fused optimiser).  The outer forward / backward is ~400 launches of 3-100 us kernels driven from Python autograd; at
+    one process per GPU that launch path is a visible share of the step (the DistributedDataParallel experiment shows it:
+    1.25 ms of pure host-side hook work appeared 1:1 in the step time, profiles/r02_ddp_n2_variants.txt).
+    The first `warmup` calls per input signature run eagerly, the next one is captured.  The learning rate is a device
+    tensor (`optimizer.param_groups[i]['lr']`), so schedules keep working: `set_lr` writes it."""
+
+    def __init__(self, step, warmup=2):
+        self.step, self.warmup = step, warmup
+        self.seen, self.graphs = {}, {}
+
+    def __call__(self, images, target):
+        step = self.step
+        key = (tuple(images.shape), images.dtype, tuple(target.shape), target.dtype)
+        hit = self.graphs.get(key)
+        if hit is None:
+            n = self.seen.get(key, 0)
+            self.seen[key] = n + 1
+            if n < self.warmup or not images.is_cuda:
+                return step.eager_step(images, target)
+            sx, sy = images.detach().clone(), target.detach().clone()
+            step.use_graph(False)                          # the attack is recorded inline: captures do not nest
+            ops.invalidate_derived()
+            step.optimizer.zero_grad(set_to_none=True)
+            graph = torch.cuda.CUDAGraph()
+            n0 = _abi.LAUNCHES['count']
+            with torch.cuda.graph(graph, capture_error_mode='thread_local'):
+                loss = step.eager_step(sx, sy)
+            hit = self.graphs[key] = (graph, sx, sy, loss, _abi.LAUNCHES['count'] - n0)
+        graph, sx, sy, loss, n_kernels = hit
+        sx.copy_(images, non_blocking=True)
+        sy.copy_(target, non_blocking=True)
+        graph.replay()
+        ops.invalidate_derived()                           # eager consumers (validation) must re-derive from the new weights
+        _abi.LAUNCHES['count'] += n_kernels
+        return loss
+
+
 class DevicePrefetcher:
     """Pinned host batches -> device, one batch ahead on a copy stream: the device side of the reference's input path
     (`DataLoader(pin_memory=True)` workers + `images.cuda(non_blocking=True)`, main.py:961-966), so that the 77 MB
@@ -159,13 +199,60 @@ class DeviceEma:
         return out
 
 
+class FlatGradAllReduce:
+    """The step's one collective (main.py:890,992: DDP's mean of the fp32 weight gradients over the ranks) as ONE NCCL
+    all-reduce over a flat fp32 buffer, issued when the backward has finished.
+
+    Why not `DistributedDataParallel`: measured at 2 GPUs (profiles/r02_ddp_n2_variants.txt) the wrapper costs 1.25 ms per
+    33 ms step whatever the bucket size (8 / 25 / 120 MB), gradient dtype (fp32 / bf16 hook) or NCCL CTA budget -- it is
+    the reducer's per-parameter hooks and bucket bookkeeping on a launch-bound backward (186 parameters), not wire time:
+    115 MB over NVLink 5 is ~0.2 ms.  Here: one multi-tensor copy of the gradients into the flat buffer (35 us), one
+    all-reduce (AVG), and `p.grad` re-pointed at views of the buffer for the optimiser.  Same arithmetic as DDP's
+    (sum, then / world size in fp32).  Like DDP's constructor, the parameters and buffers of rank 0 are broadcast once."""
+
+    def __init__(self, module):
+        import torch.distributed as dist
+        self.dist = dist
+        self.world = dist.get_world_size()
+        self.params = [p for p in module.parameters() if p.requires_grad]
+        dev = self.params[0].device
+        self.flat = torch.zeros(sum(p.numel() for p in self.params), device=dev, dtype=torch.float32)
+        self.views, off = [], 0
+        for p in self.params:
+            self.views.append(self.flat[off:off + p.numel()].view_as(p))
+            off += p.numel()
+        with torch.no_grad():
+            for t in list(module.parameters()) + list(module.buffers()):
+                dist.broadcast(t.data, 0)
+        self.avg = dist.get_backend() == 'nccl'
+
+    @torch.no_grad()
+    def reduce(self):
+        src, dst = [], []
+        for p, v in zip(self.params, self.views):
+            if p.grad is None:
+                v.zero_()
+            elif p.grad.data_ptr() != v.data_ptr():
+                src.append(p.grad if p.grad.dtype == torch.float32 else p.grad.float())
+                dst.append(v)
+        if src:
+            torch._foreach_copy_(dst, src)
+        if self.avg:
+            self.dist.all_reduce(self.flat, op=self.dist.ReduceOp.AVG)
+        else:                                                   # gloo (CPU tests): no AVG
+            self.dist.all_reduce(self.flat)
+            self.flat.div_(self.world)
+        for p, v in zip(self.params, self.views):
+            p.grad = v
+
+
 class AdvTrainStep:
     """One adversarial training step on one rank (main.py:961-997)."""
 
     def __init__(self, base_model, attack='apgd', norm='Linf', eps=4. / 255., n_iter=2, lr=1e-3, weight_decay=0.05,
                  label_smoothing=0., ema=False, distributed=False, device=None, autocast_dtype=torch.bfloat16,
                  channels_last=True, mixup_fn=None, perturb=None, graph_attack=False, param_groups=None,
-                 optimizer='adamw', momentum=0.9):
+                 optimizer='adamw', momentum=0.9, graph_step=False):
         self.device = device
         # `perturb` overrides the attack callable (same (model, x, y) contract as main.py:283)
         perturb = perturb if perturb is not None else make_attack(attack, norm, eps, n_iter, mixup_fn=mixup_fn)
@@ -179,13 +266,23 @@ class AdvTrainStep:
         model = model.to(device)
         self.raw = model
         self.ema = DeviceEma(model) if ema else None                           # created before the DDP wrap (main.py:884)
-        if distributed:
+        self.flat_reduce = None
+        import os
+        if distributed and os.environ.get('B200AT_DDP', 'flat') == 'flat':
+            self.flat_reduce = FlatGradAllReduce(model)
+        elif distributed:
             ids = [device.index] if (device is not None and device.type == 'cuda') else None
             # main.py:890.  broadcast_buffers=False: the only buffers are the normaliser's constant mean/std, and the
             # per-forward re-broadcast would bump their version counters, i.e. force a device->host read of the 3+3
             # constants (a host synchronisation) in front of every fused first-stem-stage launch.
+            # B200AT_DDP_BUCKET_MB / B200AT_DDP_BF16: measurement knobs for the all-reduce tail (profiles/r02_ddp_n2_*.txt);
+            # defaults are torch's (25 MB buckets, fp32 gradients: main.py:890 uses DDP as is).  B200AT_DDP=torch selects it.
+            bucket_mb = float(os.environ.get('B200AT_DDP_BUCKET_MB', '25'))
             model = nn.parallel.DistributedDataParallel(model, device_ids=ids, broadcast_buffers=False,
-                                                        gradient_as_bucket_view=True)
+                                                        gradient_as_bucket_view=True, bucket_cap_mb=bucket_mb)
+            if os.environ.get('B200AT_DDP_BF16') == '1':
+                from torch.distributed.algorithms.ddp_comm_hooks import default_hooks
+                model.register_comm_hook(None, default_hooks.bf16_compress_hook)
         self.model = model
         self.perturb = perturb is not None
         if param_groups is not None:                                           # the driver's per-arch rule (main.py:395-452)
@@ -199,10 +296,23 @@ class AdvTrainStep:
         if optimizer == 'sgd':                                                 # main.py:454-457
             self.optimizer = torch.optim.SGD(groups, lr=lr, momentum=momentum)
         else:
-            self.optimizer = torch.optim.AdamW(groups, lr=lr, betas=(0.9, 0.95), fused=on_gpu)
+            # graph_step: the optimiser is recorded in the step's CUDA graph -> capturable (device-side step counter and lr)
+            cap = bool(graph_step and on_gpu)
+            self.optimizer = torch.optim.AdamW(groups, lr=torch.tensor(float(lr), device=device) if cap else lr,
+                                               betas=(0.9, 0.95), fused=on_gpu, capturable=cap)
         self.label_smoothing = label_smoothing
         self.mixup_fn = mixup_fn
         self.autocast_dtype = autocast_dtype
+        self.graphed = GraphedStep(self) if (graph_step and on_gpu and optimizer != 'sgd' and
+                                            (not distributed or self.flat_reduce is not None)) else None
+
+    def set_lr(self, lr):
+        """learning rate of every group (main.py:957-959 sets it per iteration); a device tensor under `graph_step`"""
+        for g in self.optimizer.param_groups:
+            if torch.is_tensor(g['lr']):
+                g['lr'].fill_(float(lr))
+            else:
+                g['lr'] = lr
 
     def use_graph(self, on):
         """switch the attack between its CUDA-graph replay and the eager launch sequence (same kernels)"""
@@ -215,6 +325,11 @@ class AdvTrainStep:
         return F.cross_entropy(output.float(), target, label_smoothing=self.label_smoothing)
 
     def __call__(self, images, target):
+        if self.graphed is not None:
+            return self.graphed(images, target)
+        return self.eager_step(images, target)
+
+    def eager_step(self, images, target):
         self.model.train()
         if self.perturb:
             self.raw.set_perturb(True)
@@ -224,7 +339,9 @@ class AdvTrainStep:
         with torch.autocast(device_type=images.device.type, dtype=self.autocast_dtype):
             output = self.model(images, target) if self.perturb else self.model(images)
             loss = self.loss(output, target)
-        loss.backward()                                                         # DDP all-reduce overlaps here
+        loss.backward()                                                         # (B200AT_DDP=torch: all-reduce overlaps here)
+        if self.flat_reduce is not None:
+            self.flat_reduce.reduce()                                           # the step's only collective
         self.optimizer.step()
         ops.invalidate_derived()          # fused optimisers do not move the parameters' version counters (see ops.py)
         if self.ema is not None:

@@ -70,7 +70,8 @@ def test_attack_shards_without_communication(tmp_path):
     assert res == {'Linf': True, 'L2': True, 'L1': True}, res
 
 
-def _ddp_worker(rank, world, port, out):
+def _ddp_worker(rank, world, port, out, mode='flat'):
+    os.environ['B200AT_DDP'] = mode                  # 'flat': one all-reduce over a flat buffer; 'torch': DistributedDataParallel
     _setup(rank, world, port)
     import revisiting_at_b200  # noqa: F401
     from revisiting_at_b200 import attack
@@ -78,8 +79,11 @@ def _ddp_worker(rank, world, port, out):
     from hostcheck.backend import HostBackend
     from oracle.small_cnn import SmallCNN
     perturb = partial(attack.run_apgd, HostBackend(), norm='Linf', eps=8 / 255., n_iter=2)
-    torch.manual_seed(0)
+    torch.manual_seed(rank)                          # ranks start from DIFFERENT weights: the constructor must broadcast rank 0's
     model = SmallCNN()
+    if rank == 0:
+        torch.manual_seed(0)
+        model = SmallCNN()
     x, y = _data()
     step = AdvTrainStep(model, distributed=True, device=torch.device('cpu'), autocast_dtype=torch.float32,
                         channels_last=False, perturb=perturb, lr=1e-2)
@@ -100,9 +104,10 @@ def _ddp_worker(rank, world, port, out):
     dist.destroy_process_group()
 
 
-def test_ddp_step_matches_single_process(tmp_path):
+@pytest.mark.parametrize('mode', ['flat', 'torch'])
+def test_ddp_step_matches_single_process(tmp_path, mode):
     out = str(tmp_path / 'res.pt')
-    mp.spawn(_ddp_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    mp.spawn(_ddp_worker, args=(2, _free_port(), out, mode), nprocs=2, join=True)
     res = torch.load(out)
     assert res['ranks_equal'] and res['loss_finite'], res
     assert res['max_diff_vs_single'] < 1e-4, res     # AdamW amplifies fp32 sum-order noise of the mean gradient

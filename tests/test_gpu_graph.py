@@ -68,3 +68,40 @@ def test_train_step_with_graphed_attack_matches_eager(cuda_dev):
         want, stale = o.eval()(x.cpu()), o0.eval()(x.cpu())
     assert (got - want).abs().max() <= 5e-2, (got - want).abs().max()
     assert (want - stale).abs().max() > 0.2            # the six steps moved the logits far beyond that tolerance
+
+
+def test_whole_step_graph_trains_like_the_eager_step(cuda_dev):
+    """`graph_step=True`: attack + training forward / backward + fused AdamW (+ EMA) replayed from ONE CUDA graph.  Two
+    trainers from the same weights see the same six batches; the weight-gradient kernels use atomics, so the parameters
+    are compared with a tolerance, and the learning-rate tensor is changed between replays to show schedules still act."""
+    from revisiting_at_b200 import convnext
+    from revisiting_at_b200.train_step import AdvTrainStep
+    base = convnext.build('convnext_tiny', normalize=True, seed=0)
+    g = torch.Generator().manual_seed(4)
+    batches = [(torch.rand(8, 3, 64, 64, generator=g).to(cuda_dev), torch.randint(0, 1000, (8,), generator=g).to(cuda_dev))
+               for _ in range(6)]
+    eager = AdvTrainStep(copy.deepcopy(base), 'apgd', 'Linf', 4. / 255., 2, device=cuda_dev, graph_attack=True, ema=True)
+    whole = AdvTrainStep(copy.deepcopy(base), 'apgd', 'Linf', 4. / 255., 2, device=cuda_dev, graph_attack=True, ema=True,
+                         graph_step=True)
+    le, lw = [], []
+    for i, (x, y) in enumerate(batches):
+        lr = 1e-3 * (1 + i)
+        eager.set_lr(lr); whole.set_lr(lr)
+        le.append(eager(x, y).item()); lw.append(whole(x, y).item())
+    assert len(whole.graphed.graphs) == 1
+    assert all(abs(a - b) <= 2e-2 * abs(a) for a, b in zip(le, lw)), (le, lw)
+    pe = torch.cat([p.detach().flatten() for p in eager.raw.parameters()])
+    pw = torch.cat([p.detach().flatten() for p in whole.raw.parameters()])
+    moved = (pe - torch.cat([p.detach().flatten() for p in base.parameters()]).to(cuda_dev)).abs().max().item()
+    assert moved > 1e-3                                                   # six AdamW steps with growing lr did move them
+    cos = torch.nn.functional.cosine_similarity(pe - pw.new_zeros(()), pw, dim=0).item()
+    assert cos > 0.9999, cos
+    # the replay really applies the CURRENT learning rate: a step with lr = 0 leaves the parameters untouched
+    whole.set_lr(0.0)
+    before = pw.clone()
+    whole(*batches[0])
+    after = torch.cat([p.detach().flatten() for p in whole.raw.parameters()])
+    assert torch.equal(before, after)
+    # the EMA shadow is updated inside the graph as well
+    ee = torch.cat([t.flatten() for t in eager.ema.shadow]); ew = torch.cat([t.flatten() for t in whole.ema.shadow])
+    assert (ee - ew).abs().max().item() <= 1e-4 and not torch.equal(ew, torch.cat([p.detach().flatten() for p in base.parameters()]).to(cuda_dev))
