@@ -59,7 +59,7 @@ def parse():
     ap.add_argument('--ema', type=int, default=None, help='on-device EMA of the parameters (default: on for convnext_base = config 4)')
     ap.add_argument('--label-smoothing', type=float, default=None, help='default 0.1 for convnext_base (config 4), else 0')
     ap.add_argument('--no-graph', action='store_true', help='launch the attack kernel by kernel instead of replaying its CUDA graph')
-    ap.add_argument('--graph-step', type=int, default=int(os.environ.get('B200AT_GRAPH_STEP', '0')), help='1: replay the WHOLE step (attack + training forward/backward + all-reduce + AdamW) from one CUDA graph')
+    ap.add_argument('--graph-step', type=int, default=int(os.environ.get('B200AT_GRAPH_STEP', '1')), help='1: replay the WHOLE step (attack + training forward/backward + all-reduce + AdamW) from one CUDA graph')
     ap.add_argument('--cpu-seconds', type=float, default=20.0, help='budget of the cpu_baseline sample')
     ap.add_argument('--res', type=int, default=RES, help='image side (224 = the metric line; 320 = the secondary resolution of north_star)')
     return ap.parse_args()

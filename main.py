@@ -315,6 +315,10 @@ class ImageNetTrainer:
         step = AdvTrainStep(model, attack=attack, perturb=perturb, distributed=bool(distributed), device=self.device,
                             ema=bool(model_ema), channels_last=bool(use_channel_last), mixup_fn=None,
                             graph_attack=attack == 'apgd' and self.mixup_fn is None,
+                            # the whole step (attack, forward, backward, all-reduce, AdamW, EMA) as one CUDA graph; the
+                            # host-side Mixup draw and the fgsm noise keep those configurations on the eager path
+                            graph_step=(attack == 'apgd' and self.mixup_fn is None and optimizer == 'adamw' and
+                                        os.environ.get('B200AT_GRAPH_STEP', '1') == '1'),
                             param_groups=lambda named: weight_decay_groups(named, arch, weight_decay),
                             optimizer=optimizer, momentum=momentum)
         return step
@@ -345,8 +349,7 @@ class ImageNetTrainer:
             target = target.to(self.device, non_blocking=True)
             if self.mixup_fn is not None:
                 images, target = self.mixup_fn(images, target)
-            for group in self.optimizer.param_groups:
-                group['lr'] = float(lrs[ix])
+            self.step.set_lr(float(lrs[ix]))                          # a device tensor when the step is a CUDA graph
             loss = self.step(images, target)
             seen += images.shape[0]
             if log_level > 0:

@@ -219,7 +219,9 @@ class FlatGradAllReduce:
         self.flat = torch.zeros(sum(p.numel() for p in self.params), device=dev, dtype=torch.float32)
         self.views, off = [], 0
         for p in self.params:
-            self.views.append(self.flat[off:off + p.numel()].view_as(p))
+            # same strides as the parameter (channels_last conv weights included): the fused optimiser wants parameter and
+            # gradient in one layout; every parameter is dense, so its strides address exactly numel() elements
+            self.views.append(self.flat[off:off + p.numel()].as_strided(p.shape, p.stride()))
             off += p.numel()
         with torch.no_grad():
             for t in list(module.parameters()) + list(module.buffers()):
