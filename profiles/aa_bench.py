@@ -22,7 +22,7 @@ from revisiting_at_b200 import _abi, autoattack, convnext  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument('--arch', default='convnext_large')
 ap.add_argument('--res', type=int, default=320)
-ap.add_argument('--n', type=int, default=100)
+ap.add_argument('--n', '--points', dest='n', type=int, default=100)
 ap.add_argument('--bs', type=int, default=100)
 ap.add_argument('--iters', type=int, default=100)
 ap.add_argument('--targets', type=int, default=9)
