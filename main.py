@@ -253,6 +253,10 @@ class ImageNetTrainer:
                             label_smoothing, seed, augmentations, world_size):
         torch.manual_seed(seed)
         res = self.get_resolution(0)
+        if self.get_resolution(10 ** 6) != res:
+            # the reference retargets the decoder every epoch (main.py:716-720); this driver builds its loaders once
+            raise SystemExit('progressive resizing (resolution.min_res != resolution.max_res) is not built: '
+                             'pass equal --resolution.min_res / --resolution.max_res')
         world = world_size if distributed else 1
         if train_dataset.startswith('synthetic'):
             train = SyntheticLoader(train_dataset, batch_size, res, seed * 1000 + self.gpu)

@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(kThreads) l2_phase_kernel(B200atImages p, floa
 // held at 2 CTAs per SM (37 samples x 2.4 MB in flight, inside the 126 MB L2) by the dynamic shared-memory request.
 // HBM traffic 20 B/element instead of 52.
 constexpr int kL2Cluster = 8;
-constexpr int kL2Threads = 512;           // 2 CTAs x 16 warps per SM: the loads in flight that the HBM phase needs
+constexpr int kL2Threads = 256;           // 2 CTAs x 8 warps per SM, four vectors (all operands) in flight per thread
 constexpr int kL2SmemCap = 100 * 1024;    // dynamic shared memory per CTA: the gradient slice; also bounds residency to 2 CTAs / SM
 
 // `gbuf`: this CTA's slice of the gradient in shared memory (filled in phase 0, read by phases 1..3: 12 of the 52 B/element
@@ -148,27 +148,35 @@ __device__ __forceinline__ float l2_cluster_phase(const B200atImages& p, int b, 
   const int v0 = rank * per, v1 = (v0 + per < nvec_row) ? v0 + per : nvec_row;
   const B200atL2Ctx ctx = b200at_l2_ctx<PHASE>(p, b, sums);
   const int64_t base = (int64_t)b * p.n;
-  float acc0 = 0.0f, acc1 = 0.0f, acc2 = 0.0f, acc3 = 0.0f;
+  float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
   B200atVec<VEC>* gv = reinterpret_cast<B200atVec<VEC>*>(gbuf);
-  auto one = [&](int v) -> float {
+  // loads of a vector: the gradient from HBM (phase 0, streamed and parked in shared memory) or from shared memory
+  auto load = [&](int v, B200atL2Ops<VEC>& in) {
     const int64_t e = base + (int64_t)v * VEC;
-    if (gbuf == nullptr) return b200at_l2_body_ctx<PHASE, VEC, (PHASE < 3)>(p, e, ctx, eps, a, one_minus_a);
-    if (PHASE == 0) {                                    // the gradient is read from HBM exactly once: stream it, park it
-      const B200atVec<VEC> g = b200at_ld_stream<VEC>((ctx.restore ? p.grad_best : p.grad) + e);
-      gv[v - v0] = g;
-      return b200at_l2_body_ctx<0, VEC, false>(p, e, ctx, eps, a, one_minus_a, &g);
+    if (gbuf == nullptr) { b200at_l2_load<PHASE, VEC, (PHASE < 3)>(p, e, ctx, nullptr, in); return; }
+    if (PHASE == 0) {
+      in.g = b200at_ld_stream<VEC>((ctx.restore ? p.grad_best : p.grad) + e);
+      gv[v - v0] = in.g;
+    } else {
+      const B200atVec<VEC> g = gv[v - v0];
+      b200at_l2_load<PHASE, VEC, (PHASE < 3)>(p, e, ctx, &g, in);
     }
-    const B200atVec<VEC> g = gv[v - v0];
-    return b200at_l2_body_ctx<PHASE, VEC, (PHASE < 3)>(p, e, ctx, eps, a, one_minus_a, &g);
   };
   int v = v0 + threadIdx.x;
-  for (; v + 3 * kL2Threads < v1; v += 4 * kL2Threads) {      // four independent vectors in flight per thread
-    acc0 += one(v);
-    acc1 += one(v + kL2Threads);
-    acc2 += one(v + 2 * kL2Threads);
-    acc3 += one(v + 3 * kL2Threads);
+  for (; v + 3 * kL2Threads < v1; v += 4 * kL2Threads) {      // four vectors: all loads first, then the (aliasing) stores
+    B200atL2Ops<VEC> in[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) load(v + k * kL2Threads, in[k]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      acc[k] += b200at_l2_apply<PHASE, VEC>(p, base + (int64_t)(v + k * kL2Threads) * VEC, ctx, eps, a, one_minus_a, in[k]);
   }
-  for (; v < v1; v += kL2Threads) acc0 += one(v);
+  for (; v < v1; v += kL2Threads) {
+    B200atL2Ops<VEC> in;
+    load(v, in);
+    acc[0] += b200at_l2_apply<PHASE, VEC>(p, base + (int64_t)v * VEC, ctx, eps, a, one_minus_a, in);
+  }
+  const float acc0 = acc[0], acc1 = acc[1], acc2 = acc[2], acc3 = acc[3];
   if (PHASE == 3) return 0.0f;
   return cta_sum<kL2Threads>((acc0 + acc1) + (acc2 + acc3), red);    // valid in warp 0
 }

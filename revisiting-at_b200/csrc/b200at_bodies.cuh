@@ -211,57 +211,62 @@ B200AT_HD B200atL2Ctx b200at_l2_ctx(const B200atImages& p, int b, const float* s
 }
 
 // KEEP: load with the L2-resident policy (phases 0..2 of the single-launch form: the next phase re-reads the operands).
-// `e` = first element of the vector (of sample b, whose constants are in c).
+// `e` = first element of the vector (of sample b, whose constants are in c).  Split in a load half and an apply half so
+// that a caller can issue the loads of several vectors before the first store (x_new may alias x_old: the compiler
+// cannot move a later load above an earlier store itself).
 // `gpre`: the gradient vector if the caller already holds it (shared-memory copy made in phase 0), else null.
+template <int VEC>
+struct B200atL2Ops { B200atVec<VEC> x, xc, xo, g; };
+
 template <int PHASE, int VEC, bool KEEP>
-B200AT_HD float b200at_l2_body_ctx(const B200atImages& p, int64_t e, const B200atL2Ctx& c, float eps, float a,
-                                   float one_minus_a, const B200atVec<VEC>* gpre = nullptr) {
-  const bool improved = c.improved, write_adv = c.write_adv, restore = c.restore;
-  B200atVec<VEC> x, xo, xc, g;
-  if (gpre) {
-    g = *gpre;
-    if (PHASE > 0) {
-      x = KEEP ? b200at_ld_keep<VEC>(p.x + e) : b200at_ld_stream<VEC>(p.x + e);
-      xc = KEEP ? b200at_ld_keep<VEC>((restore ? p.x_best : p.x_adv) + e) : b200at_ld_stream<VEC>((restore ? p.x_best : p.x_adv) + e);
-    }
-    if (PHASE > 1) xo = KEEP ? b200at_ld_keep<VEC>(p.x_old + e) : b200at_ld_stream<VEC>(p.x_old + e);
-  } else if (KEEP) {
-    g = b200at_ld_keep<VEC>((restore ? p.grad_best : p.grad) + e);
-    if (PHASE > 0) {
-      x = b200at_ld_keep<VEC>(p.x + e);
-      xc = b200at_ld_keep<VEC>((restore ? p.x_best : p.x_adv) + e);
-    }
-    if (PHASE > 1) xo = b200at_ld_keep<VEC>(p.x_old + e);
-  } else {
-    g = b200at_ld_stream<VEC>((restore ? p.grad_best : p.grad) + e);
-    if (PHASE > 0) {
-      x = b200at_ld_stream<VEC>(p.x + e);
-      xc = b200at_ld_stream<VEC>((restore ? p.x_best : p.x_adv) + e);
-    }
-    if (PHASE > 1) xo = b200at_ld_stream<VEC>(p.x_old + e);
+B200AT_HD void b200at_l2_load(const B200atImages& p, int64_t e, const B200atL2Ctx& c, const B200atVec<VEC>* gpre,
+                              B200atL2Ops<VEC>& o) {
+  const bool restore = c.restore;
+  if (gpre) o.g = *gpre;
+  else o.g = KEEP ? b200at_ld_keep<VEC>((restore ? p.grad_best : p.grad) + e)
+                  : b200at_ld_stream<VEC>((restore ? p.grad_best : p.grad) + e);
+  if (PHASE > 0) {
+    o.x = KEEP ? b200at_ld_keep<VEC>(p.x + e) : b200at_ld_stream<VEC>(p.x + e);
+    o.xc = KEEP ? b200at_ld_keep<VEC>((restore ? p.x_best : p.x_adv) + e)
+                : b200at_ld_stream<VEC>((restore ? p.x_best : p.x_adv) + e);
   }
+  if (PHASE > 1) o.xo = KEEP ? b200at_ld_keep<VEC>(p.x_old + e) : b200at_ld_stream<VEC>(p.x_old + e);
+}
+
+template <int PHASE, int VEC>
+B200AT_HD float b200at_l2_apply(const B200atImages& p, int64_t e, const B200atL2Ctx& c, float eps, float a,
+                                float one_minus_a, const B200atL2Ops<VEC>& in) {
+  const bool improved = c.improved, write_adv = c.write_adv, restore = c.restore;
   if (PHASE == 3) {
     if (!restore) {
-      if (write_adv) b200at_st_stream<VEC>(p.x_best_adv + e, xc);
+      if (write_adv) b200at_st_stream<VEC>(p.x_best_adv + e, in.xc);
       if (improved) {
-        b200at_st_stream<VEC>(p.x_best + e, xc);
-        b200at_st_stream<VEC>(p.grad_best + e, g);
+        b200at_st_stream<VEC>(p.x_best + e, in.xc);
+        b200at_st_stream<VEC>(p.grad_best + e, in.g);
       }
     } else {
       if (write_adv) b200at_st_stream<VEC>(p.x_best_adv + e, b200at_ld_stream<VEC>(p.x_adv + e));
-      b200at_st_stream<VEC>(p.x_adv + e, xc);
+      b200at_st_stream<VEC>(p.x_adv + e, in.xc);
     }
   }
   B200atVec<VEC> o;
   float acc = 0.0f;
 #pragma unroll
   for (int i = 0; i < VEC; ++i) {
-    o.v[i] = b200at_l2_elem<PHASE>(PHASE > 0 ? x.v[i] : 0.0f, PHASE > 0 ? xc.v[i] : 0.0f, PHASE > 1 ? xo.v[i] : 0.0f,
-                                   g.v[i], c.step, eps, a, one_minus_a, c.nm);
+    o.v[i] = b200at_l2_elem<PHASE>(PHASE > 0 ? in.x.v[i] : 0.0f, PHASE > 0 ? in.xc.v[i] : 0.0f,
+                                   PHASE > 1 ? in.xo.v[i] : 0.0f, in.g.v[i], c.step, eps, a, one_minus_a, c.nm);
     acc = B200AT_ADD(acc, B200AT_MUL(o.v[i], o.v[i]));
   }
   if (PHASE == 3) b200at_st_keep<VEC>(p.x_new + e, o);
   return acc;
+}
+
+template <int PHASE, int VEC, bool KEEP>
+B200AT_HD float b200at_l2_body_ctx(const B200atImages& p, int64_t e, const B200atL2Ctx& c, float eps, float a,
+                                   float one_minus_a, const B200atVec<VEC>* gpre = nullptr) {
+  B200atL2Ops<VEC> in;
+  b200at_l2_load<PHASE, VEC, KEEP>(p, e, c, gpre, in);
+  return b200at_l2_apply<PHASE, VEC>(p, e, c, eps, a, one_minus_a, in);
 }
 
 // per-vector form (four-launch kernels, tests/hostcheck): vi = vector index over the whole batch

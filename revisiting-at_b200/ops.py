@@ -235,7 +235,10 @@ def install_derived(snapshot):
 
 def invalidate_derived(keep_tags=('host3',)):
     """Forget every cached kernel-side parameter copy (except host-side constants): the next use rebuilds
-    it.  Called right before a CUDA-graph capture so that the cast / transpose / fold kernels are recorded
+    it.  REQUIRED after any parameter write that does not move the tensor's version counter -- `p.data.copy_()` /
+    `p.data.mul_()` (swapping EMA weights in for an evaluation, manual weight surgery), fused optimisers outside
+    `torch.optim`'s step hook -- or the model silently runs on the previous bf16 / transposed copies
+    (`load_state_dict`, `copy_`, `add_` on the parameter itself DO move it and need nothing).  Called right before a CUDA-graph capture so that the cast / transpose / fold kernels are recorded
     INSIDE the graph and every replay re-derives them from the (in-place updated) fp32 master parameters."""
     for k in [k for k in _PCACHE if k[1] not in keep_tags]:
         del _PCACHE[k]
