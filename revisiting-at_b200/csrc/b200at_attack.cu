@@ -135,12 +135,13 @@ __global__ void __launch_bounds__(kThreads) l2_phase_kernel(B200atImages p, floa
 // held at 2 CTAs per SM (37 samples x 2.4 MB in flight, inside the 126 MB L2) by the dynamic shared-memory request.
 // HBM traffic 20 B/element instead of 52.
 constexpr int kL2Cluster = 8;
-constexpr int kL2Threads = 256;           // 2 CTAs x 8 warps per SM, four vectors (all operands) in flight per thread
+// threads per CTA: 512 (2 CTAs x 16 warps per SM, four vectors in flight per thread) measured 140 us per step at
+// 1024 x 3 x 224 x 224, 256 threads 161 us (profiles/r02_k1_driver_l2.txt); B200AT_L2_THREADS=256 selects the latter.
 constexpr int kL2SmemCap = 100 * 1024;    // dynamic shared memory per CTA: the gradient slice; also bounds residency to 2 CTAs / SM
 
 // `gbuf`: this CTA's slice of the gradient in shared memory (filled in phase 0, read by phases 1..3: 12 of the 52 B/element
 // the four phases read come from there instead of from L2), or null when the slice does not fit (n / 8 floats > the buffer).
-template <int PHASE, int VEC>
+template <int PHASE, int VEC, int kL2Threads>
 __device__ __forceinline__ float l2_cluster_phase(const B200atImages& p, int b, int rank, float eps, float a,
                                                   float one_minus_a, const float* sums, float* red, float* gbuf) {
   const int nvec_row = (int)(p.n / VEC);                 // n < 2^31 (checked by the entry point)
@@ -163,13 +164,26 @@ __device__ __forceinline__ float l2_cluster_phase(const B200atImages& p, int b, 
     }
   };
   int v = v0 + threadIdx.x;
-  for (; v + 3 * kL2Threads < v1; v += 4 * kL2Threads) {      // four vectors: all loads first, then the (aliasing) stores
-    B200atL2Ops<VEC> in[4];
+  if (kL2Threads <= 256) {
+    for (; v + 3 * kL2Threads < v1; v += 4 * kL2Threads) {    // four vectors: all loads first, then the (aliasing) stores
+      B200atL2Ops<VEC> in[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) load(v + k * kL2Threads, in[k]);
+      for (int k = 0; k < 4; ++k) load(v + k * kL2Threads, in[k]);
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
-      acc[k] += b200at_l2_apply<PHASE, VEC>(p, base + (int64_t)(v + k * kL2Threads) * VEC, ctx, eps, a, one_minus_a, in[k]);
+      for (int k = 0; k < 4; ++k)
+        acc[k] += b200at_l2_apply<PHASE, VEC>(p, base + (int64_t)(v + k * kL2Threads) * VEC, ctx, eps, a, one_minus_a, in[k]);
+    }
+  } else {
+    // 512 threads leave 64 registers per thread: holding four vectors' operands spills (210 us); vector by vector, the
+    // 32 warps of the SM supply the loads in flight (140 us)
+    for (; v + 3 * kL2Threads < v1; v += 4 * kL2Threads) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        B200atL2Ops<VEC> in;
+        load(v + k * kL2Threads, in);
+        acc[k] += b200at_l2_apply<PHASE, VEC>(p, base + (int64_t)(v + k * kL2Threads) * VEC, ctx, eps, a, one_minus_a, in);
+      }
+    }
   }
   for (; v < v1; v += kL2Threads) {
     B200atL2Ops<VEC> in;
@@ -189,7 +203,7 @@ __device__ __forceinline__ float l2_cluster_total(cooperative_groups::cluster_gr
   return t;
 }
 
-template <int VEC>
+template <int VEC, int kL2Threads>
 __global__ void __launch_bounds__(kL2Threads) l2_cluster_kernel(B200atImages p, float eps, float a, float one_minus_a) {
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
@@ -201,45 +215,49 @@ __global__ void __launch_bounds__(kL2Threads) l2_cluster_kernel(B200atImages p, 
   const int64_t slice = ((p.n / VEC + kL2Cluster - 1) / kL2Cluster) * VEC;
   float* gbuf = (slice * 4 <= kL2SmemCap) ? l2_gbuf : nullptr;
   float sums[3] = {0.f, 0.f, 0.f};
-  float t = l2_cluster_phase<0, VEC>(p, b, rank, eps, a, one_minus_a, sums, red, gbuf);
+  float t = l2_cluster_phase<0, VEC, kL2Threads>(p, b, rank, eps, a, one_minus_a, sums, red, gbuf);
   if (threadIdx.x == 0) part[0] = t;
   cluster.sync();
   sums[0] = l2_cluster_total(cluster, part, 0);
-  t = l2_cluster_phase<1, VEC>(p, b, rank, eps, a, one_minus_a, sums, red, gbuf);
+  t = l2_cluster_phase<1, VEC, kL2Threads>(p, b, rank, eps, a, one_minus_a, sums, red, gbuf);
   if (threadIdx.x == 0) part[1] = t;
   cluster.sync();
   sums[1] = l2_cluster_total(cluster, part, 1);
-  t = l2_cluster_phase<2, VEC>(p, b, rank, eps, a, one_minus_a, sums, red, gbuf);
+  t = l2_cluster_phase<2, VEC, kL2Threads>(p, b, rank, eps, a, one_minus_a, sums, red, gbuf);
   if (threadIdx.x == 0) part[2] = t;
   cluster.sync();
   sums[2] = l2_cluster_total(cluster, part, 2);
-  l2_cluster_phase<3, VEC>(p, b, rank, eps, a, one_minus_a, sums, red, gbuf);
+  l2_cluster_phase<3, VEC, kL2Threads>(p, b, rank, eps, a, one_minus_a, sums, red, gbuf);
   cluster.sync();   // nobody leaves while a peer may still be reading its partials
+}
+
+template <int VEC, int THREADS>
+int launch_l2_cluster(const B200atImages& p, float eps, float a, float oma, cudaStream_t s) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(kL2Cluster, (unsigned)p.B);
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = kL2SmemCap;
+  cfg.stream = s;
+  static bool configured[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!configured[dev & 63]) {
+    cudaError_t e = cudaFuncSetAttribute(l2_cluster_kernel<VEC, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kL2SmemCap);
+    if (e != cudaSuccess) return (int)e;
+    configured[dev & 63] = true;
+  }
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kL2Cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return (int)cudaLaunchKernelEx(&cfg, l2_cluster_kernel<VEC, THREADS>, p, eps, a, oma);
 }
 
 template <int VEC>
 int launch_l2(const B200atImages& p, float* scratch, float eps, float a, float oma, cudaStream_t s) {
   static const bool four_launches = [] { const char* e = getenv("B200AT_L2_PHASES"); return e != nullptr && e[0] == '4'; }();
-  if (!four_launches) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(kL2Cluster, (unsigned)p.B);
-    cfg.blockDim = dim3(kL2Threads);
-    cfg.dynamicSmemBytes = kL2SmemCap;
-    cfg.stream = s;
-    static bool configured[64] = {};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (!configured[dev & 63]) {
-      cudaError_t e = cudaFuncSetAttribute(l2_cluster_kernel<VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, kL2SmemCap);
-      if (e != cudaSuccess) return (int)e;
-      configured[dev & 63] = true;
-    }
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = kL2Cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    return (int)cudaLaunchKernelEx(&cfg, l2_cluster_kernel<VEC>, p, eps, a, oma);
-  }
+  static const bool narrow = [] { const char* e = getenv("B200AT_L2_THREADS"); return e != nullptr && atoi(e) == 256; }();
+  if (!four_launches) return narrow ? launch_l2_cluster<VEC, 256>(p, eps, a, oma, s) : launch_l2_cluster<VEC, 512>(p, eps, a, oma, s);
   dim3 grid(kChunks, (unsigned)p.B);
   l2_phase_kernel<0, VEC><<<grid, kThreads, 0, s>>>(p, scratch, eps, a, oma);
   l2_phase_kernel<1, VEC><<<grid, kThreads, 0, s>>>(p, scratch, eps, a, oma);

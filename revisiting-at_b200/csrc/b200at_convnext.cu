@@ -25,23 +25,10 @@ typedef __nv_bfloat162 bf162;
 
 __device__ __forceinline__ float gelu_f(float v) { return b200at_gelu(v); }
 __device__ __forceinline__ float gelu_grad_f(float v) { return b200at_gelu_grad(v); }
-// packed fp32x2 FMA (sm_100 FFMA2): one issue slot for the two channels a thread carries
-__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
-  unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b),
-                     rc = *reinterpret_cast<unsigned long long*>(&c), rd;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
-  return *reinterpret_cast<float2*>(&rd);
-}
-__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
-  unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b), rd;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
-  return *reinterpret_cast<float2*>(&rd);
-}
-__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
-  unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b), rd;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
-  return *reinterpret_cast<float2*>(&rd);
-}
+// packed fp32x2 forms (sm_100 FFMA2): one issue slot for the two channels a thread carries
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return b200at_ffma2(a, b, c); }
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) { return b200at_fadd2(a, b); }
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) { return b200at_fmul2(a, b); }
 // bf16x2 word -> two fp32 (exact): low half << 16, high half masked -- two ALU-pipe instructions, none on the FMA pipe
 __device__ __forceinline__ float2 bf2_to_f2(uint32_t u) {
   return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
@@ -355,7 +342,7 @@ __global__ void __launch_bounds__(kRingThreads) ln_fwd_ring_kernel(const bf16* _
         float2 o0 = ffma2(f[j][0], fmul2(rs2, wr[j][0]), br[j][0]);
         float2 o1 = ffma2(f[j][1], fmul2(rs2, wr[j][1]), br[j][1]);
         if (GELU) {
-          o0.x = gelu_f(o0.x); o0.y = gelu_f(o0.y); o1.x = gelu_f(o1.x); o1.y = gelu_f(o1.y);
+          o0 = b200at_gelu2(o0); o1 = b200at_gelu2(o1);
         }
         yr[G * j] = make_uint2(f2_to_bf2(o0), f2_to_bf2(o1));
       }
@@ -471,7 +458,7 @@ __global__ void __launch_bounds__(kRingThreads) ln_bwd_ring_kernel(const bf16* _
           if (!live) d = make_float2(0.f, 0.f);
           if (GELU) {
             const float2 pre = ffma2(xh[j][h], wr[j][h], br[j][h]);
-            d.x *= gelu_grad_f(pre.x); d.y *= gelu_grad_f(pre.y);
+            d = fmul2(d, b200at_gelu_grad2(pre));
           }
           if (PGRAD) { aw[j][h] = ffma2(d, xh[j][h], aw[j][h]); ab[j][h] = fadd2(ab[j][h], d); }
           g[j][h] = fmul2(d, wr[j][h]);
@@ -536,13 +523,19 @@ __global__ void __launch_bounds__(256) bias_gelu_fwd_kernel(const bf16* __restri
     float f[8];
     unpack4(make_uint2(u0.x, u0.y), f); unpack4(make_uint2(u0.z, u0.w), f + 4);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) f[k] = gelu_f(f[k] + bb[k]);
+    for (int k = 0; k < 8; k += 2) {
+      const float2 r = b200at_gelu2(fadd2(make_float2(f[k], f[k + 1]), make_float2(bb[k], bb[k + 1])));
+      f[k] = r.x; f[k + 1] = r.y;
+    }
     uint2 lo = pack4(f), hi = pack4(f + 4);
     reinterpret_cast<uint4*>(h)[q] = make_uint4(lo.x, lo.y, hi.x, hi.y);
     if (two) {
       unpack4(make_uint2(u1.x, u1.y), f); unpack4(make_uint2(u1.z, u1.w), f + 4);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) f[k] = gelu_f(f[k] + bb[k]);
+      for (int k = 0; k < 8; k += 2) {
+      const float2 r = b200at_gelu2(fadd2(make_float2(f[k], f[k + 1]), make_float2(bb[k], bb[k + 1])));
+      f[k] = r.x; f[k + 1] = r.y;
+    }
       lo = pack4(f); hi = pack4(f + 4);
       reinterpret_cast<uint4*>(h)[q + stride] = make_uint4(lo.x, lo.y, hi.x, hi.y);
     }
@@ -583,7 +576,11 @@ __global__ void __launch_bounds__(256) bias_gelu_bwd_kernel(const bf16* __restri
       unpack4(make_uint2(u[w].x, u[w].y), f); unpack4(make_uint2(u[w].z, u[w].w), f + 4);
       unpack4(make_uint2(d[w].x, d[w].y), g); unpack4(make_uint2(d[w].z, d[w].w), g + 4);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) g[k] *= gelu_grad_f(f[k] + bb[k]);
+      for (int k = 0; k < 8; k += 2) {
+        const float2 r = fmul2(make_float2(g[k], g[k + 1]),
+                               b200at_gelu_grad2(fadd2(make_float2(f[k], f[k + 1]), make_float2(bb[k], bb[k + 1]))));
+        g[k] = r.x; g[k + 1] = r.y;
+      }
       const uint2 lo = pack4(g), hi = pack4(g + 4);
       reinterpret_cast<uint4*>(dz)[q + w * stride] = make_uint4(lo.x, lo.y, hi.x, hi.y);
       if (DBIAS) {   // sum what the weight-gradient GEMM will see: the bf16-rounded dz

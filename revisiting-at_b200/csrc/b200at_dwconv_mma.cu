@@ -292,9 +292,250 @@ __global__ void __launch_bounds__(kThreads, 1) dwconv7_mma_kernel(const __grid_c
   if (tid == 0) b200at::tma_store_wait_all();
 }
 
+// ---------------------------------------------------------------------------------------------- v4: two warp groups
+// The three phases of a tile are all bound by the load/store unit, but inside ONE CTA they ran back to back with barriers
+// in between, and the unit idled 45 % of the time (profiles/r02_dwconv_mma_ncu_v3.txt).  Here warps 0-7 ("T") only move
+// data -- phase 1 of tile i+1 and phase 3 of tile i-1 -- while warps 8-15 ("M", two channels each) run phase 2 of tile i
+// on the other of two plane buffers.  Hand-off through mbarriers (planes_full / planes_done, one arrival per warp);
+// the T group synchronises with itself through named barrier 1.
+__device__ __forceinline__ void bar_t_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+template <int NT, bool ADD, bool MULTI>
+__global__ void __launch_bounds__(kThreads, 1) dwconv7_mma_pp_kernel(const __grid_constant__ CUtensorMap map_x,
+                                                                    const __grid_constant__ CUtensorMap map_add,
+                                                                    const __grid_constant__ CUtensorMap map_y,
+                                                                    const DwmParams p) {
+  constexpr int kCols = 8 * NT + 8;
+  constexpr int G16 = (kCols + 15) / 16;
+  constexpr int kBoxW = 16 * G16;
+  constexpr int kRowBytes = kBoxW * 32;
+  constexpr int kWs = 49 * kCG + kCG;                     // floats per tap buffer
+  extern __shared__ __align__(1024) uint8_t dwm_smem_raw[];
+  uint8_t* smem = dwm_smem_raw + ((1024u - (b200at::smem_u32(dwm_smem_raw) & 1023u)) & 1023u);
+  const uint32_t sa = b200at::smem_u32(smem);
+  const uint32_t so = sa + p.sa_bytes;
+  const uint32_t planes0 = so + p.so_bytes;
+  const uint32_t pbuf = (uint32_t)kCG * p.plane_bytes + 128;                 // bytes per plane buffer
+  uint8_t* tail = smem + p.sa_bytes + p.so_bytes + 2 * (size_t)pbuf;
+  float* ws0 = reinterpret_cast<float*>(tail);            // [2][kWs]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tail + 2 * sizeof(float) * kWs);
+  uint64_t* in_full = &bars[0];
+  uint64_t* add_full = &bars[1];
+  uint64_t* planes_full = &bars[2];                       // [2]
+  uint64_t* planes_done = &bars[4];                       // [2]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, q = lane & 3;
+  const int mi = lane >> 3, r8 = lane & 7;
+  const uint32_t pb = (uint32_t)p.plane_bytes;
+  const uint32_t mat_off = (uint32_t)(32 * (8 * (mi >> 1) + r8) + 16 * ((mi & 1) ^ ((r8 >> 2) & 1)));
+  auto decode = [&](int tile, int& cg, int& n0, int& h0) {
+    cg = tile % p.cgroups;
+    int s = tile / p.cgroups;
+    const int th = s % p.tiles_h;
+    n0 = (s / p.tiles_h) * p.NB; h0 = th * p.TH;
+  };
+  const uint32_t in_bytes = (uint32_t)(p.NB * p.IH) * kRowBytes, add_bytes = (uint32_t)(p.NB * p.TH) * kRowBytes;
+  const int ntiles = (p.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles of this CTA
+  if (tid == 0) {
+    b200at::tma_prefetch_desc(&map_x);
+    b200at::tma_prefetch_desc(&map_y);
+    if (ADD) b200at::tma_prefetch_desc(&map_add);
+    b200at::mbar_init(in_full, 1);
+    b200at::mbar_init(add_full, 1);
+    for (int b = 0; b < 2; ++b) { b200at::mbar_init(&planes_full[b], 8); b200at::mbar_init(&planes_done[b], 8); }
+    b200at::mbar_fence_init();
+    if (ntiles > 0) {
+      int cg, n0, h0;
+      decode(blockIdx.x, cg, n0, h0);
+      b200at::mbar_expect_tx(in_full, in_bytes);
+      b200at::tma_load_4d(&map_x, in_full, smem, cg * kCG, -4, h0 - 3, n0);
+      if (ADD) {
+        b200at::mbar_expect_tx(add_full, add_bytes);
+        b200at::tma_load_4d(&map_add, add_full, smem + p.sa_bytes, cg * kCG, -4, h0, n0);
+      }
+    }
+  }
+  __syncthreads();
+
+  if (warp < 8) {
+    // ================================================================ T group: phase 1 of tile i, phase 3 of tile i - 1
+    auto phase3 = [&](int j) {      // tile index j (of this CTA): planes[j & 1] -> output staging -> TMA store
+      const int tile = (int)blockIdx.x + j * (int)gridDim.x;
+      int cg, n0, h0;
+      decode(tile, cg, n0, h0);
+      const int rows_out_img = min(p.TH, p.H - h0);
+      const int R = p.NB * rows_out_img;
+      const uint32_t planes = planes0 + (j & 1) * pbuf;
+      b200at::mbar_wait(&planes_done[j & 1], (uint32_t)((j >> 1) & 1));
+      if (ADD) b200at::mbar_wait(add_full, (uint32_t)(j & 1));
+      for (int t = warp; t < R * G16; t += 8) {
+        const int r = t / G16, grp = t - r * G16;
+        const int img = MULTI ? r / rows_out_img : 0, hr = r - img * rows_out_img;
+        const uint32_t src = planes + g * pb + (img * p.IH + hr) * p.S + (16 * grp + 2 * q) * 2;
+        uint32_t v[4];
+        v[0] = lds32(src);
+        v[1] = lds32(src + 8 * pb);
+        if (16 * grp + 8 < kCols) { v[2] = lds32(src + 16); v[3] = lds32(src + 8 * pb + 16); }
+        else { v[2] = 0u; v[3] = 0u; }
+        const uint32_t st = so + (img * p.TH + hr) * kRowBytes + grp * 512 + mat_off;
+        if (ADD) {
+          uint32_t u[4];
+          ldsm4_trans(u, st);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) v[i] = add_bf16x2(v[i], u[i]);
+        }
+        stsm4_trans(st, v);
+      }
+      b200at::fence_proxy_async();
+      bar_t_sync();
+      if (tid == 0) {
+        b200at::tma_store_4d(&map_y, smem + p.sa_bytes + 128, cg * kCG, 0, h0, n0);
+        b200at::tma_store_commit();
+        if (ADD && j + 1 < ntiles) {                      // the next tile's residual-gradient tile, once the store has read SO
+          int cg1, n1, h1;
+          decode(tile + (int)gridDim.x, cg1, n1, h1);
+          b200at::tma_store_wait_read();
+          b200at::mbar_expect_tx(add_full, add_bytes);
+          b200at::tma_load_4d(&map_add, add_full, smem + p.sa_bytes, cg1 * kCG, -4, h1, n1);
+        }
+      }
+    };
+    for (int i = 0; i < ntiles; ++i) {
+      const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+      int cg, n0, h0;
+      decode(tile, cg, n0, h0);
+      const int c0 = cg * kCG;
+      const int rows_in = p.NB * p.IH;
+      const uint32_t planes = planes0 + (i & 1) * pbuf;
+      float* ws = ws0 + (i & 1) * kWs;
+      // taps of this channel group into registers (L2 latency under the wait below)
+      float tapv[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int kk = tid + 256 * k;
+        tapv[k] = kk < 49 * kCG ? p.wt[(int64_t)(kk / kCG) * p.C + c0 + (kk % kCG)] : 0.0f;
+      }
+      const float bias_v = (tid < kCG && p.bias) ? p.bias[c0 + tid] : 0.0f;
+      // planes[i & 1] was last read by phase 3 of tile i - 2 (this group, two iterations ago, behind a group barrier)
+      b200at::mbar_wait(in_full, (uint32_t)(i & 1));
+      for (int t = warp; t < rows_in * G16; t += 8) {
+        const int ri = t / G16, grp = t - ri * G16;
+        uint32_t v[4];
+        ldsm4_trans(v, sa + ri * kRowBytes + grp * 512 + mat_off);
+        const uint32_t dst = planes + g * pb + ri * p.S + (16 * grp + 2 * q) * 2;
+        sts32(dst, v[0]);
+        sts32(dst + 8 * pb, v[1]);
+        if (16 * grp + 8 < kCols) {
+          sts32(dst + 16, v[2]);
+          sts32(dst + 8 * pb + 16, v[3]);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int kk = tid + 256 * k;
+        if (kk < 49 * kCG) ws[(kk % kCG) * 49 + kk / kCG] = tapv[k];
+      }
+      if (tid < kCG) ws[49 * kCG + tid] = bias_v;
+      __syncwarp();
+      if (lane == 0) b200at::mbar_arrive(&planes_full[i & 1]);           // release: planes + taps of tile i are complete
+      if (tid == 0) b200at::tma_store_wait_read();                        // the previous store has read the output staging
+      bar_t_sync();                                                       // every T warp is done reading the input staging
+      if (tid == 0 && i + 1 < ntiles) {
+        int cg1, n1, h1;
+        decode(tile + (int)gridDim.x, cg1, n1, h1);
+        b200at::fence_proxy_async();
+        b200at::mbar_expect_tx(in_full, in_bytes);
+        b200at::tma_load_4d(&map_x, in_full, smem, cg1 * kCG, -4, h1 - 3, n1);
+      }
+      if (i > 0) phase3(i - 1);
+    }
+    if (ntiles > 0) phase3(ntiles - 1);
+    if (tid == 0) b200at::tma_store_wait_all();
+  } else {
+    // ================================================================ M group: phase 2, channels 2 (warp - 8), 2 (warp - 8) + 1
+    const int mw = warp - 8;
+    for (int i = 0; i < ntiles; ++i) {
+      const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+      int cg, n0, h0;
+      decode(tile, cg, n0, h0);
+      const int rows_out_img = min(p.TH, p.H - h0);
+      const int R = p.NB * rows_out_img;
+      const uint32_t planes = planes0 + (i & 1) * pbuf;
+      const float* ws = ws0 + (i & 1) * kWs;
+      b200at::mbar_wait(&planes_full[i & 1], (uint32_t)((i >> 1) & 1));
+#pragma unroll 1
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c = 2 * mw + cc;
+        const uint32_t plane = planes + c * pb;
+        uint32_t bfr[7][2];
+        {
+          const int j0 = 2 * q - g - 1;
+          const bool first = j0 >= -1;
+          const int j = first ? j0 : j0 + 8;
+          const float* wc = ws + c * 49;
+#pragma unroll
+          for (int dh = 0; dh < 7; ++dh) {
+            const float w0 = (j >= 0 && j < 7) ? wc[dh * 7 + j] : 0.0f;
+            const float w1 = (j + 1 >= 0 && j + 1 < 7) ? wc[dh * 7 + j + 1] : 0.0f;
+            const uint32_t v = pack_bf16x2(w0, w1);
+            bfr[dh][0] = first ? v : 0u;
+            bfr[dh][1] = first ? 0u : v;
+          }
+        }
+        const float bias = ws[49 * kCG + c];
+        const int mtiles = (R + 15) >> 4;
+#pragma unroll 1
+        for (int t = 0; t < mtiles; ++t) {
+          int r = 16 * t + (mi & 1) * 8 + r8;
+          r = r < R ? r : 0;
+          const int img = MULTI ? r / rows_out_img : 0, hr = r - img * rows_out_img;
+          const uint32_t a_base = plane + (img * p.IH + hr) * p.S + (mi >> 1) * 16;
+          float acc[NT][4];
+#pragma unroll
+          for (int j = 0; j < NT; ++j) { acc[j][0] = bias; acc[j][1] = bias; acc[j][2] = bias; acc[j][3] = bias; }
+#pragma unroll
+          for (int dh = 0; dh < 7; ++dh) {
+            uint32_t a[(NT + 2) / 2][4];
+#pragma unroll
+            for (int cp = 0; cp < (NT + 2) / 2; ++cp) ldsm4(a[cp], a_base + dh * p.S + cp * 32);
+#pragma unroll
+            for (int j = 0; j < NT; ++j) {
+              if ((j & 1) == 0) mma16816(acc[j], a[j / 2][0], a[j / 2][1], a[j / 2][2], a[j / 2][3], bfr[dh][0], bfr[dh][1]);
+              else mma16816(acc[j], a[j / 2][2], a[j / 2][3], a[(j + 1) / 2][0], a[(j + 1) / 2][1], bfr[dh][0], bfr[dh][1]);
+            }
+          }
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            const int ro = 16 * t + g + 8 * half;
+            if (ro < R) {
+              const int im = MULTI ? ro / rows_out_img : 0, ho = ro - im * rows_out_img;
+              const uint32_t dst = plane + (im * p.IH + ho) * p.S + (2 * q + 4) * 2;
+#pragma unroll
+              for (int j = 0; j < NT; ++j) sts32(dst + j * 16, pack_bf16x2(acc[j][2 * half], acc[j][2 * half + 1]));
+            }
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) b200at::mbar_arrive(&planes_done[i & 1]);            // release: the outputs of this warp's channels
+    }
+  }
+}
+
 template <int NT, bool ADD, bool MULTI>
 int launch_one(const CUtensorMap& mx, const CUtensorMap& ma, const CUtensorMap& my, const DwmParams& p, size_t smem, int grid,
                cudaStream_t s) {
+  // two warp groups on two plane buffers when they fit (B200AT_DWM_PP=0: the single-group kernel)
+  static const bool pp_on = [] { const char* e = getenv("B200AT_DWM_PP"); return e == nullptr || e[0] != '0'; }();
+  const size_t smem_pp = 1024 + (size_t)p.sa_bytes + p.so_bytes + 2 * ((size_t)kCG * p.plane_bytes + 128) +
+                         2 * sizeof(float) * (49 * kCG + kCG) + 64;
+  if (pp_on && !MULTI && smem_pp <= 225 * 1024) {     // several images per tile: the single group measured faster (r02n)
+    static b200at::SmemConfig conf_pp;
+    cudaError_t e = b200at::ensure_dynamic_smem(dwconv7_mma_pp_kernel<NT, ADD, MULTI>, (int)smem_pp, conf_pp);
+    if (e != cudaSuccess) return (int)e;
+    dwconv7_mma_pp_kernel<NT, ADD, MULTI><<<grid, kThreads, smem_pp, s>>>(mx, ma, my, p);
+    return (int)cudaGetLastError();
+  }
   static b200at::SmemConfig conf;
   cudaError_t e = b200at::ensure_dynamic_smem(dwconv7_mma_kernel<NT, ADD, MULTI>, (int)smem, conf);
   if (e != cudaSuccess) return (int)e;

@@ -12,8 +12,30 @@
 // 10 FMA-pipe instructions + MUFU.RCP + MUFU.EX2 (the .ftz approx forms: no denormal fix-up code) per GELU, 14 per
 // GELU'.  Error vs double precision: 3.3e-7 / 3.0e-7 absolute (checked over [-12, 12]), far below the 2^-9
 // relative step of the bf16 results.
+//
+// b200at_gelu2 / b200at_gelu_grad2 evaluate two elements with the packed fp32x2 forms (sm_100 FFMA2 / FMUL2 / FADD2):
+// the same operations in the same order on each lane, so the results are bit-identical to the scalar functions, at half
+// the FMA-pipe instructions -- the MUFU pair per element is then what bounds a GELU epilogue.
 #pragma once
 #include <cuda_runtime.h>
+
+__device__ __forceinline__ float2 b200at_ffma2(float2 a, float2 b, float2 c) {
+  unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b),
+                     rc = *reinterpret_cast<unsigned long long*>(&c), rd;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  return *reinterpret_cast<float2*>(&rd);
+}
+__device__ __forceinline__ float2 b200at_fadd2(float2 a, float2 b) {
+  unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b), rd;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  return *reinterpret_cast<float2*>(&rd);
+}
+__device__ __forceinline__ float2 b200at_fmul2(float2 a, float2 b) {
+  unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b), rd;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  return *reinterpret_cast<float2*>(&rd);
+}
+__device__ __forceinline__ float2 b200at_dup2(float x) { return make_float2(x, x); }
 
 __device__ __forceinline__ float b200at_rcp(float x) {
   float y;
@@ -49,4 +71,33 @@ __device__ __forceinline__ float b200at_gelu_grad(float v) {
   const float h = b200at_phi_tail(fabsf(v), &e);
   const float cdf = 0.5f + copysignf(0.5f - h, v);
   return fmaf(v * 0.3989422804014327f, e, cdf);
+}
+
+// ---- two elements at a time (bit-identical to the scalar forms above).  nax = -|v|: the sign flips are folded into the
+// constants, (-|v|)(-k) == |v| k exactly.
+__device__ __forceinline__ float2 b200at_phi_tail2(float2 nax, float2* e) {
+  const float2 xs = b200at_fmul2(nax, b200at_dup2(-0.8493218f));
+  const float2 d = b200at_ffma2(nax, b200at_dup2(-0.23164189f), b200at_dup2(1.0f));
+  const float2 t = make_float2(b200at_rcp(d.x), b200at_rcp(d.y));
+  float2 q = b200at_ffma2(b200at_dup2(0.5307027f), t, b200at_dup2(-0.72657603f));
+  q = b200at_ffma2(q, t, b200at_dup2(0.7107069f));
+  q = b200at_ffma2(q, t, b200at_dup2(-0.14224836f));
+  q = b200at_ffma2(q, t, b200at_dup2(0.1274148f));
+  const float2 x2 = b200at_fmul2(xs, xs);
+  *e = make_float2(b200at_ex2(-x2.x), b200at_ex2(-x2.y));
+  return b200at_fmul2(b200at_fmul2(q, t), *e);
+}
+__device__ __forceinline__ float2 b200at_gelu2(float2 v) {
+  float2 e;
+  const float2 nax = make_float2(-fabsf(v.x), -fabsf(v.y));
+  const float2 h = b200at_phi_tail2(nax, &e);
+  return b200at_ffma2(nax, h, make_float2(fmaxf(v.x, 0.0f), fmaxf(v.y, 0.0f)));
+}
+__device__ __forceinline__ float2 b200at_gelu_grad2(float2 v) {
+  float2 e;
+  const float2 nax = make_float2(-fabsf(v.x), -fabsf(v.y));
+  const float2 h = b200at_phi_tail2(nax, &e);
+  const float2 r = b200at_ffma2(h, b200at_dup2(-1.0f), b200at_dup2(0.5f));        // 0.5 - h, one rounding
+  const float2 cdf = b200at_fadd2(b200at_dup2(0.5f), make_float2(copysignf(r.x, v.x), copysignf(r.y, v.y)));
+  return b200at_ffma2(b200at_fmul2(v, b200at_dup2(0.3989422804014327f)), e, cdf);
 }

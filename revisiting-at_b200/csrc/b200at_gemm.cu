@@ -129,8 +129,6 @@ __device__ __forceinline__ uint4* stage_piece(uint8_t* tile, int row, int piece)
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-__device__ __forceinline__ float gelu_f(float v) { return b200at_gelu(v); }
-__device__ __forceinline__ float gelu_grad_f(float v) { return b200at_gelu_grad(v); }
 __device__ __forceinline__ void unpack8(const uint4& u, float* f) {
   const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
@@ -303,7 +301,10 @@ __global__ void __launch_bounds__(32 * (kEpilogueWarp0 + EW), 1) gemm_kernel(con
               unpack8(__ldg(reinterpret_cast<const uint4*>(p.aux + row_off + col0 + c)), z);
               unpack8(__ldg(reinterpret_cast<const uint4*>(p.aux + row_off + col0 + c + 8)), z + 8);
 #pragma unroll
-              for (int i = 0; i < 16; ++i) g[i] *= gelu_grad_f(z[i]);
+              for (int i = 0; i < 16; i += 2) {
+                const float2 r = b200at_fmul2(make_float2(g[i], g[i + 1]), b200at_gelu_grad2(make_float2(z[i], z[i + 1])));
+                g[i] = r.x; g[i + 1] = r.y;
+              }
             }
           }
         }
@@ -313,7 +314,10 @@ __global__ void __launch_bounds__(32 * (kEpilogueWarp0 + EW), 1) gemm_kernel(con
           bf16* dst = (n_out == 2 && o == 0) ? p.c2 : p.c;
           if (EPI == B200AT_EPI_BIAS_GELU && o == n_out - 1) {
 #pragma unroll
-            for (int i = 0; i < kStripCols; ++i) f[i] = gelu_f(f[i]);
+            for (int i = 0; i < kStripCols; i += 2) {
+              const float2 r = b200at_gelu2(make_float2(f[i], f[i + 1]));
+              f[i] = r.x; f[i + 1] = r.y;
+            }
           }
 #pragma unroll
           for (int c = 0; c < kStripCols; c += 8) {

@@ -426,12 +426,20 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const __grid_constant_
                                  __uint_as_float(bb.x), __uint_as_float(bb.y), __uint_as_float(bb.z), __uint_as_float(bb.w)};
           if (MODE == 0) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) f[i] = b200at_gelu(f[i] + bias[i]);
+            for (int i = 0; i < 8; i += 2) {
+              const float2 g = b200at_gelu2(b200at_fadd2(make_float2(f[i], f[i + 1]), make_float2(bias[i], bias[i + 1])));
+              f[i] = g.x; f[i + 1] = g.y;
+            }
           } else {
             float zf[8];
             unpack8(zq[h], zf);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) f[i] *= b200at_gelu_grad(zf[i] + bias[i]);
+            for (int i = 0; i < 8; i += 2) {
+              const float2 g = b200at_fmul2(make_float2(f[i], f[i + 1]),
+                                            b200at_gelu_grad2(b200at_fadd2(make_float2(zf[i], zf[i + 1]),
+                                                                           make_float2(bias[i], bias[i + 1]))));
+              f[i] = g.x; f[i + 1] = g.y;
+            }
           }
           sts128(prow_a + ((((uint32_t)(pc + h)) ^ swz) << 4), pack8(f));
         }
