@@ -156,6 +156,153 @@ struct GemmParams {
   int block_n, tiles_m, tiles_n;
 };
 
+// ------------------------------------------------------------------------------------------------ GELU / GELU' epilogues
+// The first version of these two epilogues ran the generic strip code above with 64 columns in registers: 34 instructions
+// per element (half of them address arithmetic, re-materialised lane ids and one scalar LDG per bias value) and, for GELU',
+// a row-per-lane read of the saved pre-activation (32 lines touched per instruction, 16 useful bytes each) -- 69 / 87 us at
+// 25088 x 1536 x 384 against 32 + 32 / 33 + 44 us for the plain GEMM followed by the elementwise kernel
+// (profiles/r02_gemm_epilogue_ncu.txt).  This version walks a warp's columns 32 at a time:
+//   aux (GELU': the saved z) comes in as 64-byte row segments, 8 rows per instruction, through the warp's staging tile, and
+//       the loads of the next pass are in flight during the arithmetic of the current one (the first pass of a tile is
+//       requested before the accumulator barrier);
+//   bias sits in shared memory (one broadcast LDS.128 per 4 columns);  the arithmetic is the packed fp32x2 GELU;
+//   every shared-memory access is an explicit ld/st.shared on a 32-bit address computed once per warp.
+constexpr int kPassCols = 32;
+constexpr int kFusedTileBytes = 32 * kPassCols * 2;    // per-warp staging tile: 32 rows x 64 B, pieces XOR-swizzled by (row >> 1) & 3
+constexpr int kMaxBiasCols = 8192;
+
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ float2 bf2_to_f2(uint32_t u) {
+  return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+}
+__device__ __forceinline__ uint32_t f2_to_bf2(float2 v) {
+  const __nv_bfloat162 t = __floats2bfloat162_rn(v.x, v.y);
+  return *reinterpret_cast<const uint32_t*>(&t);
+}
+
+template <int EPI>
+__device__ __forceinline__ void fused_epilogue(const bf16* __restrict__ aux, bf16* __restrict__ c_out, bf16* __restrict__ c2_out,
+                                               int M, int N, int block_n, int tiles_n, int num_tiles, uint32_t tmem_base,
+                                               uint64_t* tfull, uint64_t* tempty, uint32_t tile_a, uint32_t bias_a, int warp,
+                                               int lane) {
+  const int q = warp & 3, sub = (warp - kEpilogueWarp0) >> 2;        // TMEM lane quarter; which 64-column group of each 256
+  const uint32_t row_a = tile_a + (uint32_t)lane * 64u;               // row-per-lane view
+  const uint32_t rsw = (uint32_t)((lane >> 1) & 3);
+  const int lr = lane >> 2, lp = lane & 3;                            // line view: 4 lanes per 64-byte row segment, 8 rows
+  const uint32_t line_a = tile_a + (uint32_t)lr * 64u + (((uint32_t)lp ^ (uint32_t)((lr >> 1) & 3)) << 4);   // + 512 k
+  int it = 0;
+  for (int tile_id = blockIdx.x; tile_id < num_tiles; tile_id += gridDim.x, ++it) {
+    const int tm = tile_id / tiles_n, tn = tile_id - tm * tiles_n;
+    const int acc = it & 1;
+    const uint32_t acc_phase = (it >> 1) & 1;
+    const int row0 = tm * kBlockM + q * 32;
+    const int ncol0 = tn * block_n;
+    const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * block_n);
+    const int64_t line_off = (int64_t)(row0 + lr) * N + ncol0 + lp * 8;
+    const int rows_left = M - row0 - lr;                              // line k is inside the matrix when 8 k < rows_left
+    auto pass_col = [&](int e) { return sub * 64 + (e >> 1) * 256 + (e & 1) * kPassCols; };
+    auto pass_width = [&](int e) {
+      const int c = pass_col(e);
+      int w = block_n - c;
+      const int wn = N - ncol0 - c;
+      w = w < wn ? w : wn;
+      return w < kPassCols ? w : kPassCols;
+    };
+    uint4 zpre[4];
+    auto load_aux = [&](int e) {
+      const int c = pass_col(e), w = pass_width(e);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        zpre[k] = make_uint4(0u, 0u, 0u, 0u);
+        if (lp * 8 < w && 8 * k < rows_left)
+          zpre[k] = __ldg(reinterpret_cast<const uint4*>(aux + line_off + (int64_t)(8 * k) * N + c));
+      }
+    };
+    auto store_tile = [&](bf16* __restrict__ dst, int c, int w, const uint4* o) {      // rows per lane in, 64-byte segments out
+#pragma unroll
+      for (int j = 0; j < 4; ++j) sts128(row_a + (((uint32_t)j ^ rsw) << 4), o[j]);
+      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint4 t = lds128(line_a + 512u * k);
+        if (lp * 8 < w && 8 * k < rows_left) *reinterpret_cast<uint4*>(dst + line_off + (int64_t)(8 * k) * N + c) = t;
+      }
+      __syncwarp();
+    };
+    if (EPI == B200AT_EPI_GELU_GRAD) load_aux(0);
+    mbar_wait(&tfull[acc], acc_phase);
+    tc_fence_after();
+    for (int e = 0; pass_col(e) < block_n; ++e) {
+      const int c = pass_col(e), w = pass_width(e);
+      if (w <= 0) break;
+      uint32_t v[32];
+      tmem_ld16(t_row + (uint32_t)c, v);
+      if (w > 16) tmem_ld16(t_row + (uint32_t)(c + 16), v + 16);
+      uint4 zrow[4];
+      if (EPI == B200AT_EPI_GELU_GRAD) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) sts128(line_a + 512u * k, zpre[k]);
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) zrow[j] = lds128(row_a + (((uint32_t)j ^ rsw) << 4));
+        __syncwarp();
+        if (pass_col(e + 1) < block_n) load_aux(e + 1);
+      }
+      tmem_ld_wait();
+      uint4 o[4];
+      if (EPI == B200AT_EPI_GELU_GRAD) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t zw[4] = {zrow[j].x, zrow[j].y, zrow[j].z, zrow[j].w};
+          uint32_t ow[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float2 g = make_float2(__uint_as_float(v[8 * j + 2 * i]), __uint_as_float(v[8 * j + 2 * i + 1]));
+            ow[i] = f2_to_bf2(b200at_fmul2(g, b200at_gelu_grad2(bf2_to_f2(zw[i]))));
+          }
+          o[j] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+        }
+        store_tile(c_out, c, w, o);
+      } else {
+        float2 f[16];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t ba = bias_a + (uint32_t)((ncol0 + c + 8 * j) * 4);
+          const uint4 b0 = lds128(ba), b1 = lds128(ba + 16);
+          const uint32_t bw[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+          uint32_t ow[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            f[4 * j + i] = b200at_fadd2(make_float2(__uint_as_float(v[8 * j + 2 * i]), __uint_as_float(v[8 * j + 2 * i + 1])),
+                                        make_float2(__uint_as_float(bw[2 * i]), __uint_as_float(bw[2 * i + 1])));
+            ow[i] = f2_to_bf2(f[4 * j + i]);
+          }
+          o[j] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+        }
+        if (c2_out != nullptr) store_tile(c2_out, c, w, o);                 // the pre-activation (bias included)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint32_t ow[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) ow[i] = f2_to_bf2(b200at_gelu2(f[4 * j + i]));
+          o[j] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+        }
+        store_tile(c_out, c, w, o);
+      }
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&tempty[acc]);
+  }
+}
+
 template <int EPI, int EW>
 __global__ void __launch_bounds__(32 * (kEpilogueWarp0 + EW), 1) gemm_kernel(const __grid_constant__ CUtensorMap map_a,
                                                               const __grid_constant__ CUtensorMap map_b,
@@ -173,7 +320,8 @@ __global__ void __launch_bounds__(32 * (kEpilogueWarp0 + EW), 1) gemm_kernel(con
   uint64_t* tfull = bars + 2 * kStages;    // [2]
   uint64_t* tempty = bars + 2 * kStages + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
-  uint8_t* staging = smem + kStages * stage_bytes + 256;   // [EW][kStageTileBytes]
+  uint8_t* staging = smem + kStages * stage_bytes + 256;   // [EW][kStageTileBytes]  (EW == 16: [EW][kFusedTileBytes], then bias)
+  float* sbias = reinterpret_cast<float*>(staging + EW * kFusedTileBytes);   // EW == 16 only: [tiles_n * block_n]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_k = (p.K + kBlockK - 1) / kBlockK;
@@ -194,6 +342,10 @@ __global__ void __launch_bounds__(32 * (kEpilogueWarp0 + EW), 1) gemm_kernel(con
                  "r"(tmem_cols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (EW == 16 && EPI == B200AT_EPI_BIAS_GELU) {
+    const int padded = p.tiles_n * p.block_n;
+    for (int i = threadIdx.x; i < padded; i += blockDim.x) sbias[i] = (p.bias != nullptr && i < p.N) ? p.bias[i] : 0.0f;
   }
   tc_fence_before();
   __syncthreads();
@@ -247,6 +399,9 @@ __global__ void __launch_bounds__(32 * (kEpilogueWarp0 + EW), 1) gemm_kernel(con
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
     }
+  } else if (warp >= kEpilogueWarp0 && EW == 16) {
+    fused_epilogue<EPI>(p.aux, p.c, p.c2, p.M, p.N, p.block_n, p.tiles_n, num_tiles, tmem_base, tfull, tempty,
+                        smem_u32(staging) + (uint32_t)((warp - kEpilogueWarp0) * kFusedTileBytes), smem_u32(sbias), warp, lane);
   } else if (warp >= kEpilogueWarp0) {
     // ------------------------------------------------------------------ epilogue (TMEM -> regs -> smem -> global)
     const int q = warp & 3;                            // TMEM lane quarter this warp may access
@@ -390,7 +545,9 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, in
   constexpr int EW = (EPI == B200AT_EPI_BIAS_GELU || EPI == B200AT_EPI_GELU_GRAD) ? 16 : 8;
   constexpr int kStages = EW > 8 ? 3 : 4;
   const size_t smem = 1024 + (size_t)kStages * (kBlockM * kBlockK * 2 + (size_t)p.block_n * kBlockK * 2) + 256 +
-                      (size_t)EW * kStageTileBytes;
+                      (EW == 16 ? (size_t)EW * kFusedTileBytes + sizeof(float) * (size_t)p.tiles_n * p.block_n
+                                : (size_t)EW * kStageTileBytes);
+  if (EW == 16 && (int64_t)p.tiles_n * p.block_n > kMaxBiasCols) return (int)cudaErrorInvalidValue;
   static b200at::SmemConfig configured;
   cudaError_t e = b200at::ensure_dynamic_smem(gemm_kernel<EPI, EW>, 227 * 1024, configured);
   if (e != cudaSuccess) return (int)e;

@@ -175,11 +175,11 @@ def _f32(t):
 #   'dgrad1'    d(t2) = dz W1                     (no epilogue; same speed as cuBLAS, one library call less)
 #   'fc1'       pwconv1 forward, plain (bias rides in the GELU kernel): 3-9 % faster than cuBLAS at these shapes
 #   'dgrad2'    da = dout (gamma W2)              (plain; same shapes as 'fc1')
-#   'gelu'      pwconv1 forward with bias + GELU fused (+ pre-activation saved)   [slower: epilogue-bound]
-#   'gelu_grad' dz = (dout W2g) * GELU'(z)        fused                           [slower: epilogue-bound]
+#   'gelu'      pwconv1 forward with bias + GELU fused (+ pre-activation saved): 50 vs 32 + 33 us at 25088 x 1536 x 384
+#   'gelu_grad' dz = (dout W2g) * GELU'(z) fused: 55 vs 33 + 44 us            (profiles/r02_ops_bench_gemm_epilogues.txt)
 #   'mlp'       the whole MLP (pwconv1 -> GELU -> pwconv2 + scale + bias + residual, and its input gradient) as ONE
 #               kernel per direction with the 4C hidden kept on chip (csrc/b200at_mlp.cu), for C in {96, 128, 192}
-TCGEN05 = set(filter(None, os.environ.get('B200AT_TCGEN05', 'residual,dgrad1,fc1,dgrad2,mlp').split(',')))
+TCGEN05 = set(filter(None, os.environ.get('B200AT_TCGEN05', 'residual,dgrad1,fc1,dgrad2,mlp,gelu,gelu_grad').split(',')))
 _MLP_OK = {}
 
 
@@ -634,9 +634,14 @@ class _ViTBlock(Function):
         rstd2 = torch.empty_like(mean1)
         _abi.ln_fwd(x1, n2wf, n2bf, t2, mean2, rstd2, 1e-6, False)
         b1f = _f32(b1)
-        z = _gemm(t2, P['w1'])                                          # bias added inside the GELU kernels
-        a = torch.empty_like(z)
-        _abi.bias_gelu_fwd(z, b1f, a)
+        if 'gelu' in TCGEN05:
+            z = torch.empty(M, P['w1'].shape[0], device=x.device, dtype=BF16)   # pre-activation INCLUDING the bias
+            a = _gemm(t2, P['w1'], _abi.EPI_BIAS_GELU, bias=b1f, c2=z)
+            b1f = torch.zeros_like(b1f)                                 # what the backward adds to the saved z
+        else:
+            z = _gemm(t2, P['w1'])                                      # bias added inside the GELU kernels
+            a = torch.empty_like(z)
+            _abi.bias_gelu_fwd(z, b1f, a)
         out = _gemm(a, P['w2'], _abi.EPI_RESIDUAL, bias=_f32(b2), aux=x1)
         ctx.param_grads, ctx.prep, ctx.heads, ctx.scale = pg, P, heads, scale
         keep = (x2, mean1, rstd1, qkv, o, lse, x1, mean2, rstd2, z, n1wf, n1bf, n2wf, n2bf, b1f)
@@ -654,10 +659,15 @@ class _ViTBlock(Function):
         pg = ctx.param_grads and any(ctx.needs_input_grad[1:13])
         d2 = dout.contiguous().view(M, D)
         # ---- MLP branch
-        da = _gemm(d2, P['w2_t'])                                       # [M,4D]
-        dz = torch.empty_like(da)
         db1 = torch.zeros(4 * D, device=dev, dtype=torch.float32) if pg else None
-        _abi.bias_gelu_bwd(da, z, b1f, dz, db1)
+        if 'gelu' in TCGEN05 and 'gelu_grad' in TCGEN05:                # the saved z includes the bias
+            dz = _gemm(d2, P['w2_t'], _abi.EPI_GELU_GRAD, aux=z)        # [M,4D]
+            if pg:
+                _abi.colsum_bf16(dz, db1)
+        else:
+            da = _gemm(d2, P['w2_t'])
+            dz = torch.empty_like(da)
+            _abi.bias_gelu_bwd(da, z, b1f, dz, db1)
         dt2 = _gemm(dz, P['w1_t'])                                      # [M,D]
         dn2w = torch.zeros(D, device=dev, dtype=torch.float32) if pg else None
         dn2b = torch.zeros(D, device=dev, dtype=torch.float32) if pg else None

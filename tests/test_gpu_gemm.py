@@ -64,3 +64,27 @@ def test_gemm_back_to_back_tiles_reuse_tmem(abi, cuda_dev):
     c = torch.empty(M, N, device=cuda_dev, dtype=BF16)
     abi.gemm_bf16(a, b, c, abi.EPI_NONE)
     _check(c, a.float() @ b.float().t(), 'multi-tile')
+
+
+def test_gemm_gelu_epilogues_over_many_tiles(abi, cuda_dev):
+    """the GELU / GELU' epilogues (16 epilogue warps, 32-column passes, aux prefetched one pass ahead) on more output tiles
+    than SMs, a ragged last row tile, and without the optional pre-activation output"""
+    M, N, K = 148 * 128 * 2 + 77, 512, 192
+    g = torch.Generator(device='cuda').manual_seed(11)
+    a = torch.randn(M, K, generator=g, device=cuda_dev).to(BF16)
+    b = (torch.randn(N, K, generator=g, device=cuda_dev) * K ** -0.5).to(BF16)
+    bias = torch.randn(N, generator=g, device=cuda_dev)
+    aux = torch.randn(M, N, generator=g, device=cuda_dev).to(BF16)
+    acc = a.float() @ b.float().t()
+    c = torch.full((M, N), float('nan'), device=cuda_dev, dtype=BF16)
+    abi.gemm_bf16(a, b, c, abi.EPI_BIAS_GELU, bias=bias)
+    _check(c, F.gelu(acc + bias), 'bias_gelu without c2')
+    c2 = torch.full((M, N), float('nan'), device=cuda_dev, dtype=BF16)
+    abi.gemm_bf16(a, b, c, abi.EPI_BIAS_GELU, bias=bias, c2=c2)
+    _check(c2, acc + bias, 'pre-activation')
+    _check(c, F.gelu(acc + bias), 'bias_gelu')
+    c.fill_(float('nan'))
+    abi.gemm_bf16(a, b, c, abi.EPI_GELU_GRAD, aux=aux)
+    z = aux.float().requires_grad_()
+    (gp,) = torch.autograd.grad(F.gelu(z).sum(), z)
+    _check(c, acc * gp, 'gelu_grad')
