@@ -1,6 +1,8 @@
 """Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list: time share per kernel name.
 
-    python profiles/summarize_launches.py gpurun_out/rXX_launches.csv [--top 40] > profiles/rXX_launches_summary.txt
+    python profiles/summarize_launches.py gpurun_out/rXX_launches.csv [--top 40] [--rows A:B] > profiles/rXX_launches_summary.txt
+
+--rows A:B keeps launches A..B-1 of the list (one step: from after one optimizer launch group to the end of the next).
 """
 import collections
 import csv
@@ -15,7 +17,12 @@ def main():
         lines = [l for l in f if not l.startswith('==')]
     agg = collections.defaultdict(lambda: [0, 0.0])
     tot = 0.0
-    for row in csv.DictReader(lines):
+    rows = list(csv.DictReader(lines))
+    if '--rows' in sys.argv:
+        a, b = sys.argv[sys.argv.index('--rows') + 1].split(':')
+        rows = rows[int(a):int(b)]
+        path = f'{path} (launches {a}..{int(b) - 1})'
+    for row in rows:
         try:
             v = float(row['Metric Value'].replace(',', ''))
         except (KeyError, ValueError):
