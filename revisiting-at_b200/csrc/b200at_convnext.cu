@@ -54,6 +54,7 @@ __device__ __forceinline__ uint2 pack4(const float* f) {
 // A group of G lanes (4/8/16/32) owns one pixel row of C channels; each lane holds VPL 8-byte vectors
 // (4 bf16) in registers, so a warp works on 32/G rows at once (small C: more rows in flight per warp).
 constexpr int kLnThreads = 256;
+constexpr int kLnMaxVec = 12 * 32;        // float4 groups of the widest row the plain LayerNorm kernels take (C <= 1536)
 
 template <int G>
 __device__ __forceinline__ float group_sum(float v) {
@@ -83,17 +84,16 @@ __global__ void __launch_bounds__(kLnThreads) ln_fwd_kernel(const bf16* __restri
   const int gl = threadIdx.x % G;                       // lane within the row group
   const int nv = C >> 2;
   constexpr int kRows = kLnThreads / G;                 // rows per CTA iteration
-  float wr[VPL][4], br[VPL][4], pbr[VPL][4];
-#pragma unroll
-  for (int j = 0; j < VPL; ++j) {
-    const int v = gl + G * j;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      wr[j][k] = v < nv ? w[v * 4 + k] : 0.f;
-      br[j][k] = v < nv ? b[v * 4 + k] : 0.f;
-      pbr[j][k] = (pre_bias && v < nv) ? pre_bias[v * 4 + k] : 0.f;
-    }
+  // weight, bias and the optional pre-bias live in shared memory, not in 12 VPL registers per thread: at C = 384 / 768 the
+  // register form ran 24 / 16 warps per SM (80 / 128 registers), too few loads in flight for the small maps of stages 2-3
+  __shared__ float4 sw4[kLnMaxVec], sb4[kLnMaxVec], spb4[kLnMaxVec];
+  const bool has_pb = pre_bias != nullptr;
+  for (int c = threadIdx.x; c < C; c += kLnThreads) {
+    reinterpret_cast<float*>(sw4)[c] = w[c];
+    reinterpret_cast<float*>(sb4)[c] = b[c];
+    if (has_pb) reinterpret_cast<float*>(spb4)[c] = pre_bias[c];
   }
+  __syncthreads();
   const float inv_c = 1.0f / (float)C;
   const int64_t rows_pad = (M + kRows - 1) / kRows * kRows;   // keep whole warps in the loop (shuffles)
   for (int64_t row = (int64_t)blockIdx.x * kRows + threadIdx.x / G; row < rows_pad; row += (int64_t)gridDim.x * kRows) {
@@ -106,8 +106,10 @@ __global__ void __launch_bounds__(kLnThreads) ln_fwd_kernel(const bf16* __restri
       const int v = gl + G * j;
       if (live && v < nv) {
         unpack4(__ldcs(xr + v), f[j]);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) f[j][k] += pbr[j][k];
+        if (has_pb) {
+          const float4 pb = spb4[v];
+          f[j][0] += pb.x; f[j][1] += pb.y; f[j][2] += pb.z; f[j][3] += pb.w;
+        }
         s += (f[j][0] + f[j][1]) + (f[j][2] + f[j][3]);
       } else {
         f[j][0] = f[j][1] = f[j][2] = f[j][3] = 0.f;
@@ -131,9 +133,11 @@ __global__ void __launch_bounds__(kLnThreads) ln_fwd_kernel(const bf16* __restri
       const int v = gl + G * j;
       if (v < nv) {
         float o[4];
+        const float4 w4 = sw4[v], b4 = sb4[v];
+        const float wv[4] = {w4.x, w4.y, w4.z, w4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          o[k] = (f[j][k] - mu) * rs * wr[j][k] + br[j][k];
+          o[k] = (f[j][k] - mu) * rs * wv[k] + bv[k];
           if (GELU) o[k] = gelu_f(o[k]);
         }
         yr[v] = pack4(o);
@@ -156,18 +160,20 @@ __global__ void __launch_bounds__(kLnThreads) ln_bwd_kernel(const bf16* __restri
   const int gl = threadIdx.x % G;
   const int nv = C >> 2;
   constexpr int kRows = kLnThreads / G;
-  float wr[VPL][4], br[VPL][4], aw[VPL][4], ab[VPL][4], pbr[VPL][4];
+  float aw[VPL][4], ab[VPL][4];
 #pragma unroll
   for (int j = 0; j < VPL; ++j) {
-    const int v = gl + G * j;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      wr[j][k] = v < nv ? w[v * 4 + k] : 0.f;
-      br[j][k] = (GELU && v < nv) ? b[v * 4 + k] : 0.f;
-      pbr[j][k] = (pre_bias && v < nv) ? pre_bias[v * 4 + k] : 0.f;
-      aw[j][k] = 0.f; ab[j][k] = 0.f;
-    }
+    for (int k = 0; k < 4; ++k) { aw[j][k] = 0.f; ab[j][k] = 0.f; }
   }
+  __shared__ float4 sw4[kLnMaxVec], sb4[kLnMaxVec], spb4[kLnMaxVec];   // see ln_fwd_kernel
+  const bool has_pb = pre_bias != nullptr;
+  for (int c = threadIdx.x; c < C; c += kLnThreads) {
+    reinterpret_cast<float*>(sw4)[c] = w[c];
+    if (GELU) reinterpret_cast<float*>(sb4)[c] = b[c];
+    if (has_pb) reinterpret_cast<float*>(spb4)[c] = pre_bias[c];
+  }
+  if (!PGRAD) __syncthreads();
   if (PGRAD) {
     for (int c = threadIdx.x; c < 2 * C; c += kLnThreads) red[c] = 0.f;
     __syncthreads();
@@ -188,13 +194,18 @@ __global__ void __launch_bounds__(kLnThreads) ln_bwd_kernel(const bf16* __restri
         float xv[4], dv[4];
         unpack4(__ldcs(xr + v), xv);
         unpack4(__ldcs(gr + v), dv);
+        const float4 w4 = sw4[v];
+        const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+        float bv[4] = {0.f, 0.f, 0.f, 0.f}, pv[4] = {0.f, 0.f, 0.f, 0.f};
+        if (GELU) { const float4 b4 = sb4[v]; bv[0] = b4.x; bv[1] = b4.y; bv[2] = b4.z; bv[3] = b4.w; }
+        if (has_pb) { const float4 p4 = spb4[v]; pv[0] = p4.x; pv[1] = p4.y; pv[2] = p4.z; pv[3] = p4.w; }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          xh[j][k] = ((xv[k] + pbr[j][k]) - mu) * rs;
+          xh[j][k] = ((xv[k] + pv[k]) - mu) * rs;
           float d = dv[k];
-          if (GELU) d *= gelu_grad_f(xh[j][k] * wr[j][k] + br[j][k]);
+          if (GELU) d *= gelu_grad_f(xh[j][k] * wv[k] + bv[k]);
           if (PGRAD) { aw[j][k] += d * xh[j][k]; ab[j][k] += d; }
-          g[j][k] = d * wr[j][k];
+          g[j][k] = d * wv[k];
           s1 += g[j][k];
           s2 += g[j][k] * xh[j][k];
         }
@@ -1029,7 +1040,7 @@ inline void ln_shape(int nv, int& G, int& VPL) {
 inline int ln_grid(int64_t M, int G) {
   const int rows = kLnThreads / G;
   int64_t g = (M + rows - 1) / rows;
-  const int64_t cap = 148 * 8;
+  const int64_t cap = 148 * 4;          // one resident wave of the <= 64-register forms (weights in shared memory)
   return (int)(g < cap ? (g < 1 ? 1 : g) : cap);
 }
 
