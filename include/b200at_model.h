@@ -112,6 +112,16 @@ int b200at_stem0_bwd_input(const void* dy, const float* x, const float* mean3, c
 int b200at_gemm_bf16(const void* a, const void* b, void* c, void* c2, const void* aux, const float* bias,
                      int64_t M, int64_t N, int64_t K, int epilogue, void* stream);
 
+/* Conv2d(kernel 3, stride 2, padding 1) WITHOUT bias on NHWC bf16 input -- the second convolution of the CvSt stems
+ * (utils_architecture.py:205-211 ConvBlock1: conv -> LayerNorm -> GELU; the bias rides in b200at_ln_fwd_bias) -- as an
+ * implicit GEMM on the tcgen05 kernel: M = output pixels in tiles of whole output rows, N = Cout, K = 9 taps x 64
+ * channels; the A tile of a tap is ONE TMA box of the input with element stride 2 along W and H (zero fill = padding
+ * ring and the channels >= Cin).  x [B][H][W][Cin], y [B][H/2][W/2][Cout] bf16; wk [Cout][9*64] bf16 with
+ * wk[co][(kh*3+kw)*64 + ci] = w[co][ci][kh][kw], zero for ci >= Cin.  H, W even, Cin % 8 == 0, Cin <= 64, Cout % 16 == 0,
+ * W/2 <= 128.  Returns -1 (and launches nothing) for a shape it does not take. */
+int b200at_conv3x3s2_fwd(const void* x, const void* wk, void* y, int64_t B, int64_t H, int64_t W, int64_t Cin,
+                         int64_t Cout, void* stream);
+
 /* Kernel-side copies of one ConvNeXt block's MLP weights, rebuilt once per optimiser step (models/convnext.py:42-49 with
  * the layer scale `gamma` folded into pwconv2): w1b = bf16(W1) [4C][C], w1t = w1b^T [C][4C], w2g = bf16(gamma[:,None] W2)
  * [C][4C], w2gt = w2g^T [4C][C] (the four operands b200at_mlp_fused / b200at_gemm_bf16 take in the two directions) and

@@ -14,6 +14,7 @@ import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
+import torch.nn.functional as F  # noqa: E402
 import revisiting_at_b200  # noqa: E402,F401
 from revisiting_at_b200 import _abi  # noqa: E402
 
@@ -131,6 +132,20 @@ def main():
     timeit(f'stem0_bwd_input {H // 2}x{H // 2}x{C0} -> 3x{H}x{H}',
            lambda: _abi.stem0_bwd_input(dy, x, mean3, std3, wk, cb, lw, lb, dx), 8. * x.numel() + 2. * npx * C0,
            fma=2 * 27. * C0 * npx)
+
+    # second stem convolution (3x3 s2, 48 -> 96 at 112 x 112): implicit GEMM on the tcgen05 kernel vs the library convolution
+    from revisiting_at_b200 import ops as _ops
+    Hs, Ci, Co = 112, 48, 96
+    xs = rnd(B, Hs, Hs, Ci)
+    cw = torch.randn(Co, Ci, 3, 3, generator=g, device=dev) * 0.05
+    wk2 = _ops._conv3x3s2_wk(cw)
+    ys = torch.empty(B, Hs // 2, Hs // 2, Co, device=dev, dtype=BF16)
+    cwb = cw.to(BF16).contiguous(memory_format=torch.channels_last)
+    xs_nchw = xs.permute(0, 3, 1, 2)
+    npo = B * (Hs // 2) ** 2
+    fl2 = 2. * npo * Co * 9 * Ci
+    timeit(f'conv3x3s2 implicit GEMM {Hs}x{Hs}x{Ci} -> {Co}', lambda: _abi.conv3x3s2_fwd(xs, wk2, ys), 2. * xs.numel() + 2. * npo * Co, fl2)
+    timeit(f'conv3x3s2 library       {Hs}x{Hs}x{Ci} -> {Co}', lambda: F.conv2d(xs_nchw, cwb, None, stride=2, padding=1), 2. * xs.numel() + 2. * npo * Co, fl2)
 
     if not a.once:
         print(f'{"kernel":58s} {"us":>9} {"GB/s alg":>9} {"TFLOP/s":>8} {"TFMA/s":>7}')

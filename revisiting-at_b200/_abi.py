@@ -105,6 +105,7 @@ def _declare(L):
         'b200at_dwconv7_fwd': [P, P, P, P, P, I64, I64, I64, I64, P],
         'b200at_dwconv7_wgrad': [P, P, P, P, I64, I64, I64, I64, P],
         'b200at_gemm_bf16': [P, P, P, P, P, P, I64, I64, I64, I, P],
+        'b200at_conv3x3s2_fwd': [P, P, P, I64, I64, I64, I64, I64, P],
         'b200at_mlp_fused_supported': [I64],
         'b200at_mlp_fused': [P, P, P, P, P, P, P, P, P, I64, I64, I, P],
         'b200at_normalize_nhwc_bf16': [P, P, P, P, I64, I64, I64, P],
@@ -506,6 +507,21 @@ def gemm_bf16(a, b, c, epilogue=EPI_NONE, bias=None, aux=None, c2=None):
                                       _act(c2, 'c2') if c2 is not None else c_void_p(0),
                                       _act(aux, 'aux') if aux is not None else c_void_p(0),
                                       _par(bias, 'bias', N), M, N, K, epilogue, _stream()), 'gemm_bf16')
+
+
+def conv3x3s2_fwd(x, wk, y):
+    """y[B,H/2,W/2,Co] = conv3x3 stride 2 pad 1 of x[B,H,W,Ci] (NHWC bf16, no bias) as an implicit GEMM on the tcgen05 kernel
+    (include/b200at_model.h: b200at_conv3x3s2_fwd).  wk [Co, 9*64] bf16.  Returns False when the kernel does not take the shape."""
+    B, H, W, Ci = x.shape
+    Co = wk.shape[0]
+    if tuple(wk.shape) != (Co, 576) or tuple(y.shape) != (B, H // 2, W // 2, Co):
+        raise B200atError(f'conv3x3s2 shapes: x {tuple(x.shape)} wk {tuple(wk.shape)} y {tuple(y.shape)}')
+    with _Timed('conv3x3s2_fwd'):
+        rc = lib().b200at_conv3x3s2_fwd(_act(x, 'x'), _act(wk, 'wk'), _act(y, 'y'), B, H, W, Ci, Co, _stream())
+    if rc == -1:
+        return False
+    _check(rc, 'conv3x3s2_fwd')
+    return True
 
 
 def mlp_fused_supported(C):

@@ -70,6 +70,13 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile(
@@ -154,6 +161,12 @@ struct GemmParams {
   const float* bias;  // [N] or null
   int M, N, K;
   int block_n, tiles_m, tiles_n;
+  int tile_rows;      // output rows an M tile really holds (128; the implicit-GEMM convolution: whole output image rows)
+  // implicit GEMM of a 3x3 stride-2 pad-1 convolution on NHWC input (b200at_conv3x3s2_fwd): k-block kb = tap (kh, kw), the A
+  // tile of tile tm is the TMA box {64 channels, conv_ow pixels at stride 2, conv_rows rows at stride 2} at (kw - 1, 2 oh0 + kh - 1)
+  int conv;           // 0: plain GEMM
+  int conv_rows, conv_tiles_per_img;
+  uint32_t conv_a_bytes;
 };
 
 // ------------------------------------------------------------------------------------------------ GELU / GELU' epilogues
@@ -303,7 +316,7 @@ __device__ __forceinline__ void fused_epilogue(const bf16* __restrict__ aux, bf1
   }
 }
 
-template <int EPI, int EW>
+template <int EPI, int EW, bool CONV = false>
 __global__ void __launch_bounds__(32 * (kEpilogueWarp0 + EW), 1) gemm_kernel(const __grid_constant__ CUtensorMap map_a,
                                                               const __grid_constant__ CUtensorMap map_b,
                                                               const GemmParams p) {
@@ -312,15 +325,20 @@ __global__ void __launch_bounds__(32 * (kEpilogueWarp0 + EW), 1) gemm_kernel(con
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t a_bytes = kBlockM * kBlockK * 2;
   const uint32_t b_bytes = (uint32_t)p.block_n * kBlockK * 2;
-  const uint32_t stage_bytes = a_bytes + b_bytes;
-  constexpr int kStages = EW > 8 ? 3 : 4;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * stage_bytes);
+  // CONV: the whole weight matrix (9 k-blocks) stays in shared memory behind the A ring -- re-fetching 110 KB of weights for
+  // every 112-pixel tile made the kernel L2-bandwidth-bound (839 MB of L2 reads, 91 us at 112 x 112 x 48 -> 96, batch 128)
+  const uint32_t stage_bytes = CONV ? a_bytes : a_bytes + b_bytes;
+  constexpr int kStages = CONV ? 5 : (EW > 8 ? 3 : 4);
+  uint8_t* wres = smem + kStages * stage_bytes;                        // CONV: [num_k][b_bytes]
+  const uint32_t wres_bytes = CONV ? (uint32_t)((p.K + kBlockK - 1) / kBlockK) * b_bytes : 0u;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * stage_bytes + wres_bytes);
   uint64_t* full = bars;                   // [kStages]
   uint64_t* empty = bars + kStages;        // [kStages]
   uint64_t* tfull = bars + 2 * kStages;    // [2]
   uint64_t* tempty = bars + 2 * kStages + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
-  uint8_t* staging = smem + kStages * stage_bytes + 256;   // [EW][kStageTileBytes]  (EW == 16: [EW][kFusedTileBytes], then bias)
+  uint64_t* wfull = bars + 2 * kStages + 5;   // CONV: the resident weights have landed
+  uint8_t* staging = smem + kStages * stage_bytes + wres_bytes + 256;   // [EW][kStageTileBytes]  (EW == 16: [EW][kFusedTileBytes], then bias)
   float* sbias = reinterpret_cast<float*>(staging + EW * kFusedTileBytes);   // EW == 16 only: [tiles_n * block_n]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -335,6 +353,7 @@ __global__ void __launch_bounds__(32 * (kEpilogueWarp0 + EW), 1) gemm_kernel(con
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], EW); }
+    if (CONV) mbar_init(wfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -357,14 +376,25 @@ __global__ void __launch_bounds__(32 * (kEpilogueWarp0 + EW), 1) gemm_kernel(con
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
+      if (CONV) {                                  // tiles_n == 1: one weight matrix for every tile
+        mbar_expect_tx(wfull, wres_bytes);
+        for (int kb = 0; kb < num_k; ++kb) tma_load_2d(&map_b, wfull, wres + kb * b_bytes, kb * kBlockK, 0);
+      }
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int tm = tile / p.tiles_n, tn = tile % p.tiles_n;
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sa = smem + stage * stage_bytes;
-          mbar_expect_tx(&full[stage], stage_bytes);
-          tma_load_2d(&map_a, &full[stage], sa, kb * kBlockK, tm * kBlockM);
-          tma_load_2d(&map_b, &full[stage], sa + a_bytes, kb * kBlockK, tn * p.block_n);
+          if (CONV) {
+            const int img = tm / p.conv_tiles_per_img, oh0 = (tm - img * p.conv_tiles_per_img) * p.conv_rows;
+            const int kh = kb / 3, kw = kb - 3 * kh;
+            mbar_expect_tx(&full[stage], p.conv_a_bytes);
+            tma_load_4d(&map_a, &full[stage], sa, 0, kw - 1, 2 * oh0 + kh - 1, img);
+          } else {
+            mbar_expect_tx(&full[stage], stage_bytes);
+            tma_load_2d(&map_a, &full[stage], sa, kb * kBlockK, tm * kBlockM);
+            tma_load_2d(&map_b, &full[stage], sa + a_bytes, kb * kBlockK, tn * p.block_n);
+          }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -375,6 +405,7 @@ __global__ void __launch_bounds__(32 * (kEpilogueWarp0 + EW), 1) gemm_kernel(con
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
+    if (CONV) mbar_wait(wfull, 0);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
@@ -386,7 +417,7 @@ __global__ void __launch_bounds__(32 * (kEpilogueWarp0 + EW), 1) gemm_kernel(con
         tc_fence_after();
         if (elect_one()) {
           const uint8_t* sa = smem + stage * stage_bytes;
-          const uint64_t da = make_desc(sa), db = make_desc(sa + a_bytes);
+          const uint64_t da = make_desc(sa), db = make_desc(CONV ? wres + kb * b_bytes : sa + a_bytes);
 #pragma unroll
           for (int k = 0; k < kBlockK / kUmmaK; ++k) {
             // advance 32 B along K inside the 128 B swizzle atom: +2 in the (addr >> 4) field
@@ -414,9 +445,9 @@ __global__ void __launch_bounds__(32 * (kEpilogueWarp0 + EW), 1) gemm_kernel(con
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
-      const int row0 = tm * kBlockM + q * 32;           // first row of this warp's quarter
+      const int row0 = tm * p.tile_rows + q * 32;       // first row of this warp's quarter
       const int row = row0 + lane;
-      const bool row_ok = row < p.M;
+      const bool row_ok = q * 32 + lane < p.tile_rows && row < p.M;
       const int64_t row_off = (int64_t)row * p.N;
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.block_n);
       for (int s0 = half * kStripCols; s0 < p.block_n; s0 += (EW / 4) * kStripCols) {
@@ -484,7 +515,7 @@ __global__ void __launch_bounds__(32 * (kEpilogueWarp0 + EW), 1) gemm_kernel(con
           for (int j = 0; j < 8; ++j) {
             const int r = (lane >> 3) + 4 * j;          // 4 rows per store instruction
             const int col = col0 + piece * 8;
-            if (piece * 8 < width && row0 + r < p.M && col < p.N)
+            if (piece * 8 < width && q * 32 + r < p.tile_rows && row0 + r < p.M && col < p.N)
               *reinterpret_cast<uint4*>(dst + (int64_t)(row0 + r) * p.N + col) = *stage_piece(tile, r, piece);
           }
           __syncwarp();
@@ -540,6 +571,18 @@ int pick_block_n(int64_t N) {
   return 128;
 }
 
+int launch_conv(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, int grid, cudaStream_t s) {
+  constexpr int kStages = 5;
+  const size_t smem = 1024 + (size_t)kStages * (kBlockM * kBlockK * 2) + (size_t)((p.K + kBlockK - 1) / kBlockK) * p.block_n * kBlockK * 2 +
+                      256 + (size_t)8 * kStageTileBytes;
+  if (smem > 227 * 1024) return -1;
+  static b200at::SmemConfig configured;
+  cudaError_t e = b200at::ensure_dynamic_smem(gemm_kernel<B200AT_EPI_NONE, 8, true>, 227 * 1024, configured);
+  if (e != cudaSuccess) return (int)e;
+  gemm_kernel<B200AT_EPI_NONE, 8, true><<<grid, 32 * (kEpilogueWarp0 + 8), smem, s>>>(ma, mb, p);
+  return (int)cudaGetLastError();
+}
+
 template <int EPI>
 int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, int grid, cudaStream_t s) {
   constexpr int EW = (EPI == B200AT_EPI_BIAS_GELU || EPI == B200AT_EPI_GELU_GRAD) ? 16 : 8;
@@ -569,6 +612,8 @@ extern "C" int b200at_gemm_bf16(const void* a, const void* b, void* c, void* c2,
   p.block_n = pick_block_n(N);
   p.tiles_m = (int)((M + kBlockM - 1) / kBlockM);
   p.tiles_n = (int)((N + p.block_n - 1) / p.block_n);
+  p.tile_rows = kBlockM;
+  p.conv = 0; p.conv_rows = 0; p.conv_tiles_per_img = 1; p.conv_a_bytes = 0;
   CUtensorMap ma, mb;
   if (!make_map(&ma, a, M, K, kBlockM) || !make_map(&mb, b, N, K, p.block_n)) return (int)cudaErrorUnknown;
   int dev = 0, sms = 148;
@@ -585,4 +630,51 @@ extern "C" int b200at_gemm_bf16(const void* a, const void* b, void* c, void* c2,
     case B200AT_EPI_GELU_GRAD: return launch<B200AT_EPI_GELU_GRAD>(ma, mb, p, grid, s);
     default: return (int)cudaErrorInvalidValue;
   }
+}
+
+// out[b][oh][ow][co] = sum_{kh,kw,ci} x[b][2 oh + kh - 1][2 ow + kw - 1][ci] w[co][ci][kh][kw]   (Conv2d(k=3, s=2, p=1), no bias)
+// as an implicit GEMM on the kernel above: M = output pixels (tiles of whole output rows), N = Cout, K = 9 taps x 64 (the
+// channels of a tap padded to one SWIZZLE_128B k-block; TMA zero-fills channels >= Cin and the padding ring).
+// wk: [Cout][9 * 64] bf16, wk[co][(kh * 3 + kw) * 64 + ci] = w[co][ci][kh][kw], zero for ci >= Cin.  Returns -1 for shapes it
+// does not take (the caller keeps the library convolution for those).
+extern "C" int b200at_conv3x3s2_fwd(const void* x, const void* wk, void* y, int64_t B, int64_t H, int64_t W, int64_t Cin,
+                                    int64_t Cout, void* stream) {
+  if (B <= 0) return 0;
+  if (H % 2 || W % 2 || Cin % 8 || Cin > 64 || Cout % 16 || Cout > 256) return -1;
+  const int64_t OH = H / 2, OW = W / 2;
+  if (OW > 128 || (reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(y) & 15) ||
+      (reinterpret_cast<uintptr_t>(wk) & 15))
+    return -1;
+  int rows = (int)(kBlockM / OW);
+  while (rows > 1 && OH % rows) --rows;
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return (int)cudaErrorUnknown;
+  GemmParams p;
+  p.c = (bf16*)y; p.c2 = nullptr; p.aux = nullptr; p.bias = nullptr;
+  p.M = (int)(B * OH * OW); p.N = (int)Cout; p.K = 9 * kBlockK;
+  p.block_n = pick_block_n(Cout);
+  p.tile_rows = rows * (int)OW;
+  p.tiles_m = (int)(B * (OH / rows));
+  p.tiles_n = (int)((Cout + p.block_n - 1) / p.block_n);
+  p.conv = 1; p.conv_rows = rows; p.conv_tiles_per_img = (int)(OH / rows);
+  p.conv_a_bytes = (uint32_t)(kBlockK * 2 * OW * rows);
+  if ((int64_t)B * OH * OW > 0x7fffffff) return -1;
+  CUtensorMap ma, mb;
+  {
+    const cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    const cuuint64_t strides[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
+    const cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)(2 * OW), (cuuint32_t)(2 * rows), 1};
+    const cuuint32_t estr[4] = {1, 2, 2, 1};
+    if (fn(&ma, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr,
+           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return (int)cudaErrorUnknown;
+  }
+  if (!make_map(&mb, wk, Cout, 9 * kBlockK, p.block_n)) return (int)cudaErrorUnknown;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int tiles = p.tiles_m * p.tiles_n;
+  if (p.tiles_n != 1) return -1;
+  return launch_conv(ma, mb, p, tiles < sms ? tiles : sms, (cudaStream_t)stream);
 }

@@ -466,6 +466,54 @@ def _host3(t):
 
 
 STEM0_KERNEL = os.environ.get('B200AT_STEM0', '1') == '1'
+STEM_CONV_GEMM = os.environ.get('B200AT_STEM_CONV', 'gemm') == 'gemm'
+
+
+def _conv3x3s2_wk(w):
+    """[Co, Ci, 3, 3] -> [Co, 9 * 64] bf16: tap-major, the channels of a tap padded to one 64-wide k-block"""
+    Co, Ci = w.shape[0], w.shape[1]
+    wk = torch.zeros(Co, 9, 64, device=w.device, dtype=BF16)
+    wk[:, :, :Ci] = w.permute(0, 2, 3, 1).reshape(Co, 9, Ci).to(BF16)
+    return wk.view(Co, 576)
+
+
+class _Conv3x3S2(Function):
+    """Conv2d(k=3, s=2, p=1, no bias) on NHWC bf16 (the later convolutions of the CvSt stems,
+    utils_architecture.py:205-211): forward = implicit GEMM on the tcgen05 kernel (b200at_conv3x3s2_fwd); the input and
+    weight gradients stay library calls."""
+
+    @staticmethod
+    def forward(ctx, x, cw):
+        x = x.contiguous()
+        B, H, W, _ = x.shape
+        wk = _derived(cw, 'conv3x3s2_wk', _conv3x3s2_wk)
+        y = torch.empty(B, H // 2, W // 2, cw.shape[0], device=x.device, dtype=BF16)
+        if not _abi.conv3x3s2_fwd(x, wk, y):             # a shape the kernel does not take (shared-memory budget)
+            y = F.conv2d(x.permute(0, 3, 1, 2), _bf16(cw), None, stride=2, padding=1).permute(0, 2, 3, 1).contiguous()
+        ctx.param_grads = not _INPUT_GRAD_ONLY[0]
+        ctx.save_for_backward(x, cw)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, cw = ctx.saved_tensors
+        xc = x.permute(0, 3, 1, 2)                       # NCHW views of channels_last storage
+        dyc = dy.contiguous().permute(0, 3, 1, 2)
+        wb = _bf16(cw).contiguous(memory_format=torch.channels_last)
+        want_w = ctx.param_grads and ctx.needs_input_grad[1]
+        dx, dw, _ = torch.ops.aten.convolution_backward(dyc, xc, wb, None, (2, 2), (1, 1), (1, 1), False, (0, 0), 1,
+                                                        (ctx.needs_input_grad[0], want_w, False))
+        if dx is not None:
+            dx = dx.permute(0, 2, 3, 1)                  # channels_last result viewed as NHWC
+        if dw is not None:
+            dw = dw.to(cw.dtype)
+        return dx, dw
+
+
+def _conv3x3s2_ok(x, cw):
+    B, H, W, Ci = x.shape
+    return (STEM_CONV_GEMM and x.dtype == BF16 and H % 2 == 0 and W % 2 == 0 and Ci % 8 == 0 and Ci <= 64
+            and cw.shape[0] % 16 == 0 and cw.shape[0] <= 256 and W // 2 <= 128 and tuple(cw.shape[2:]) == (3, 3))
 
 
 def stem_layer(x, cw, cb, lw, lb, stride, first, mean=None, std=None):
@@ -488,6 +536,9 @@ def stem_layer(x, cw, cb, lw, lb, stride, first, mean=None, std=None):
             x = (x - mean) / std
         x = x.to(BF16).contiguous(memory_format=torch.channels_last)
     else:
+        if stride == 2 and cw.shape[0] % 8 == 0 and _conv3x3s2_ok(x, cw):
+            y = _Conv3x3S2.apply(x, cw)
+            return layer_norm(y, lw, lb, 1e-6, gelu=True, pre_bias=cb)
         x = x.permute(0, 3, 1, 2)                        # NHWC storage viewed as NCHW channels_last
     # the library convolution runs WITHOUT its bias: torch adds a conv bias as a separate full pass over the output (the
     # largest activations of the network: 0.5 ms per step) and reduces its gradient in another; both ride in the

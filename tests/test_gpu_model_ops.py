@@ -333,3 +333,27 @@ def test_normalize_nhwc_matches_the_eager_expression_bit_for_bit(cuda_dev):
         assert torch.equal(y, want)
         _abi.normalize_nhwc_bf16(x, None, None, y)
         assert torch.equal(y, x.to(torch.bfloat16).permute(0, 2, 3, 1))
+
+
+@pytest.mark.parametrize('shape,Co', [((2, 112, 112, 48), 96), ((3, 40, 40, 64), 96), ((1, 160, 160, 48), 96),
+                                      ((2, 24, 56, 16), 32), ((5, 8, 8, 8), 16)])
+def test_conv3x3s2_implicit_gemm(ops, cuda_dev, shape, Co):
+    """the stems' second convolution (utils_architecture.py:205-211) as an implicit GEMM on the tcgen05 kernel against the
+    library convolution of the same bf16 operands; gradients flow through the library calls of its backward"""
+    g = torch.Generator(device='cuda').manual_seed(sum(shape) + Co)
+    B, H, W, Ci = shape
+    x = torch.randn(shape, generator=g, device=cuda_dev).to(torch.bfloat16).requires_grad_()
+    w = (torch.randn(Co, Ci, 3, 3, generator=g, device=cuda_dev) * (9 * Ci) ** -0.5).requires_grad_()
+    assert ops._conv3x3s2_ok(x, w)
+    y = ops._Conv3x3S2.apply(x, w)
+    xr = x.detach().float().requires_grad_()
+    wr = w.detach().to(torch.bfloat16).float().requires_grad_()
+    yr = F.conv2d(xr.permute(0, 3, 1, 2), wr, None, stride=2, padding=1).permute(0, 2, 3, 1)
+    assert y.shape == yr.shape
+    err = (y.detach().float() - yr.detach()).abs()
+    assert float(err.max()) <= 2e-2 + 1e-2 * float(yr.detach().abs().max()), float(err.max())
+    dy = torch.randn(y.shape, generator=g, device=cuda_dev).to(torch.bfloat16)
+    y.backward(dy)
+    yr.backward(dy.float())
+    assert torch.nn.functional.cosine_similarity(x.grad.float().flatten(), xr.grad.flatten(), dim=0) > 0.999
+    assert torch.nn.functional.cosine_similarity(w.grad.float().flatten(), wr.grad.flatten(), dim=0) > 0.999
