@@ -81,11 +81,17 @@ int b200at_dwconv7_wgrad(const void* x, const void* dy, float* dw, float* db, in
  * ImageNormalizer (:86-98) folded in:  y = GELU(LN(conv((x - mean) / std) + bias)).
  * x: fp32 NCHW [B][3][H][W] (the attack's iterate, read as is); y: NHWC bf16 [B][Ho][Wo][C0], Ho = (H-1)/2+1.
  * wk: fp32 [27][C0], wk[c*9+kh*3+kw][co] = weight[co][c][kh][kw].  mean3 / std3: HOST pointers to 3 floats, or
- * null for no normalisation.  C0 in {48, 64, 96}.  Used for the attack's evaluations (no weight gradients);
- * the training forward keeps the library convolution, whose weight gradient it needs. */
+ * null for no normalisation.  C0 in {48, 64, 96}.  b200at_stem0_fwd serves the attack's evaluations (no weight
+ * gradients), b200at_stem0_fwd_save the training forward. */
 int b200at_stem0_fwd(const float* x, const float* mean3, const float* std3, const float* wk, const float* bias,
                      const float* ln_w, const float* ln_b, void* y, int64_t B, int64_t H, int64_t W, int64_t C0,
                      float eps, void* stream);
+/* The same stage for the TRAINING forward: additionally y_pre [B][Ho][Wo][C0] bf16 = the convolution output WITHOUT its bias
+ * and mean / rstd [B*Ho*Wo] fp32 = the LayerNorm statistics, i.e. exactly what b200at_ln_bwd_bias(dy, y_pre, pre_bias = bias,
+ * ..., fuse_gelu = 1) needs; the convolution's weight gradient is then a library call on (normalised x, d y_pre). */
+int b200at_stem0_fwd_save(const float* x, const float* mean3, const float* std3, const float* wk, const float* bias,
+                          const float* ln_w, const float* ln_b, void* y, void* y_pre, float* mean, float* rstd, int64_t B,
+                          int64_t H, int64_t W, int64_t C0, float eps, void* stream);
 /* dL/dx (fp32 NCHW, every element written) of the above given dy = dL/dy (NHWC bf16): the attack's
  * `torch.autograd.grad(loss, [x_adv])` (autopgd_train_clean.py:185,283) through the first layer.  Recomputes the
  * pre-LayerNorm activation from x; nothing is saved by the forward. */

@@ -112,6 +112,7 @@ def _declare(L):
         'b200at_prepare_mlp_weights': [P, P, P, P, P, P, P, P, P, I64, P],
         'b200at_finish_mlp_grads': [P, P, P, P, P, P, P, P, I64, P],
         'b200at_stem0_fwd': [P, P, P, P, P, P, P, P, I64, I64, I64, I64, F, P],
+        'b200at_stem0_fwd_save': [P, P, P, P, P, P, P, P, P, P, P, I64, I64, I64, I64, F, P],
         'b200at_stem0_bwd_input': [P, P, P, P, P, P, P, P, P, I64, I64, I64, I64, F, P],
         'b200at_attn_fwd': [P, P, P, I64, I64, I64, F, P],
         'b200at_attn_bwd': [P, P, P, P, P, I64, I64, I64, F, P],
@@ -444,6 +445,22 @@ def stem0_fwd(x, mean3, std3, wk, bias, ln_w, ln_b, y, eps=1e-6):
         _check(lib().b200at_stem0_fwd(_x_nchw(x), m, sd, _par(wk, 'wk', 27 * C0), _par(bias, 'bias', C0),
                                       _par(ln_w, 'ln_w', C0), _par(ln_b, 'ln_b', C0), _act(y, 'y'), B, H, W, C0, eps,
                                       _stream()), 'stem0_fwd')
+
+
+def stem0_fwd_save(x, mean3, std3, wk, bias, ln_w, ln_b, y, y_pre, mean, rstd, eps=1e-6):
+    """stem0_fwd for the training forward: also y_pre (conv output without bias, bf16) and the LayerNorm statistics."""
+    B, _, H, W = x.shape
+    C0 = bias.numel()
+    shp = (B, (H - 1) // 2 + 1, (W - 1) // 2 + 1, C0)
+    if tuple(y.shape) != shp or tuple(y_pre.shape) != shp:
+        raise B200atError(f'stem0_fwd_save: y shape {tuple(y.shape)} / {tuple(y_pre.shape)}')
+    M = shp[0] * shp[1] * shp[2]
+    m, sd = _host3(mean3), _host3(std3)
+    with _Timed('stem0_fwd_save'):
+        _check(lib().b200at_stem0_fwd_save(_x_nchw(x), m, sd, _par(wk, 'wk', 27 * C0), _par(bias, 'bias', C0),
+                                           _par(ln_w, 'ln_w', C0), _par(ln_b, 'ln_b', C0), _act(y, 'y'), _act(y_pre, 'y_pre'),
+                                           _par(mean, 'mean', M), _par(rstd, 'rstd', M), B, H, W, C0, eps, _stream()),
+               'stem0_fwd_save')
 
 
 def normalize_nhwc_bf16(x, mean3, std3, y):

@@ -101,8 +101,14 @@ __device__ __forceinline__ void ln_stats(const float2* acc, float eps, float& mu
 
 constexpr int kFwdThreads = 128;
 
-template <int C0>
-__global__ void __launch_bounds__(kFwdThreads) stem0_fwd_kernel(const StemParams p, bf16* __restrict__ y) {
+// SAVE (the training forward): also the convolution output WITHOUT its bias (bf16, what the unfused path hands to the
+// LayerNorm kernels as `x` with `pre_bias`) and the LayerNorm statistics, so that the backward can stay b200at_ln_bwd_bias +
+// the convolution's weight gradient.
+template <int C0, bool SAVE = false>
+__global__ void __launch_bounds__(kFwdThreads) stem0_fwd_kernel(const StemParams p, bf16* __restrict__ y,
+                                                                bf16* __restrict__ y_pre = nullptr,
+                                                                float* __restrict__ mean_out = nullptr,
+                                                                float* __restrict__ rstd_out = nullptr) {
   constexpr int kPitch = C0 * 2 + 16;                       // bytes per staged pixel row (pad: conflict-free 16 B stores)
   __shared__ __align__(16) float wsm[27 * C0];
   __shared__ __align__(16) float bsm[C0], lw[C0], lb[C0];
@@ -113,17 +119,18 @@ __global__ void __launch_bounds__(kFwdThreads) stem0_fwd_kernel(const StemParams
   const int64_t total = (int64_t)p.B * p.Ho * p.Wo;
   const int64_t pix0 = (int64_t)blockIdx.x * kFwdThreads;
   const int64_t pix = pix0 + threadIdx.x;
+  float2 acc[C0 / 2];
+  uint8_t* row = stage + threadIdx.x * kPitch;
   if (pix < total) {
     const int wo = (int)(pix % p.Wo);
     const int ho = (int)((pix / p.Wo) % p.Ho);
     const int n = (int)(pix / ((int64_t)p.Wo * p.Ho));
     float v[27];
     load_window(p, n, ho, wo, v);
-    float2 acc[C0 / 2];
     conv_pixel<C0>(wsm, bsm, v, acc);
     float mu, rs;
     ln_stats<C0>(acc, p.eps, mu, rs);
-    uint8_t* row = stage + threadIdx.x * kPitch;
+    if (SAVE) { mean_out[pix] = mu; rstd_out[pix] = rs; }
 #pragma unroll
     for (int j = 0; j < C0 / 2; j += 4) {
       uint32_t w[4];
@@ -146,6 +153,28 @@ __global__ void __launch_bounds__(kFwdThreads) stem0_fwd_kernel(const StemParams
   for (int q = threadIdx.x; q < (int)live * kPieces; q += kFwdThreads) {
     const int r = q / kPieces, piece = q % kPieces;
     dst[q] = *reinterpret_cast<const uint4*>(stage + r * kPitch + piece * 16);
+  }
+  if (SAVE) {
+    __syncthreads();
+    if (pix < total) {
+#pragma unroll
+      for (int j = 0; j < C0 / 2; j += 4) {
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int c = 2 * (j + i);
+          bf162 t = __floats2bfloat162_rn(acc[j + i].x - bsm[c], acc[j + i].y - bsm[c + 1]);
+          w[i] = *reinterpret_cast<uint32_t*>(&t);
+        }
+        *reinterpret_cast<uint4*>(row + j * 4) = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+    }
+    __syncthreads();
+    uint4* dst2 = reinterpret_cast<uint4*>(y_pre + pix0 * C0);
+    for (int q = threadIdx.x; q < (int)live * kPieces; q += kFwdThreads) {
+      const int r = q / kPieces, piece = q % kPieces;
+      dst2[q] = *reinterpret_cast<const uint4*>(stage + r * kPitch + piece * 16);
+    }
   }
 }
 
@@ -715,6 +744,26 @@ int b200at_stem0_fwd(const float* x, const float* mean3, const float* std3, cons
     case 48: stem0_fwd_kernel<48><<<(unsigned)grid, kFwdThreads, 0, s>>>(p, (bf16*)y); break;
     case 64: stem0_fwd_kernel<64><<<(unsigned)grid, kFwdThreads, 0, s>>>(p, (bf16*)y); break;
     case 96: stem0_fwd_kernel<96><<<(unsigned)grid, kFwdThreads, 0, s>>>(p, (bf16*)y); break;
+    default: return (int)cudaErrorInvalidValue;
+  }
+  return (int)cudaGetLastError();
+}
+
+int b200at_stem0_fwd_save(const float* x, const float* mean3, const float* std3, const float* wk, const float* bias,
+                          const float* ln_w, const float* ln_b, void* y, void* y_pre, float* mean, float* rstd, int64_t B,
+                          int64_t H, int64_t W, int64_t C0, float eps, void* stream) {
+  if (B <= 0) return 0;
+  StemParams p;
+  if (H < 1 || W < 1 || !fill(p, x, mean3, std3, wk, bias, ln_w, ln_b, B, H, W, eps)) return (int)cudaErrorInvalidValue;
+  if (y_pre == nullptr || mean == nullptr || rstd == nullptr) return (int)cudaErrorInvalidValue;
+  const int64_t total = (int64_t)p.B * p.Ho * p.Wo;
+  const int64_t grid = (total + kFwdThreads - 1) / kFwdThreads;
+  if (grid > 0x7fffffff) return (int)cudaErrorInvalidValue;
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (C0) {
+    case 48: stem0_fwd_kernel<48, true><<<(unsigned)grid, kFwdThreads, 0, s>>>(p, (bf16*)y, (bf16*)y_pre, mean, rstd); break;
+    case 64: stem0_fwd_kernel<64, true><<<(unsigned)grid, kFwdThreads, 0, s>>>(p, (bf16*)y, (bf16*)y_pre, mean, rstd); break;
+    case 96: stem0_fwd_kernel<96, true><<<(unsigned)grid, kFwdThreads, 0, s>>>(p, (bf16*)y, (bf16*)y_pre, mean, rstd); break;
     default: return (int)cudaErrorInvalidValue;
   }
   return (int)cudaGetLastError();

@@ -458,6 +458,45 @@ class _Stem0(Function):
         return dx, None, None, None, None, None, None
 
 
+class _Stem0Train(Function):
+    """The same first stem stage in the TRAINING forward (x: the attack's detached fp32 output): the fused kernel also
+    leaves the convolution output (without bias) and the LayerNorm statistics, so the backward is the LN+GELU backward
+    kernel with the conv bias as `pre_bias`, its column sum for the conv bias, and the library weight gradient of the
+    convolution on the re-normalised input.  No input gradient (x does not require one)."""
+
+    @staticmethod
+    def forward(ctx, x, cw, cb, lw, lb, mean3, std3):
+        B, _, H, W = x.shape
+        C0 = cw.shape[0]
+        wk = _derived(cw, 'stem0_wk', lambda w: w.float().reshape(w.shape[0], 27).t().contiguous())   # [27][C0]
+        cbf, lwf, lbf = _f32(cb), _f32(lw), _f32(lb)
+        shp = (B, (H - 1) // 2 + 1, (W - 1) // 2 + 1, C0)
+        y = torch.empty(shp, device=x.device, dtype=BF16)
+        y_pre = torch.empty(shp, device=x.device, dtype=BF16)
+        mean = torch.empty(shp[0] * shp[1] * shp[2], device=x.device, dtype=torch.float32)
+        rstd = torch.empty_like(mean)
+        _abi.stem0_fwd_save(x, mean3, std3, wk, cbf, lwf, lbf, y, y_pre, mean, rstd)
+        ctx.save_for_backward(x, y_pre, mean, rstd, cw, cbf, lwf, lbf)
+        ctx.norm = (mean3, std3)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, y_pre, mean, rstd, cw, cbf, lwf, lbf = ctx.saved_tensors
+        C0 = cw.shape[0]
+        dpre = torch.empty_like(y_pre)
+        dlw, dlb, dcb = _zeros_split(dy.device, C0, C0, C0)
+        _abi.ln_bwd(dy.contiguous(), y_pre, lwf, lbf, mean, rstd, dpre, dlw, dlb, True, pre_bias=cbf)
+        _abi.colsum_bf16(dpre.view(-1, C0), dcb)
+        B, _, H, W = x.shape
+        t = torch.empty(B, H, W, 3, device=x.device, dtype=BF16)
+        _abi.normalize_nhwc_bf16(x, ctx.norm[0], ctx.norm[1], t)
+        _, dcw, _ = torch.ops.aten.convolution_backward(dpre.permute(0, 3, 1, 2), t.permute(0, 3, 1, 2),
+                                                        _bf16(cw).contiguous(memory_format=torch.channels_last), None,
+                                                        (2, 2), (1, 1), (1, 1), False, (0, 0), 1, (False, True, False))
+        return None, dcw.to(cw.dtype), dcb, dlw, dlb, None, None
+
+
 def _host3(t):
     """3 python floats of the normaliser's mean / std buffer (one D2H copy per buffer object and version)."""
     if t is None:
@@ -467,6 +506,7 @@ def _host3(t):
 
 STEM0_KERNEL = os.environ.get('B200AT_STEM0', '1') == '1'
 STEM_CONV_GEMM = os.environ.get('B200AT_STEM_CONV', 'gemm') == 'gemm'
+STEM0_TRAIN = os.environ.get('B200AT_STEM0_TRAIN', '1') == '1'     # fused first stage in the training forward too
 
 
 def _conv3x3s2_wk(w):
@@ -526,6 +566,10 @@ def stem_layer(x, cw, cb, lw, lb, stride, first, mean=None, std=None):
             and (_INPUT_GRAD_ONLY[0] or not torch.is_grad_enabled())):
         wk = _derived(cw, 'stem0_wk', lambda w: w.float().reshape(w.shape[0], 27).t().contiguous())   # [27][C0]
         return _Stem0.apply(x.contiguous(), wk, _f32(cb), _f32(lw), _f32(lb), _host3(mean), _host3(std))
+    if (first and STEM0_TRAIN and STEM0_KERNEL and stride == 2 and cw.shape[0] in (48, 64, 96) and x.dtype == torch.float32
+            and x.is_contiguous() and x.shape[1] == 3 and not x.requires_grad and x.shape[2] % 2 == 0 and x.shape[3] % 2 == 0):
+        # training forward on the attack's (detached) output: the fused kernel, keeping what the backward needs
+        return _Stem0Train.apply(x, cw, cb, lw, lb, _host3(mean), _host3(std))
     if first and x.dtype == torch.float32 and x.is_contiguous() and x.shape[1] == 3 and not x.requires_grad:
         # training forward on the attack's (detached) output: normalise + cast + NHWC in one pass
         t = torch.empty(x.shape[0], x.shape[2], x.shape[3], 3, device=x.device, dtype=BF16)

@@ -357,3 +357,30 @@ def test_conv3x3s2_implicit_gemm(ops, cuda_dev, shape, Co):
     yr.backward(dy.float())
     assert torch.nn.functional.cosine_similarity(x.grad.float().flatten(), xr.grad.flatten(), dim=0) > 0.999
     assert torch.nn.functional.cosine_similarity(w.grad.float().flatten(), wr.grad.flatten(), dim=0) > 0.999
+
+
+@pytest.mark.parametrize('C0', [48, 96])
+@pytest.mark.parametrize('shape', [(2, 3, 64, 64), (1, 3, 224, 224)])
+def test_stem0_training_forward_keeps_what_the_backward_needs(ops, cuda_dev, C0, shape):
+    """the fused first stem stage in the training forward (detached fp32 input, parameters require grad): output and all
+    parameter gradients against fp32 torch autograd of conv -> LN -> GELU on the normalised input"""
+    g = torch.Generator(device='cuda').manual_seed(C0 + shape[2] + 1)
+    x = torch.rand(*shape, generator=g, device=cuda_dev)
+    P = [(torch.randn(C0, 3, 3, 3, generator=g, device=cuda_dev) * 0.3), torch.randn(C0, generator=g, device=cuda_dev) * 0.1,
+         1 + 0.2 * torch.randn(C0, generator=g, device=cuda_dev), 0.2 * torch.randn(C0, generator=g, device=cuda_dev)]
+    mean = torch.tensor([0.485, 0.456, 0.406], device=cuda_dev).view(1, 3, 1, 1)
+    std = torch.tensor([0.229, 0.224, 0.225], device=cuda_dev).view(1, 3, 1, 1)
+    Pr = [p.clone().requires_grad_() for p in P]
+    h = F.conv2d((x - mean) / std, Pr[0], Pr[1], stride=2, padding=1).permute(0, 2, 3, 1)
+    ref = F.gelu(F.layer_norm(h, (C0,), Pr[2], Pr[3], 1e-6))
+    dy = torch.randn(ref.shape, generator=g, device=cuda_dev).to(BF16)
+    rg = torch.autograd.grad(ref, Pr, dy.float())
+    Pt = [p.clone().requires_grad_() for p in P]
+    out = ops.stem_layer(x, Pt[0], Pt[1], Pt[2], Pt[3], 2, True, mean, std)
+    assert type(out.grad_fn).__name__.startswith('_Stem0Train')
+    _close(out, ref, atol=1e-2)
+    tg = torch.autograd.grad(out, Pt, dy)
+    for name, a, b in zip(('conv weight', 'conv bias', 'ln weight', 'ln bias'), tg, rg):
+        cos = F.cosine_similarity(a.float().flatten(), b.flatten(), dim=0).item()
+        assert cos > 0.999, (name, cos)
+        assert abs(a.float().norm().item() / b.norm().item() - 1) < 2e-2, name
