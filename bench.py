@@ -107,13 +107,15 @@ def synth_batch(batch, seed):
 
 
 ENGINE_NOTE = {
-    False: 'hand-written NHWC bf16 kernels: fused first stem stage, dwconv7 fwd/dgrad/wgrad, LayerNorm (+patch layout for '
-           'the downsample), fused tcgen05 MLP kernel per direction (pwconv1 -> GELU -> pwconv2+scale+bias+residual, hidden '
-           'on chip) for C <= 192, tcgen05 GEMM + bias/GELU kernels for the wider stages and the downsample conv2x2s2; '
-           'cuBLAS for the weight-gradient GEMMs, cuDNN for the strided 3x3 stem convs outside the fused first stage',
-    True: 'hand-written kernels: fused first stem stage, LayerNorm(+GELU), bias+GELU, mma.sync attention fwd/bwd, '
-          'tcgen05 GEMM (qkv+bias, proj/fc2+bias+residual, fc1, all input-gradient GEMMs); cuBLAS for weight-gradient '
-          'GEMMs, cuDNN for stem convs 2-4',
+    False: 'hand-written NHWC bf16 kernels: fused first stem stage (attack evaluations and training forward; tensor-core input '
+           'gradient), second stem convolution forward as an implicit GEMM on the tcgen05 kernel, dwconv7 fwd/dgrad (tensor-core '
+           'Toeplitz form on the wide maps) and wgrad, LayerNorm (+patch layout for the downsample), fused tcgen05 MLP kernel per '
+           'direction (pwconv1 -> GELU -> pwconv2+scale+bias+residual, hidden on chip) for C <= 192, tcgen05 GEMM with fused '
+           'bias+GELU / GELU-grad / residual epilogues for the wider stages and the downsample conv2x2s2; library calls: cuBLAS '
+           'weight-gradient GEMMs, cuDNN input / weight gradients of the 3x3 stem convolutions',
+    True: 'hand-written kernels: fused first stem stage, LayerNorm(+GELU), mma.sync attention fwd/bwd, tcgen05 GEMM (qkv+bias, '
+          'proj/fc2+bias+residual, fc1 with bias+GELU, GELU-grad GEMM, all input-gradient GEMMs); cuBLAS for weight-gradient '
+          'GEMMs; second stem convolution forward on the tcgen05 kernel, cuDNN for its gradients and for stem convs 3-4',
 }
 
 

@@ -710,7 +710,7 @@ struct DwTile {
   // resident CTAs per SM the register budget is cut for: the half-height tile keeps 7 instead of 14 accumulator rows
   // per column, which buys a third CTA (21 instead of 14 warps per SM: the full-height form is latency-bound at 2.9
   // active warps per scheduler, profiles/r01_ncu_dwconv_stem0_v11_summary.txt)
-  static constexpr int kMinCtas = (TH == 7 && TW == 28) ? 3 : 2;
+  static constexpr int kMinCtas = (TH == 7 && TW >= 14) ? 3 : 2;
 };
 
 struct DwParams {
@@ -1334,6 +1334,10 @@ int b200at_dwconv7_fwd(const void* x, const float* wt, const float* bias, const 
   static const bool half_height = [] { const char* e = getenv("B200AT_DW_TH7"); return e == nullptr || e[0] != '0'; }();
   if (W > 14) return half_height ? launch_dwconv<7, 28, 1>(x, wt, bias, add, y, B, H, W, C, s)
                                  : launch_dwconv<14, 28, 1>(x, wt, bias, add, y, B, H, W, C, s);
+  // 14-wide maps: the half-height tile (3 CTAs / SM) there too: 41.8 / 40.6 vs 43.8 / 42.7 us at 14 x 14 x 384, batch 128
+  // (profiles/r02_ops_bench_dwconv_half14.txt); B200AT_DW_TH7_14=0 keeps the full-height tile
+  static const bool half14 = [] { const char* e = getenv("B200AT_DW_TH7_14"); return e == nullptr || e[0] != '0'; }();
+  if ((W > 8 || H > 7) && half14 && H > 7) return launch_dwconv<7, 14, 2>(x, wt, bias, add, y, B, H, W, C, s);
   if (W > 8 || H > 7) return launch_dwconv<14, 14, 2>(x, wt, bias, add, y, B, H, W, C, s);
   return launch_dwconv<7, 8, 3>(x, wt, bias, add, y, B, H, W, C, s);
 }

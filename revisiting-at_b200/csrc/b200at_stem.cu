@@ -137,9 +137,9 @@ __global__ void __launch_bounds__(kFwdThreads) stem0_fwd_kernel(const StemParams
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int c = 2 * (j + i);
-        const float a = b200at_gelu((acc[j + i].x - mu) * rs * lw[c] + lb[c]);
-        const float b = b200at_gelu((acc[j + i].y - mu) * rs * lw[c + 1] + lb[c + 1]);
-        bf162 t = __floats2bfloat162_rn(a, b);
+        const float2 ab = b200at_gelu2(make_float2((acc[j + i].x - mu) * rs * lw[c] + lb[c],
+                                                   (acc[j + i].y - mu) * rs * lw[c + 1] + lb[c + 1]));
+        bf162 t = __floats2bfloat162_rn(ab.x, ab.y);
         w[i] = *reinterpret_cast<uint32_t*>(&t);
       }
       *reinterpret_cast<uint4*>(row + j * 4) = make_uint4(w[0], w[1], w[2], w[3]);
@@ -222,8 +222,9 @@ __global__ void __launch_bounds__(kBwdThreads) stem0_bwd_kernel(const StemParams
           const int c = 2 * (j + i);
           const float2 d = __bfloat1622float2(*reinterpret_cast<const bf162*>(&w4[i]));
           const float xa = (acc[j + i].x - mu) * rs, xb = (acc[j + i].y - mu) * rs;
-          const float ga = d.x * b200at_gelu_grad(xa * lw[c] + lb[c]) * lw[c];
-          const float gb = d.y * b200at_gelu_grad(xb * lw[c + 1] + lb[c + 1]) * lw[c + 1];
+          const float2 gp = b200at_gelu_grad2(make_float2(xa * lw[c] + lb[c], xb * lw[c + 1] + lb[c + 1]));
+          const float ga = d.x * gp.x * lw[c];
+          const float gb = d.y * gp.y * lw[c + 1];
           acc[j + i] = make_float2(xa, xb);
           g[j + i] = make_float2(ga, gb);
           s1 += ga + gb;
@@ -500,10 +501,10 @@ __global__ void __launch_bounds__(kTcFwdThreads) stem0_fwd_tc_kernel(const StemP
     for (int t = 0; t < T::NT; ++t) {
       const int c = 8 * t + 2 * q;
       const float w0 = lw[c], w1 = lw[c + 1], b0 = lb[c], b1 = lb[c + 1];
-      const bf162 oa2 = __floats2bfloat162_rn(b200at_gelu((acc[t][0] - mu[0]) * rs[0] * w0 + b0),
-                                              b200at_gelu((acc[t][1] - mu[0]) * rs[0] * w1 + b1));
-      const bf162 ob2 = __floats2bfloat162_rn(b200at_gelu((acc[t][2] - mu[1]) * rs[1] * w0 + b0),
-                                              b200at_gelu((acc[t][3] - mu[1]) * rs[1] * w1 + b1));
+      const float2 ga2 = b200at_gelu2(make_float2((acc[t][0] - mu[0]) * rs[0] * w0 + b0, (acc[t][1] - mu[0]) * rs[0] * w1 + b1));
+      const float2 gb2 = b200at_gelu2(make_float2((acc[t][2] - mu[1]) * rs[1] * w0 + b0, (acc[t][3] - mu[1]) * rs[1] * w1 + b1));
+      const bf162 oa2 = __floats2bfloat162_rn(ga2.x, ga2.y);
+      const bf162 ob2 = __floats2bfloat162_rn(gb2.x, gb2.y);
       *reinterpret_cast<bf162*>(rowa + c * 2) = oa2;
       *reinterpret_cast<bf162*>(rowb + c * 2) = ob2;
     }
@@ -582,10 +583,12 @@ __global__ void __launch_bounds__(kTcBwdThreads, (C0 <= 48 ? 2 : 1)) stem0_bwd_t
       const float2 db = __bfloat1622float2(*reinterpret_cast<const bf162*>(&ub));
       const float x0 = (acc[t][0] - mu[0]) * rs[0], x1 = (acc[t][1] - mu[0]) * rs[0];
       const float x2 = (acc[t][2] - mu[1]) * rs[1], x3 = (acc[t][3] - mu[1]) * rs[1];
-      gg[t][0] = da.x * b200at_gelu_grad(x0 * w0 + b0) * w0;
-      gg[t][1] = da.y * b200at_gelu_grad(x1 * w1 + b1) * w1;
-      gg[t][2] = db.x * b200at_gelu_grad(x2 * w0 + b0) * w0;
-      gg[t][3] = db.y * b200at_gelu_grad(x3 * w1 + b1) * w1;
+      const float2 gpa = b200at_gelu_grad2(make_float2(x0 * w0 + b0, x1 * w1 + b1));
+      const float2 gpb = b200at_gelu_grad2(make_float2(x2 * w0 + b0, x3 * w1 + b1));
+      gg[t][0] = da.x * gpa.x * w0;
+      gg[t][1] = da.y * gpa.y * w1;
+      gg[t][2] = db.x * gpb.x * w0;
+      gg[t][3] = db.y * gpb.y * w1;
       acc[t][0] = x0; acc[t][1] = x1; acc[t][2] = x2; acc[t][3] = x3;
       s1a += gg[t][0] + gg[t][1]; s2a += gg[t][0] * x0 + gg[t][1] * x1;
       s1b += gg[t][2] + gg[t][3]; s2b += gg[t][2] * x2 + gg[t][3] * x3;
