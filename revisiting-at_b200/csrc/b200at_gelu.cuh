@@ -16,7 +16,7 @@
 // Forward GELU, round 2: Phi(-|v|) = 2^P7(|v|), P7 = the degree-7 weighted least-squares fit of log2 Phi(-x) on [0, 6.5]
 // (input clamped there: Phi(-6.5) = 4e-11).  7 FMAs + ONE MUFU.EX2 instead of 6 FMAs + 4 multiplies + MUFU.RCP + MUFU.EX2:
 // the XU pipe (16 lanes / clk / SM) was the busiest pipe of the GELU epilogues.  Error of GELU(v) against double precision:
-// 9.6e-8 absolute over [-12, 12] (the A&S form: 2.1e-7).  The derivative keeps the A&S form (it needs exp(-v^2/2) anyway).
+// 9.6e-8 absolute over [-12, 12] (the A&S form: 2.1e-7; profiles/fit_gelu_poly.py prints the coefficients and both numbers).  The derivative keeps the A&S form (it needs exp(-v^2/2) anyway).
 //
 // b200at_gelu2 / b200at_gelu_grad2 evaluate two elements with the packed fp32x2 forms (sm_100 FFMA2 / FMUL2 / FADD2):
 // the same operations in the same order on each lane, so the results are bit-identical to the scalar functions, at half
