@@ -210,28 +210,81 @@ class FlatGradAllReduce:
     all-reduce (AVG), and `p.grad` re-pointed at views of the buffer for the optimiser.  Same arithmetic as DDP's
     (sum, then / world size in fp32).  Like DDP's constructor, the parameters and buffers of rank 0 are broadcast once."""
 
-    def __init__(self, module):
+    def __init__(self, module, buckets=1):
         import torch.distributed as dist
         self.dist = dist
         self.world = dist.get_world_size()
         self.params = [p for p in module.parameters() if p.requires_grad]
         dev = self.params[0].device
         self.flat = torch.zeros(sum(p.numel() for p in self.params), device=dev, dtype=torch.float32)
-        self.views, off = [], 0
-        for p in self.params:
-            # same strides as the parameter (channels_last conv weights included): the fused optimiser wants parameter and
-            # gradient in one layout; every parameter is dense, so its strides address exactly numel() elements
-            self.views.append(self.flat[off:off + p.numel()].as_strided(p.shape, p.stride()))
-            off += p.numel()
+        self._layout()
         with torch.no_grad():
             for t in list(module.parameters()) + list(module.buffers()):
                 dist.broadcast(t.data, 0)
         self.avg = dist.get_backend() == 'nccl'
+        # Overlap (buckets > 1).  The backward produces the gradients in reverse execution order, and 56 % of
+        # ConvNeXt-T's weights sit in the head and the last stage, whose backward is over after a tenth of the backward's
+        # time.  The first step records the order in which the gradients arrive (post-accumulate hooks) and lays the flat
+        # buffer out in that order, cut into `buckets` contiguous ranges of about equal bytes; from then on, when the last
+        # gradient of a range has arrived the range is copied in and all-reduced on a side stream while the backward
+        # goes on, and only the last range (the stem and the first stages: a few MB) is exposed.  Inside the whole-step
+        # CUDA graph the hooks run at capture only (fork / join of the side stream become graph edges); eager, they
+        # cost host time per parameter.  Opt-in (B200AT_FLAT_BUCKETS): measured, it does not beat the single all-reduce.
+        self.nbuckets = buckets if (buckets > 1 and len(self.params) >= buckets) else 1
+        self.buckets, self.side = [], None
+        self.learning = self.nbuckets > 1
+        self.order = []
+        if self.nbuckets > 1:
+            self.side = torch.cuda.Stream(device=dev) if dev.type == 'cuda' else None     # CPU (gloo tests): in line
+            self.index_of = {id(p): i for i, p in enumerate(self.params)}
+            for p in self.params:
+                p.register_post_accumulate_grad_hook(self._hook)
+        self.arrived, self.done, self.forked = [], [], False
+
+    def _layout(self):
+        self.views, self.offsets, off = [], [], 0
+        for p in self.params:
+            # same strides as the parameter (channels_last conv weights included): the fused optimiser wants parameter and
+            # gradient in one layout; every parameter is dense, so its strides address exactly numel() elements
+            self.views.append(self.flat[off:off + p.numel()].as_strided(p.shape, p.stride()))
+            self.offsets.append(off)
+            off += p.numel()
+
+    def _hook(self, p):
+        i = self.index_of[id(p)]
+        if self.learning:
+            self.order.append(i)
+            return
+        b = self.bucket_of[i]
+        self.arrived[b] += 1
+        lo, hi = self.buckets[b]
+        if self.arrived[b] == hi - lo and not self.done[b]:
+            self._reduce_range(lo, hi, overlap=True)
+            self.done[b] = True
+
+    def _finish_learning(self):
+        """flat buffer in arrival order (gradients that never arrived: at the end), ranges of about equal bytes"""
+        seen = set()
+        order = [i for i in self.order if not (i in seen or seen.add(i))]
+        order += [i for i in range(len(self.params)) if i not in seen]
+        self.params = [self.params[i] for i in order]
+        self.index_of = {id(p): i for i, p in enumerate(self.params)}
+        self._layout()
+        total, acc, start = self.flat.numel(), 0, 0
+        for i, p in enumerate(self.params):
+            acc += p.numel()
+            if acc >= total * (len(self.buckets) + 1) / self.nbuckets or i == len(self.params) - 1:
+                self.buckets.append((start, i + 1))
+                start = i + 1
+        self.bucket_of = {i: b for b, (lo, hi) in enumerate(self.buckets) for i in range(lo, hi)}
+        self.arrived = [0] * len(self.buckets)
+        self.done = [False] * len(self.buckets)
+        self.learning = False
 
     @torch.no_grad()
-    def reduce(self):
+    def _reduce_range(self, lo, hi, overlap):
         src, dst = [], []
-        for p, v in zip(self.params, self.views):
+        for p, v in zip(self.params[lo:hi], self.views[lo:hi]):
             if p.grad is None:
                 v.zero_()
             elif p.grad.data_ptr() != v.data_ptr():
@@ -239,11 +292,39 @@ class FlatGradAllReduce:
                 dst.append(v)
         if src:
             torch._foreach_copy_(dst, src)
+        end = self.offsets[hi] if hi < len(self.params) else self.flat.numel()
+        seg = self.flat[self.offsets[lo]:end]
+        if overlap and self.side is not None:
+            self.side.wait_stream(torch.cuda.current_stream())
+            self.forked = True
+            with torch.cuda.stream(self.side):
+                self._all_reduce(seg)
+        else:
+            self._all_reduce(seg)
+
+    def _all_reduce(self, t):
         if self.avg:
-            self.dist.all_reduce(self.flat, op=self.dist.ReduceOp.AVG)
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.AVG)
         else:                                                   # gloo (CPU tests): no AVG
-            self.dist.all_reduce(self.flat)
-            self.flat.div_(self.world)
+            self.dist.all_reduce(t)
+            t.div_(self.world)
+
+    @torch.no_grad()
+    def reduce(self):
+        if self.learning:
+            self._finish_learning()                             # this step: everything after the backward, new layout
+            self._reduce_range(0, len(self.params), overlap=False)
+        elif self.buckets:
+            for b, (lo, hi) in enumerate(self.buckets):         # ranges whose last gradient never arrived
+                if not self.done[b]:
+                    self._reduce_range(lo, hi, overlap=False)
+            if self.forked:
+                torch.cuda.current_stream().wait_stream(self.side)
+            self.arrived = [0] * len(self.buckets)
+            self.done = [False] * len(self.buckets)
+            self.forked = False
+        else:
+            self._reduce_range(0, len(self.params), overlap=False)
         for p, v in zip(self.params, self.views):
             p.grad = v
 
@@ -271,7 +352,12 @@ class AdvTrainStep:
         self.flat_reduce = None
         import os
         if distributed and os.environ.get('B200AT_DDP', 'flat') == 'flat':
-            self.flat_reduce = FlatGradAllReduce(model)
+            # B200AT_FLAT_BUCKETS > 1: ranges of the flat buffer reduced while the backward runs.  Measured with the whole-step
+            # graph (profiles/r02_flat_buckets.txt): 30.33 / 30.35 / 30.33 / 30.24 ms at 2 GPUs for 1 / 2 / 3 / 4 ranges,
+            # 30.56-30.67 vs 30.70-30.72 ms at 8 GPUs for 1 vs 3 -- no gain (the all-reduce of 115 MB is ~0.3 ms of a
+            # 30 ms step and NCCL's CTAs compete with the persistent kernels while it overlaps), so the default stays 1.
+            nb = int(os.environ.get('B200AT_FLAT_BUCKETS', '1'))
+            self.flat_reduce = FlatGradAllReduce(model, buckets=nb)
         elif distributed:
             ids = [device.index] if (device is not None and device.type == 'cuda') else None
             # main.py:890.  broadcast_buffers=False: the only buffers are the normaliser's constant mean/std, and the
