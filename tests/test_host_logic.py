@@ -121,3 +121,26 @@ def test_derived_parameter_copies_follow_a_fused_optimizer_step():
     with torch.no_grad():
         p.mul_(2.)                                                                    # plain in-place ops: version check
     assert torch.equal(ops._derived(p, 'unit_test_copy', lambda w: w.clone()), p.detach())
+
+
+def test_conv3x3s2_weight_layout_is_the_implicit_gemm_of_the_convolution():
+    """b200at_conv3x3s2_fwd's contract (include/b200at_model.h): with wk = ops._conv3x3s2_wk(w), the convolution equals the
+    GEMM of the per-tap strided input rows (channels padded to 64 per tap) with wk^T -- checked here on the CPU against
+    F.conv2d of the same bf16 operands (utils_architecture.py:205-211, Conv2d(k=3, s=2, p=1))."""
+    import torch.nn.functional as F
+    from revisiting_at_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    B, H, W, Ci, Co = 2, 12, 16, 24, 32
+    x = torch.randn(B, H, W, Ci, generator=g).to(torch.bfloat16)
+    w = torch.randn(Co, Ci, 3, 3, generator=g) * 0.1
+    wk = ops._conv3x3s2_wk(w)
+    assert wk.shape == (Co, 576) and wk.dtype == torch.bfloat16
+    xp = F.pad(x.float().permute(0, 3, 1, 2), (1, 1, 1, 1))                       # zero ring = the TMA fill
+    rows = torch.zeros(B, H // 2, W // 2, 9, 64)
+    for kh in range(3):
+        for kw in range(3):
+            rows[..., kh * 3 + kw, :Ci] = xp[:, :, kh:kh + H:2, kw:kw + W:2].permute(0, 2, 3, 1)[:, :H // 2, :W // 2]
+    got = rows.reshape(-1, 576) @ wk.float().t()
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.to(torch.bfloat16).float(), None, stride=2, padding=1)
+    assert torch.allclose(got.view(B, H // 2, W // 2, Co), ref.permute(0, 2, 3, 1), atol=1e-4, rtol=1e-4)
+    assert float(wk.view(Co, 9, 64)[:, :, Ci:].abs().max()) == 0.0                # the padded channels multiply zero-filled input
