@@ -118,6 +118,12 @@ int b200at_stem0_bwd_input(const void* dy, const float* x, const float* mean3, c
 int b200at_gemm_bf16(const void* a, const void* b, void* c, void* c2, const void* aux, const float* bias,
                      int64_t M, int64_t N, int64_t K, int epilogue, void* stream);
 
+/* b200at_gemm_bf16(..., B200AT_EPI_GELU_GRAD) that also accumulates colsum[n] += sum_m C[m][n] (fp32 [N], the values as
+ * rounded to bf16): the pwconv1 bias gradient of models/convnext.py:42-44 in the backward GEMM's epilogue instead of a
+ * b200at_colsum_bf16 pass over dz. */
+int b200at_gemm_gelu_grad_colsum(const void* a, const void* b, void* c, const void* aux, float* colsum, int64_t M, int64_t N,
+                                 int64_t K, void* stream);
+
 /* Conv2d(kernel 3, stride 2, padding 1) WITHOUT bias on NHWC bf16 input -- the second convolution of the CvSt stems
  * (utils_architecture.py:205-211 ConvBlock1: conv -> LayerNorm -> GELU; the bias rides in b200at_ln_fwd_bias) -- as an
  * implicit GEMM on the tcgen05 kernel: M = output pixels in tiles of whole output rows, N = Cout, K = 9 taps x 64

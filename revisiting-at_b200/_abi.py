@@ -106,6 +106,7 @@ def _declare(L):
         'b200at_dwconv7_wgrad': [P, P, P, P, I64, I64, I64, I64, P],
         'b200at_gemm_bf16': [P, P, P, P, P, P, I64, I64, I64, I, P],
         'b200at_conv3x3s2_fwd': [P, P, P, I64, I64, I64, I64, I64, P],
+        'b200at_gemm_gelu_grad_colsum': [P, P, P, P, P, I64, I64, I64, P],
         'b200at_mlp_fused_supported': [I64],
         'b200at_mlp_fused': [P, P, P, P, P, P, P, P, P, I64, I64, I, P],
         'b200at_normalize_nhwc_bf16': [P, P, P, P, I64, I64, I64, P],
@@ -524,6 +525,17 @@ def gemm_bf16(a, b, c, epilogue=EPI_NONE, bias=None, aux=None, c2=None):
                                       _act(c2, 'c2') if c2 is not None else c_void_p(0),
                                       _act(aux, 'aux') if aux is not None else c_void_p(0),
                                       _par(bias, 'bias', N), M, N, K, epilogue, _stream()), 'gemm_bf16')
+
+
+def gemm_gelu_grad_colsum(a, b, c, aux, colsum):
+    """c[M,N] = (a @ b^T) * GELU'(aux) and colsum[N] += column sums of c (include/b200at_model.h)."""
+    M, K = a.shape
+    N = b.shape[0]
+    if b.shape[1] != K or tuple(c.shape) != (M, N) or tuple(aux.shape) != (M, N):
+        raise B200atError(f'gemm_gelu_grad_colsum shapes: a {tuple(a.shape)} b {tuple(b.shape)} c {tuple(c.shape)}')
+    with _Timed('gemm_gelu_grad_colsum'):
+        _check(lib().b200at_gemm_gelu_grad_colsum(_act(a, 'a'), _act(b, 'b'), _act(c, 'c'), _act(aux, 'aux'),
+                                                  _par(colsum, 'colsum', N), M, N, K, _stream()), 'gemm_gelu_grad_colsum')
 
 
 def conv3x3s2_fwd(x, wk, y):

@@ -1037,10 +1037,15 @@ inline void ln_shape(int nv, int& G, int& VPL) {
     if (u > best + 1e-9) { best = u; G = g; VPL = v; }
   }
 }
+inline int env_int_ln(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return (e != nullptr && e[0] != 0) ? atoi(e) : dflt;
+}
 inline int ln_grid(int64_t M, int G) {
   const int rows = kLnThreads / G;
   int64_t g = (M + rows - 1) / rows;
-  const int64_t cap = 148 * 4;          // one resident wave of the <= 64-register forms (weights in shared memory)
+  static const int per_sm = env_int_ln("B200AT_LN_CTAS", 4);
+  const int64_t cap = 148 * (int64_t)per_sm;   // 4: one resident wave of the <= 64-register forms (weights in shared memory)
   return (int)(g < cap ? (g < 1 ? 1 : g) : cap);
 }
 

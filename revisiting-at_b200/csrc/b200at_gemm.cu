@@ -159,6 +159,7 @@ struct GemmParams {
   bf16* c2;           // optional second output (EPI_BIAS_GELU: the pre-activation z = acc), or null
   const bf16* aux;    // EPI_RESIDUAL: residual [M][N];  EPI_GELU_GRAD: saved pre-activation z [M][N]
   const float* bias;  // [N] or null
+  float* colsum;      // EPI_GELU_GRAD only, or null: [N] fp32, += column sums of the (bf16-rounded) output -- the pwconv1 bias gradient
   int M, N, K;
   int block_n, tiles_m, tiles_n;
   int tile_rows;      // output rows an M tile really holds (128; the implicit-GEMM convolution: whole output image rows)
@@ -204,7 +205,7 @@ template <int EPI>
 __device__ __forceinline__ void fused_epilogue(const bf16* __restrict__ aux, bf16* __restrict__ c_out, bf16* __restrict__ c2_out,
                                                int M, int N, int block_n, int tiles_n, int num_tiles, uint32_t tmem_base,
                                                uint64_t* tfull, uint64_t* tempty, uint32_t tile_a, uint32_t bias_a, int warp,
-                                               int lane) {
+                                               int lane, bool colsum) {
   const int q = warp & 3, sub = (warp - kEpilogueWarp0) >> 2;        // TMEM lane quarter; which 64-column group of each 256
   const uint32_t row_a = tile_a + (uint32_t)lane * 64u;               // row-per-lane view
   const uint32_t rsw = (uint32_t)((lane >> 1) & 3);
@@ -242,10 +243,35 @@ __device__ __forceinline__ void fused_epilogue(const bf16* __restrict__ aux, bf1
 #pragma unroll
       for (int j = 0; j < 4; ++j) sts128(row_a + (((uint32_t)j ^ rsw) << 4), o[j]);
       __syncwarp();
+      float2 cs[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const uint4 t = lds128(line_a + 512u * k);
-        if (lp * 8 < w && 8 * k < rows_left) *reinterpret_cast<uint4*>(dst + line_off + (int64_t)(8 * k) * N + c) = t;
+        if (lp * 8 < w && 8 * k < rows_left) {
+          *reinterpret_cast<uint4*>(dst + line_off + (int64_t)(8 * k) * N + c) = t;
+          if (EPI == B200AT_EPI_GELU_GRAD && colsum) {          // what the weight-gradient GEMM will see: the rounded values
+            cs[0] = b200at_fadd2(cs[0], bf2_to_f2(t.x)); cs[1] = b200at_fadd2(cs[1], bf2_to_f2(t.y));
+            cs[2] = b200at_fadd2(cs[2], bf2_to_f2(t.z)); cs[3] = b200at_fadd2(cs[3], bf2_to_f2(t.w));
+          }
+        }
+      }
+      if (EPI == B200AT_EPI_GELU_GRAD && colsum) {              // 8 rows-of-lanes -> one: lanes 0..3 hold 8 column sums each
+#pragma unroll
+        for (int off = 4; off < 32; off <<= 1) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            cs[i].x += __shfl_xor_sync(0xffffffffu, cs[i].x, off);
+            cs[i].y += __shfl_xor_sync(0xffffffffu, cs[i].y, off);
+          }
+        }
+        if (lr == 0 && lp * 8 < w) {
+          const uint32_t a0 = bias_a + (uint32_t)((ncol0 + c + lp * 8) * 4);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(a0 + 8u * i), "f"(cs[i].x) : "memory");
+            asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(a0 + 8u * i + 4u), "f"(cs[i].y) : "memory");
+          }
+        }
       }
       __syncwarp();
     };
@@ -366,6 +392,10 @@ __global__ void __launch_bounds__(32 * (kEpilogueWarp0 + EW), 1) gemm_kernel(con
     const int padded = p.tiles_n * p.block_n;
     for (int i = threadIdx.x; i < padded; i += blockDim.x) sbias[i] = (p.bias != nullptr && i < p.N) ? p.bias[i] : 0.0f;
   }
+  if (EW == 16 && EPI == B200AT_EPI_GELU_GRAD && p.colsum != nullptr) {     // the same region: this CTA's column sums
+    const int padded = p.tiles_n * p.block_n;
+    for (int i = threadIdx.x; i < padded; i += blockDim.x) sbias[i] = 0.0f;
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -432,7 +462,8 @@ __global__ void __launch_bounds__(32 * (kEpilogueWarp0 + EW), 1) gemm_kernel(con
     }
   } else if (warp >= kEpilogueWarp0 && EW == 16) {
     fused_epilogue<EPI>(p.aux, p.c, p.c2, p.M, p.N, p.block_n, p.tiles_n, num_tiles, tmem_base, tfull, tempty,
-                        smem_u32(staging) + (uint32_t)((warp - kEpilogueWarp0) * kFusedTileBytes), smem_u32(sbias), warp, lane);
+                        smem_u32(staging) + (uint32_t)((warp - kEpilogueWarp0) * kFusedTileBytes), smem_u32(sbias), warp, lane,
+                        p.colsum != nullptr);
   } else if (warp >= kEpilogueWarp0) {
     // ------------------------------------------------------------------ epilogue (TMEM -> regs -> smem -> global)
     const int q = warp & 3;                            // TMEM lane quarter this warp may access
@@ -532,6 +563,12 @@ __global__ void __launch_bounds__(32 * (kEpilogueWarp0 + EW), 1) gemm_kernel(con
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
   }
+  if (EW == 16 && EPI == B200AT_EPI_GELU_GRAD && p.colsum != nullptr) {     // one global atomic per column and CTA
+    for (int i = threadIdx.x; i < p.N; i += blockDim.x) {
+      const float v = sbias[i];
+      if (v != 0.0f) atomicAdd(p.colsum + i, v);
+    }
+  }
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -600,14 +637,14 @@ int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, in
 
 }  // namespace
 
-extern "C" int b200at_gemm_bf16(const void* a, const void* b, void* c, void* c2, const void* aux, const float* bias,
-                                int64_t M, int64_t N, int64_t K, int epilogue, void* stream) {
+static int gemm_bf16_impl(const void* a, const void* b, void* c, void* c2, const void* aux, const float* bias, float* colsum,
+                         int64_t M, int64_t N, int64_t K, int epilogue, void* stream) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   if (N % 16 || K % 8) return (int)cudaErrorInvalidValue;
   if ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c)) & 15)
     return (int)cudaErrorInvalidValue;
   GemmParams p;
-  p.c = (bf16*)c; p.c2 = (bf16*)c2; p.aux = (const bf16*)aux; p.bias = bias;
+  p.c = (bf16*)c; p.c2 = (bf16*)c2; p.aux = (const bf16*)aux; p.bias = bias; p.colsum = colsum;
   p.M = (int)M; p.N = (int)N; p.K = (int)K;
   p.block_n = pick_block_n(N);
   p.tiles_m = (int)((M + kBlockM - 1) / kBlockM);
@@ -632,6 +669,19 @@ extern "C" int b200at_gemm_bf16(const void* a, const void* b, void* c, void* c2,
   }
 }
 
+extern "C" int b200at_gemm_bf16(const void* a, const void* b, void* c, void* c2, const void* aux, const float* bias,
+                                int64_t M, int64_t N, int64_t K, int epilogue, void* stream) {
+  return gemm_bf16_impl(a, b, c, c2, aux, bias, nullptr, M, N, K, epilogue, stream);
+}
+
+// C = (A B^T) * GELU'(aux) as b200at_gemm_bf16(..., B200AT_EPI_GELU_GRAD), and colsum[n] += sum_m C[m][n] of the bf16-rounded
+// result: the pwconv1 bias gradient without a separate pass over dz (b200at_colsum_bf16).  colsum: fp32 [N], accumulated into.
+extern "C" int b200at_gemm_gelu_grad_colsum(const void* a, const void* b, void* c, const void* aux, float* colsum, int64_t M,
+                                            int64_t N, int64_t K, void* stream) {
+  if (colsum == nullptr) return (int)cudaErrorInvalidValue;
+  return gemm_bf16_impl(a, b, c, nullptr, aux, nullptr, colsum, M, N, K, B200AT_EPI_GELU_GRAD, stream);
+}
+
 // out[b][oh][ow][co] = sum_{kh,kw,ci} x[b][2 oh + kh - 1][2 ow + kw - 1][ci] w[co][ci][kh][kw]   (Conv2d(k=3, s=2, p=1), no bias)
 // as an implicit GEMM on the kernel above: M = output pixels (tiles of whole output rows), N = Cout, K = 9 taps x 64 (the
 // channels of a tap padded to one SWIZZLE_128B k-block; TMA zero-fills channels >= Cin and the padding ring).
@@ -650,7 +700,7 @@ extern "C" int b200at_conv3x3s2_fwd(const void* x, const void* wk, void* y, int6
   EncodeTiledFn fn = encode_fn();
   if (!fn) return (int)cudaErrorUnknown;
   GemmParams p;
-  p.c = (bf16*)y; p.c2 = nullptr; p.aux = nullptr; p.bias = nullptr;
+  p.c = (bf16*)y; p.c2 = nullptr; p.aux = nullptr; p.bias = nullptr; p.colsum = nullptr;
   p.M = (int)(B * OH * OW); p.N = (int)Cout; p.K = 9 * kBlockK;
   p.block_n = pick_block_n(Cout);
   p.tile_rows = rows * (int)OW;

@@ -181,6 +181,7 @@ def _f32(t):
 #               kernel per direction with the 4C hidden kept on chip (csrc/b200at_mlp.cu), for C in {96, 128, 192}
 TCGEN05 = set(filter(None, os.environ.get('B200AT_TCGEN05', 'residual,dgrad1,fc1,dgrad2,mlp,gelu,gelu_grad').split(',')))
 _MLP_OK = {}
+GELU_GRAD_COLSUM = os.environ.get('B200AT_GELU_GRAD_COLSUM', '1') == '1'   # pwconv1 bias gradient in the GELU' GEMM's epilogue
 
 
 def _mlp_fused(C):
@@ -394,9 +395,13 @@ class _ConvNeXtBlock(Function):
             if pg:
                 _abi.colsum_bf16(dz, db1)
         elif 'gelu_grad' in TCGEN05 and ctx.zb is None:
-            dz = _gemm(d2, P['w2gt'], _abi.EPI_GELU_GRAD, aux=z)
-            if pg:
-                _abi.colsum_bf16(dz, db1)
+            if pg and GELU_GRAD_COLSUM:                                  # bias gradient in the GEMM's epilogue
+                dz = torch.empty(M, 4 * C, device=dout.device, dtype=BF16)
+                _abi.gemm_gelu_grad_colsum(d2, P['w2gt'], dz, z, db1)
+            else:
+                dz = _gemm(d2, P['w2gt'], _abi.EPI_GELU_GRAD, aux=z)
+                if pg:
+                    _abi.colsum_bf16(dz, db1)
         else:
             da = _gemm(d2, P['w2gt']) if 'dgrad2' in TCGEN05 else d2 @ P['w2g']   # [M,4C]  (layer scale folded)
             dz = torch.empty_like(da)
@@ -756,9 +761,13 @@ class _ViTBlock(Function):
         # ---- MLP branch
         db1 = torch.zeros(4 * D, device=dev, dtype=torch.float32) if pg else None
         if 'gelu' in TCGEN05 and 'gelu_grad' in TCGEN05:                # the saved z includes the bias
-            dz = _gemm(d2, P['w2_t'], _abi.EPI_GELU_GRAD, aux=z)        # [M,4D]
-            if pg:
-                _abi.colsum_bf16(dz, db1)
+            if pg and GELU_GRAD_COLSUM:
+                dz = torch.empty(M, z.shape[1], device=dev, dtype=BF16)
+                _abi.gemm_gelu_grad_colsum(d2, P['w2_t'], dz, z, db1)
+            else:
+                dz = _gemm(d2, P['w2_t'], _abi.EPI_GELU_GRAD, aux=z)    # [M,4D]
+                if pg:
+                    _abi.colsum_bf16(dz, db1)
         else:
             da = _gemm(d2, P['w2_t'])
             dz = torch.empty_like(da)

@@ -88,3 +88,21 @@ def test_gemm_gelu_epilogues_over_many_tiles(abi, cuda_dev):
     z = aux.float().requires_grad_()
     (gp,) = torch.autograd.grad(F.gelu(z).sum(), z)
     _check(c, acc * gp, 'gelu_grad')
+
+
+@pytest.mark.parametrize('M,N,K', [(148 * 128 + 77, 512, 192), (300, 3072, 768), (777, 400, 200)])
+def test_gemm_gelu_grad_with_column_sums(abi, cuda_dev, M, N, K):
+    """the GELU' GEMM that also accumulates the column sums of its (bf16-rounded) output: same output as the plain
+    epilogue, sums equal to a separate pass over it"""
+    g = torch.Generator(device='cuda').manual_seed(M + N)
+    a = torch.randn(M, K, generator=g, device=cuda_dev).to(BF16)
+    b = (torch.randn(N, K, generator=g, device=cuda_dev) * K ** -0.5).to(BF16)
+    aux = torch.randn(M, N, generator=g, device=cuda_dev).to(BF16)
+    want = torch.empty(M, N, device=cuda_dev, dtype=BF16)
+    abi.gemm_bf16(a, b, want, abi.EPI_GELU_GRAD, aux=aux)
+    got = torch.full((M, N), float('nan'), device=cuda_dev, dtype=BF16)
+    col = torch.full((N,), 0.5, device=cuda_dev)                     # accumulated INTO
+    abi.gemm_gelu_grad_colsum(a, b, got, aux, col)
+    assert torch.equal(got, want)
+    ref = want.float().sum(0) + 0.5
+    assert torch.allclose(col, ref, atol=1e-3 * M ** 0.5, rtol=1e-4), float((col - ref).abs().max())
