@@ -392,6 +392,14 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const __grid_constant_
         } else {
           mbar_wait(&z_empty[s], ph ^ 1u);                  // the TMA store of two chunks ago has read the buffer
         }
+        // bias of this warp's first 8 columns: requested before the accumulator wait (the st.shared between the later
+        // requests are volatile asm the compiler will not move a load across, so the prefetch is spelled out: without it
+        // the FADD2 that adds the bias held 15 % of the warp-stall samples at C = 192, profiles/r02_mlp192_ncu.txt)
+        // Backward only: measured, it takes 8 / 3 us off the backward at C = 96 / 192 and adds 1 / 5 us to the forward
+        // (profiles/r02_ops_bench_mlp_bias_prefetch.txt).
+        const uint32_t b1_a = bias1_a + (uint32_t)((j * kChunk + sub * 32) * 4);
+        uint4 ba, bb;
+        if (MODE == 1) { ba = lds128(b1_a); bb = lds128(b1_a + 16); }
         mbar_wait(&ta_full[s], ph);
         tc_fence_after();
         uint32_t v[32];
@@ -401,7 +409,6 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const __grid_constant_
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&ta_empty[s]);
-        const uint32_t b1_a = bias1_a + (uint32_t)((j * kChunk + sub * 32) * 4);
         uint4 stored[4];                                    // the values the unfused path stores in bf16 (z / da)
 #pragma unroll
         for (int h = 0; h < 4; ++h) {
@@ -421,9 +428,13 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_kernel(const __grid_constant_
         for (int h = 0; h < 4; ++h) {                       // 8 columns at a time
           float f[8];
           unpack8(stored[h], f);
-          const uint4 ba = lds128(b1_a + (uint32_t)(h * 32)), bb = lds128(b1_a + (uint32_t)(h * 32 + 16));
+          if (MODE == 0) { ba = lds128(b1_a + (uint32_t)(h * 32)); bb = lds128(b1_a + (uint32_t)(h * 32 + 16)); }
           const float bias[8] = {__uint_as_float(ba.x), __uint_as_float(ba.y), __uint_as_float(ba.z), __uint_as_float(ba.w),
                                  __uint_as_float(bb.x), __uint_as_float(bb.y), __uint_as_float(bb.z), __uint_as_float(bb.w)};
+          if (MODE == 1 && h < 3) {                         // the next 8 columns' bias, in flight during this GELU'
+            ba = lds128(b1_a + (uint32_t)((h + 1) * 32));
+            bb = lds128(b1_a + (uint32_t)((h + 1) * 32 + 16));
+          }
           if (MODE == 0) {
 #pragma unroll
             for (int i = 0; i < 8; i += 2) {
