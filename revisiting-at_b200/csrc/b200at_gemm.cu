@@ -201,7 +201,7 @@ __device__ __forceinline__ uint32_t f2_to_bf2(float2 v) {
   return *reinterpret_cast<const uint32_t*>(&t);
 }
 
-template <int EPI>
+template <int EPI, int EW>
 __device__ __forceinline__ void fused_epilogue(const bf16* __restrict__ aux, bf16* __restrict__ c_out, bf16* __restrict__ c2_out,
                                                int M, int N, int block_n, int tiles_n, int num_tiles, uint32_t tmem_base,
                                                uint64_t* tfull, uint64_t* tempty, uint32_t tile_a, uint32_t bias_a, int warp,
@@ -221,7 +221,7 @@ __device__ __forceinline__ void fused_epilogue(const bf16* __restrict__ aux, bf1
     const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * block_n);
     const int64_t line_off = (int64_t)(row0 + lr) * N + ncol0 + lp * 8;
     const int rows_left = M - row0 - lr;                              // line k is inside the matrix when 8 k < rows_left
-    auto pass_col = [&](int e) { return sub * 64 + (e >> 1) * 256 + (e & 1) * kPassCols; };
+    auto pass_col = [&](int e) { return sub * 64 + (e >> 1) * (EW / 4) * 64 + (e & 1) * kPassCols; };
     auto pass_width = [&](int e) {
       const int c = pass_col(e);
       int w = block_n - c;
@@ -275,7 +275,7 @@ __device__ __forceinline__ void fused_epilogue(const bf16* __restrict__ aux, bf1
       }
       __syncwarp();
     };
-    if (EPI == B200AT_EPI_GELU_GRAD) load_aux(0);
+    if (EPI == B200AT_EPI_GELU_GRAD || EPI == B200AT_EPI_RESIDUAL) load_aux(0);
     mbar_wait(&tfull[acc], acc_phase);
     tc_fence_after();
     for (int e = 0; pass_col(e) < block_n; ++e) {
@@ -285,7 +285,7 @@ __device__ __forceinline__ void fused_epilogue(const bf16* __restrict__ aux, bf1
       tmem_ld16(t_row + (uint32_t)c, v);
       if (w > 16) tmem_ld16(t_row + (uint32_t)(c + 16), v + 16);
       uint4 zrow[4];
-      if (EPI == B200AT_EPI_GELU_GRAD) {
+      if (EPI == B200AT_EPI_GELU_GRAD || EPI == B200AT_EPI_RESIDUAL) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) sts128(line_a + 512u * k, zpre[k]);
         __syncwarp();
@@ -305,6 +305,23 @@ __device__ __forceinline__ void fused_epilogue(const bf16* __restrict__ aux, bf1
           for (int i = 0; i < 4; ++i) {
             const float2 g = make_float2(__uint_as_float(v[8 * j + 2 * i]), __uint_as_float(v[8 * j + 2 * i + 1]));
             ow[i] = f2_to_bf2(b200at_fmul2(g, b200at_gelu_grad2(bf2_to_f2(zw[i]))));
+          }
+          o[j] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+        }
+        store_tile(c_out, c, w, o);
+      } else if (EPI == B200AT_EPI_RESIDUAL) {            // (acc + bias) + residual, the order of the generic epilogue
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t ba = bias_a + (uint32_t)((ncol0 + c + 8 * j) * 4);
+          const uint4 b0 = lds128(ba), b1 = lds128(ba + 16);
+          const uint32_t bw[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+          const uint32_t zw[4] = {zrow[j].x, zrow[j].y, zrow[j].z, zrow[j].w};
+          uint32_t ow[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float2 t = b200at_fadd2(make_float2(__uint_as_float(v[8 * j + 2 * i]), __uint_as_float(v[8 * j + 2 * i + 1])),
+                                          make_float2(__uint_as_float(bw[2 * i]), __uint_as_float(bw[2 * i + 1])));
+            ow[i] = f2_to_bf2(b200at_fadd2(t, bf2_to_f2(zw[i])));
           }
           o[j] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
         }
@@ -365,7 +382,7 @@ __global__ void __launch_bounds__(32 * (kEpilogueWarp0 + EW), 1) gemm_kernel(con
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
   uint64_t* wfull = bars + 2 * kStages + 5;   // CONV: the resident weights have landed
   uint8_t* staging = smem + kStages * stage_bytes + wres_bytes + 256;   // [EW][kStageTileBytes]  (EW == 16: [EW][kFusedTileBytes], then bias)
-  float* sbias = reinterpret_cast<float*>(staging + EW * kFusedTileBytes);   // EW == 16 only: [tiles_n * block_n]
+  float* sbias = reinterpret_cast<float*>(staging + EW * kFusedTileBytes);   // fused epilogues only: [tiles_n * block_n]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_k = (p.K + kBlockK - 1) / kBlockK;
@@ -388,7 +405,8 @@ __global__ void __launch_bounds__(32 * (kEpilogueWarp0 + EW), 1) gemm_kernel(con
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  if (EW == 16 && EPI == B200AT_EPI_BIAS_GELU) {
+  constexpr bool kFused = EW == 16 || (EPI == B200AT_EPI_RESIDUAL && !CONV);   // epilogues that run fused_epilogue
+  if (kFused && (EPI == B200AT_EPI_BIAS_GELU || EPI == B200AT_EPI_RESIDUAL)) {
     const int padded = p.tiles_n * p.block_n;
     for (int i = threadIdx.x; i < padded; i += blockDim.x) sbias[i] = (p.bias != nullptr && i < p.N) ? p.bias[i] : 0.0f;
   }
@@ -460,8 +478,8 @@ __global__ void __launch_bounds__(32 * (kEpilogueWarp0 + EW), 1) gemm_kernel(con
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp >= kEpilogueWarp0 && EW == 16) {
-    fused_epilogue<EPI>(p.aux, p.c, p.c2, p.M, p.N, p.block_n, p.tiles_n, num_tiles, tmem_base, tfull, tempty,
+  } else if (warp >= kEpilogueWarp0 && kFused) {
+    fused_epilogue<EPI, EW>(p.aux, p.c, p.c2, p.M, p.N, p.block_n, p.tiles_n, num_tiles, tmem_base, tfull, tempty,
                         smem_u32(staging) + (uint32_t)((warp - kEpilogueWarp0) * kFusedTileBytes), smem_u32(sbias), warp, lane,
                         p.colsum != nullptr);
   } else if (warp >= kEpilogueWarp0) {
@@ -624,10 +642,11 @@ template <int EPI>
 int launch(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, int grid, cudaStream_t s) {
   constexpr int EW = (EPI == B200AT_EPI_BIAS_GELU || EPI == B200AT_EPI_GELU_GRAD) ? 16 : 8;
   constexpr int kStages = EW > 8 ? 3 : 4;
+  constexpr bool kFused = EW == 16 || EPI == B200AT_EPI_RESIDUAL;
   const size_t smem = 1024 + (size_t)kStages * (kBlockM * kBlockK * 2 + (size_t)p.block_n * kBlockK * 2) + 256 +
-                      (EW == 16 ? (size_t)EW * kFusedTileBytes + sizeof(float) * (size_t)p.tiles_n * p.block_n
-                                : (size_t)EW * kStageTileBytes);
-  if (EW == 16 && (int64_t)p.tiles_n * p.block_n > kMaxBiasCols) return (int)cudaErrorInvalidValue;
+                      (kFused ? (size_t)EW * kFusedTileBytes + sizeof(float) * (size_t)p.tiles_n * p.block_n
+                              : (size_t)EW * kStageTileBytes);
+  if (kFused && (int64_t)p.tiles_n * p.block_n > kMaxBiasCols) return (int)cudaErrorInvalidValue;
   static b200at::SmemConfig configured;
   cudaError_t e = b200at::ensure_dynamic_smem(gemm_kernel<EPI, EW>, 227 * 1024, configured);
   if (e != cudaSuccess) return (int)e;
