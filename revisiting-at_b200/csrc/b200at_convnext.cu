@@ -857,7 +857,124 @@ constexpr int kDwTile = 14;
 constexpr int kDwIn = kDwTile + 6;   // 20
 
 // weight gradient: dw[tap][c] += sum_{pixels} dy[p][c] * x[p + tap][c];  db[c] += sum dy
-__global__ void __launch_bounds__(256) dwconv7_wgrad_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy,
+//
+// Round-1 form: one CTA per (image, 14 x 14 tile, 32 channels), the 16 column-threads' partial sums of a tap column reduced
+// through shared memory for every tile -- 15 barriers per tile on 8 warps, 28 % of the FFMA2 rate (210 us at 56 x 56 x 96).
+// This form is persistent: a CTA owns a channel group and walks every `splits`-th (image, tile); thread (channel pair,
+// output column) keeps all 49 tap sums of its column in registers ACROSS tiles (98 registers; 7 independent accumulators per
+// loaded value keep the FMA pipe busy from two warps per scheduler), the x and dy tiles arrive by cp.async one tile
+// ahead (zero fill = padding and ragged edges), and the cross-column reduction happens once per CTA.  One barrier per tile.
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+
+constexpr int kWgXBytes = kDwIn * kDwIn * kDwCh * 2;          // 25600: [20][20][32 ch] bf16
+constexpr int kWgGBytes = kDwTile * kDwTile * kDwCh * 2;      // 12544: [14][14][32 ch] bf16
+constexpr int kWgBuf = kWgXBytes + kWgGBytes;
+
+__global__ void __launch_bounds__(256, 1) dwconv7_wgrad_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy,
+                                                               float* __restrict__ dw, float* __restrict__ db, int H,
+                                                               int W, int C, int tiles_w, int tiles_h, int spatial,
+                                                               int splits) {
+  extern __shared__ __align__(16) uint8_t wg_smem[];            // [2][kWgBuf], then red7 [7][16][16] float2
+  float2 (*red7)[16][kDwCh / 2] = reinterpret_cast<float2 (*)[16][kDwCh / 2]>(wg_smem + 2 * kWgBuf);
+  const uint32_t smem_a = b200at::smem_u32(wg_smem);
+  const int cp = threadIdx.x & 15, t = threadIdx.x >> 4;
+  const int cgroups = C / kDwCh;
+  const int cg = blockIdx.x % cgroups, split = blockIdx.x / cgroups;
+  const int c0 = cg * kDwCh;
+  auto request = [&](int sp, int buf) {                          // both tiles of item `sp` into buffer `buf`
+    int bid = sp;
+    const int tw = bid % tiles_w; bid /= tiles_w;
+    const int th = bid % tiles_h; bid /= tiles_h;
+    const int64_t img = (int64_t)bid * H * W * C;
+    const int h0 = th * kDwTile, w0 = tw * kDwTile;
+    const uint32_t xa = smem_a + (uint32_t)(buf * kWgBuf), ga = xa + kWgXBytes;
+    for (int q = threadIdx.x; q < kDwIn * kDwIn * 4; q += 256) {
+      const int pix = q >> 2, piece = q & 3;
+      const int r = pix / kDwIn, c = pix - r * kDwIn;
+      const int hh = h0 + r - 3, ww = w0 + c - 3;
+      const bool ok = hh >= 0 && hh < H && ww >= 0 && ww < W;
+      cp_async16(xa + (uint32_t)(q * 16), ok ? (const void*)(x + img + ((int64_t)hh * W + ww) * C + c0 + piece * 8) : (const void*)x, ok);
+    }
+    for (int q = threadIdx.x; q < kDwTile * kDwTile * 4; q += 256) {
+      const int pix = q >> 2, piece = q & 3;
+      const int r = pix / kDwTile, c = pix - r * kDwTile;
+      const int hh = h0 + r, ww = w0 + c;
+      const bool ok = hh < H && ww < W;
+      cp_async16(ga + (uint32_t)(q * 16), ok ? (const void*)(dy + img + ((int64_t)hh * W + ww) * C + c0 + piece * 8) : (const void*)dy, ok);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  float2 acc[7][7];                                              // [tap column j][tap row i]
+#pragma unroll
+  for (int j = 0; j < 7; ++j) {
+#pragma unroll
+    for (int i = 0; i < 7; ++i) acc[j][i] = make_float2(0.f, 0.f);
+  }
+  float2 gsum = make_float2(0.f, 0.f);
+  if (split < spatial) request(split, 0);
+  int k = 0;
+  for (int sp = split; sp < spatial; sp += splits, ++k) {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();                                             // tile k has landed; tile k - 1 has been consumed
+    if (sp + splits < spatial) request(sp + splits, (k + 1) & 1);
+    if (t < kDwTile) {
+      const bf162* xt = reinterpret_cast<const bf162*>(wg_smem + (k & 1) * kWgBuf);
+      const bf162* gt = reinterpret_cast<const bf162*>(wg_smem + (k & 1) * kWgBuf + kWgXBytes);
+      float2 g[kDwTile];
+#pragma unroll
+      for (int r = 0; r < kDwTile; ++r) {
+        g[r] = __bfloat1622float2(gt[(r * kDwTile + t) * (kDwCh / 2) + cp]);
+        gsum.x += g[r].x; gsum.y += g[r].y;
+      }
+#pragma unroll
+      for (int j = 0; j < 7; ++j) {
+#pragma unroll
+        for (int r = 0; r < kDwIn; ++r) {
+          const float2 v = __bfloat1622float2(xt[(r * kDwIn + t + j) * (kDwCh / 2) + cp]);
+#pragma unroll
+          for (int i = 0; i < 7; ++i) {
+            const int o = r - i;
+            if (o >= 0 && o < kDwTile) acc[j][i] = ffma2(v, g[o], acc[j][i]);
+          }
+        }
+      }
+    }
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  // once per CTA: the 16 column-threads' sums of a tap column through shared memory, 7 x 16 threads add them up
+#pragma unroll
+  for (int j = 0; j < 7; ++j) {
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 7; ++i) red7[i][t][cp] = acc[j][i];
+    __syncthreads();
+    if (threadIdx.x < 7 * 16) {
+      const int i = threadIdx.x >> 4, c2 = threadIdx.x & 15;
+      float2 s = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int q = 0; q < 16; ++q) { s.x += red7[i][q][c2].x; s.y += red7[i][q][c2].y; }
+      atomicAdd(dw + (i * 7 + j) * C + c0 + c2 * 2, s.x);
+      atomicAdd(dw + (i * 7 + j) * C + c0 + c2 * 2 + 1, s.y);
+    }
+  }
+  __syncthreads();
+  red7[0][t][cp] = gsum;
+  __syncthreads();
+  if (t == 0) {
+    float2 s = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int q = 0; q < 16; ++q) { s.x += red7[0][q][cp].x; s.y += red7[0][q][cp].y; }
+    atomicAdd(db + c0 + cp * 2, s.x);
+    atomicAdd(db + c0 + cp * 2 + 1, s.y);
+  }
+}
+
+// The round-1 form (one CTA per tile, cross-column reduction per tile): kept for the 7 x 7 maps of the last stage, where a
+// 14 x 14 tile is three quarters padding and the persistent form's 8 warps per SM lose to 32 (61 vs 88 us at 7 x 7 x 768).
+__global__ void __launch_bounds__(256) dwconv7_wgrad_tile_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy,
                                                             float* __restrict__ dw, float* __restrict__ db, int H,
                                                             int W, int C, int tiles_w, int tiles_h) {
   __shared__ __align__(16) bf162 tile[kDwIn][kDwIn][kDwCh / 2];
@@ -1352,9 +1469,26 @@ int b200at_dwconv7_wgrad(const void* x, const void* dy, float* dw, float* db, in
   if (B <= 0) return 0;
   if (C % kDwCh) return (int)cudaErrorInvalidValue;
   const int tw = (int)((W + kDwTile - 1) / kDwTile), th = (int)((H + kDwTile - 1) / kDwTile);
-  const int64_t grid = B * th * tw * (C / kDwCh);
-  if (grid > 0x7fffffff) return (int)cudaErrorInvalidValue;
-  dwconv7_wgrad_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)dy, dw, db, (int)H, (int)W, (int)C, tw, th);
+  const int64_t spatial = B * th * tw;
+  if (spatial > 0x7fffffff) return (int)cudaErrorInvalidValue;
+  const int cgroups = (int)(C / kDwCh);
+  if (H <= 8 && W <= 8) {                                 // small maps: one CTA per (image, channel group)
+    const int64_t grid = spatial * cgroups;
+    if (grid > 0x7fffffff) return (int)cudaErrorInvalidValue;
+    dwconv7_wgrad_tile_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)dy, dw, db, (int)H, (int)W, (int)C, tw, th);
+    return (int)cudaGetLastError();
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int64_t splits = sms / cgroups;                         // one persistent CTA per SM (98 accumulator registers per thread)
+  if (splits < 1) splits = 1;
+  if (splits > spatial) splits = spatial;
+  const size_t smem = 2 * (size_t)kWgBuf + sizeof(float2) * 7 * 16 * (kDwCh / 2);
+  static b200at::SmemConfig configured;
+  cudaError_t e = b200at::ensure_dynamic_smem(dwconv7_wgrad_kernel, (int)smem, configured);
+  if (e != cudaSuccess) return (int)e;
+  dwconv7_wgrad_kernel<<<(unsigned)(splits * cgroups), 256, smem, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)dy, dw, db, (int)H, (int)W, (int)C, tw, th, (int)spatial, (int)splits);
   return (int)cudaGetLastError();
 }
 
