@@ -1,5 +1,7 @@
 """CPU: the product's host-side state machine (`attack.run_apgd`) driven through the host-compiled
 kernel bodies reproduces the reference's golden trajectories bit-exactly (l-inf path)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -144,3 +146,23 @@ def test_conv3x3s2_weight_layout_is_the_implicit_gemm_of_the_convolution():
     ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.to(torch.bfloat16).float(), None, stride=2, padding=1)
     assert torch.allclose(got.view(B, H // 2, W // 2, Co), ref.permute(0, 2, 3, 1), atol=1e-4, rtol=1e-4)
     assert float(wk.view(Co, 9, 64)[:, :, Ci:].abs().max()) == 0.0                # the padded channels multiply zero-filled input
+
+
+def test_gelu_polynomial_constants_in_the_kernel_header():
+    """csrc/b200at_gelu.cuh: Phi(-|v|) = 2^P7(-|v|) with the coefficients B200AT_GELU_P0..P7 (profiles/fit_gelu_poly.py).
+    The header's constants, evaluated the way the kernel does (fp32 Horner with fused multiply-adds, input clamped at
+    -6.5), must give GELU (models/convnext.py:43 nn.GELU(), exact erf form) to 2e-7 absolute over [-12, 12]."""
+    import re
+    import numpy as np
+    from math import erf, sqrt
+    src = open(os.path.join(os.path.dirname(__file__), '..', 'revisiting-at_b200', 'csrc', 'b200at_gelu.cuh')).read()
+    d = [float(re.search(r'#define B200AT_GELU_P%d \(([-+0-9.e]+)f\)' % k, src).group(1)) for k in range(8)]
+    v = np.linspace(-12, 12, 96001)
+    nax = -np.abs(v)
+    t = np.maximum(nax, -6.5).astype(np.float32)
+    acc = np.full(t.shape, np.float32(d[7]), dtype=np.float32)
+    for k in range(6, -1, -1):
+        acc = (acc.astype(np.float64) * t.astype(np.float64) + np.float64(np.float32(d[k]))).astype(np.float32)
+    got = nax * np.exp2(acc.astype(np.float64)) + np.maximum(v, 0)
+    ref = np.array([0.5 * x * (1 + erf(x / sqrt(2))) for x in v])
+    assert float(np.abs(got - ref).max()) < 2e-7
